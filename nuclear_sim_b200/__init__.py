@@ -1,0 +1,7 @@
+"""Import shim: the package directory is named ``nuclear-sim_b200`` (not a valid Python
+identifier), so this module points its ``__path__`` there and re-exports the public API."""
+import os as _os
+
+__path__ = [_os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "nuclear-sim_b200")]
+
+from ._api import *  # noqa: F401,F403,E402

@@ -1,0 +1,47 @@
+// TEST INFRASTRUCTURE — not part of the product.
+//
+// Host build (g++, -ffp-contract=off) of the scalar plant step.  It compiles the same
+// single-source physics headers the CUDA kernel compiles (nuclear-sim_b200/csrc/plant/*.h,
+// each function citing the reference file:line it restates), so its *independence* comes from
+// being pinned against the live Python reference: tests/test_oracle_vs_reference_golden.py
+// checks this library against fixtures produced by stepping /root/reference itself
+// (oracle/make_golden.py).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline
+// leg may load this library; the product (libnps_b200.so) never links or calls it.
+//
+// Layout here is array-of-structs: state[p * n_state + f]  (one contiguous PlantState per plant).
+#include <cstring>
+#include <cstdint>
+#include "plant_step.h"
+
+using namespace nps;
+
+extern "C" {
+
+int nps_oracle_n_state(void) { return (int)(sizeof(PlantState) / sizeof(double)); }
+int nps_oracle_n_params(void) { return (int)(sizeof(PlantParams) / sizeof(double)); }
+
+// noise: [n_plants][k_steps][5] = z_heat, z_ph, u0, u1, u2 ; action/magnitude: [n_plants][k_steps]
+int nps_oracle_step(double* state, const double* params, const int8_t* action, const double* magnitude,
+                    const double* noise, int64_t n_plants, int k_steps) {
+    PlantParams p;
+    std::memcpy(&p, params, sizeof(p));
+    const int ns = nps_oracle_n_state();
+    for (int64_t i = 0; i < n_plants; ++i) {
+        PlantState st;
+        std::memcpy(&st, state + i * ns, sizeof(st));
+        for (int k = 0; k < k_steps; ++k) {
+            StepInput in;
+            in.action = action ? (int)action[i * k_steps + k] : (int)ACT_NO_ACTION;
+            in.magnitude = magnitude ? magnitude[i * k_steps + k] : 1.0;
+            const double* z = noise ? noise + (i * k_steps + k) * 5 : nullptr;
+            in.z_heat = z ? z[0] : 0.0;
+            in.z_ph = z ? z[1] : 0.0;
+            in.u_ph[0] = z ? z[2] : 1.0; in.u_ph[1] = z ? z[3] : 1.0; in.u_ph[2] = z ? z[4] : 1.0;
+            plant_step(st, p, in);
+        }
+        std::memcpy(state + i * ns, &st, sizeof(st));
+    }
+    return 0;
+}
+
+}  // extern "C"
