@@ -66,9 +66,147 @@ struct SimState {
     double last_pump_reliability_factor;
 };
 
+// ---- water chemistry -----------------------------------------------------------------------
+// WaterChemistry members: systems/secondary/water_chemistry.py:219-272 (+ pending effects :659-682)
+struct WaterChemState {
+    double ph;
+    double iron_concentration;
+    double copper_concentration;
+    double silica_concentration;
+    double dissolved_oxygen;
+    double hardness;
+    double total_dissolved_solids;
+    double chloride;
+    double alkalinity;
+    double chlorine_residual;
+    double antiscalant_concentration;
+    double corrosion_inhibitor_level;
+    double biocide_concentration;
+    double water_aggressiveness;
+    double particle_content;
+    double scaling_tendency;
+    double corrosion_tendency;
+    double concentration_factor;
+    double treatment_efficiency;
+    double blowdown_rate;
+    double operating_hours;
+    double last_treatment_time;
+    double chemistry_stability_factor;
+    double pending_effects;
+    double pend_ph_setpoint;
+    double pend_ammonia_dose_rate;
+    double pend_morpholine_dose_rate;
+};
+
+// ---- lubrication (shared base) ----------------------------------------------------------------
+// BaseLubricationSystem members: systems/secondary/lubrication_base.py:131-175.
+// component_wear / component_perf are indexed in the owning system's component order
+// (6 used by the feedwater pump system, 5 by the turbine bearing system).
+struct LubCore {
+    double oil_level;
+    double oil_temperature;
+    double oil_pressure;
+    double oil_contamination_level;
+    double oil_moisture_content;
+    double oil_acidity_number;
+    double oil_viscosity_change;
+    double oil_operating_hours;
+    double antioxidant_level;
+    double anti_wear_additive_level;
+    double corrosion_inhibitor_level;
+    double component_wear[6];
+    double component_perf[6];
+    double lubrication_effectiveness;
+    double system_health_factor;
+    double operating_hours;
+};
+
+// ---- feedwater -------------------------------------------------------------------------------
+// FeedwaterPumpState + FeedwaterPump members (feedwater/pump_system.py:62-160,
+// primary/coolant/pump_models.py:29-47) and the pump's FeedwaterPumpLubricationSystem
+// (feedwater/pump_lubrication.py:202-215).  status: 0 RUNNING 1 STOPPED 2 STARTING 3 STOPPING 4 TRIPPED
+struct FWPumpState {
+    double speed_percent;
+    double flow_rate;
+    double status;
+    double speed_setpoint;
+    double power_consumption;
+    double available;
+    double trip_active;
+    double trip_reason;
+    double suction_pressure;
+    double discharge_pressure;
+    double npsh_available;
+    double motor_temperature;
+    double motor_current;
+    double motor_voltage;
+    double vibration_level;
+    double differential_pressure;
+    double cavitation_intensity;
+    double cavitation_damage;
+    double cavitation_time;
+    double cavitation_noise_level;
+    double flow_demand;
+    double ic_applied;
+    LubCore lub;
+    double pump_load_factor;
+    double cavitation_lubrication_effect;
+    double seal_leakage_rate;
+    double pump_efficiency_degradation;
+    double pump_flow_degradation;
+    double pump_head_degradation;
+    double npsh_margin_degradation;
+    double vibration_increase;
+};
+
+// EnhancedFeedwaterPhysics + ThreeElementControl + PerformanceDiagnostics + FeedwaterProtectionSystem
+// (feedwater/physics.py:148-183, level_control.py:131-153, performance_monitoring.py:85-112,402-421,
+//  protection_system.py:41-57,152-184)
+struct FeedwaterState {
+    FWPumpState pump[4];
+    double total_flow_rate;
+    double total_power_consumption;
+    double system_efficiency;
+    double system_availability;
+    double performance_factor;
+    double maintenance_factor;
+    double operating_hours;
+    double load_demand;
+    double n_running_prev;
+    double pump_system_available;
+    double total_flow_demand;
+    double lc_level_errors[3];
+    double lc_level_integral_errors[3];
+    double lc_previous_level_errors[3];
+    double lc_quality_integral_error;
+    double lc_control_performance;
+    double cav_current_intensity;
+    double cav_accumulated_damage;
+    double cav_n_events;
+    double cav_time_in_cavitation;
+    double cav_acoustic_signature;
+    double cav_noise_increase;
+    double cav_induced_vibration;
+    double cav_risk_score;
+    double cav_predicted_damage_rate;
+    double diag_health_score;
+    double prot_npsh_low_alarm_active;
+    double prot_npsh_low_low_trip_active;
+    double prot_npsh_critical_trip_active;
+    double prot_npsh_low_low_timer;
+    double prot_timer_low_flow;
+    double prot_timer_high_flow;
+    double prot_timer_bearing_temp;
+    double prot_timer_motor_temp;
+    double prot_timer_vibration;
+    double prot_system_trip_active;
+};
+
 struct PlantState {
     PrimaryState pri;
     SimState sim;
+    WaterChemState wc_main;
+    FeedwaterState fw;
 };
 
 // ---- batch-uniform parameters ------------------------------------------------------------
@@ -80,6 +218,21 @@ struct PlantParams {
     double noise_std_percent;
     double noise_filter_time_constant;
     double enable_secondary;
+    // feedwater (feedwater/config.py; feedwater/physics.py:101-129)
+    double fw_num_sg;
+    double fw_design_total_flow;
+    double fw_design_sg_level;
+    double fw_design_pressure;
+    double fw_design_feedwater_temperature;
+    double fw_auto_level_control;
+    double fw_lc_level_control_weight;
+    double fw_lc_feedwater_flow_weight;
+    double fw_lc_quality_gain;
+    double fwp_rated_flow;
+    double fwp_rated_power;
+    double fw_prot_low_suction_pressure_trip;
+    double fw_prot_high_discharge_pressure_trip;
+    double fw_prot_low_flow_trip;
 };
 
 }  // namespace nps

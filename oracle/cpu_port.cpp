@@ -45,3 +45,19 @@ int nps_oracle_step(double* state, const double* params, const int8_t* action, c
 }
 
 }  // extern "C"
+
+// ---- per-subsystem entry points used by tests/ to localise a mismatch --------------------------
+#include "feedwater.h"
+extern "C" int nps_oracle_feedwater(double* state, const double* params, const double* sg_levels,
+                                    const double* sg_steam_flows, const double* sg_qualities, double manual_flow,
+                                    double fw_temp, double suction, double discharge, double dt, double* out5) {
+    PlantParams p; std::memcpy(&p, params, sizeof(p));
+    PlantState st; std::memcpy(&st, state, sizeof(st));
+    FeedwaterResult r;
+    feedwater_update(st.fw, st.wc_main, p, sg_levels, sg_steam_flows, sg_qualities, manual_flow, fw_temp, suction,
+                     discharge, dt, r);
+    std::memcpy(state, &st, sizeof(st));
+    out5[0] = r.total_flow_rate; out5[1] = r.total_power_consumption; out5[2] = r.num_running_pumps;
+    out5[3] = r.system_availability; out5[4] = r.sg_flow[0];
+    return 0;
+}

@@ -1,11 +1,153 @@
 """TEST INFRASTRUCTURE — maps the reference's secondary-side object graph onto PlantState /
-PlantParams field names (filled in subsystem by subsystem as the restatement grows)."""
+PlantParams field names (nuclear_sim_b200/_layout.py).  One function per subsystem; each reads
+live attributes of the reference objects, nothing is computed here."""
+
+PUMP_STATUS = {"running": 0.0, "stopped": 1.0, "starting": 2.0, "stopping": 3.0, "tripped": 4.0}
+
+FW_LUB_COMPONENTS = ["impeller", "motor_bearings", "pump_bearings", "thrust_bearing", "mechanical_seals",
+                     "coupling_system"]
+
+PUMP_TRIP_CODES = {
+    "": 0, "Low Flow": 1, "NPSH Violation": 2, "Low Suction Pressure": 3, "High Discharge Pressure": 4,
+    "Steam Generator High Level": 5, "Severe Cavitation": 6, "Cavitation Damage Limit": 7,
+    "Critical NPSH Violation": 8, "Lubrication: Very Low Oil Level": 9, "Lubrication: Low Oil Level": 10,
+    "Lubrication: Oil System Overfill": 11, "Lubrication: Impeller Excessive Wear": 12,
+    "Lubrication: Motor Bearings Excessive Wear": 13, "Lubrication: Pump Bearings Excessive Wear": 14,
+    "Lubrication: Thrust Bearing Excessive Wear": 15, "Lubrication: Mechanical Seals Excessive Wear": 16,
+    "Lubrication: Coupling System Excessive Wear": 17, "Lubrication: Excessive Seal Leakage": 18,
+    "Lubrication: Combined Wear Limit": 19, "Lubrication: Performance Degradation": 20,
+}
+
+
+def water_chem(w, pre, d):
+    for name in ("ph", "iron_concentration", "copper_concentration", "silica_concentration", "dissolved_oxygen",
+                 "hardness", "total_dissolved_solids", "chloride", "alkalinity", "chlorine_residual",
+                 "antiscalant_concentration", "corrosion_inhibitor_level", "biocide_concentration",
+                 "water_aggressiveness", "particle_content", "scaling_tendency", "corrosion_tendency",
+                 "concentration_factor", "treatment_efficiency", "blowdown_rate", "operating_hours",
+                 "last_treatment_time", "chemistry_stability_factor"):
+        d[pre + name] = float(getattr(w, name))
+    pend = getattr(w, "_pending_chemistry_effects", None) or {}
+    phc = pend.get("ph_control")
+    d[pre + "pending_effects"] = 1.0 if phc else 0.0
+    d[pre + "pend_ph_setpoint"] = float(phc.get("ph_setpoint", 0.0)) if phc else 0.0
+    d[pre + "pend_ammonia_dose_rate"] = float(phc.get("ammonia_dose_rate", 0.0)) if phc else 0.0
+    d[pre + "pend_morpholine_dose_rate"] = float(phc.get("morpholine_dose_rate", 0.0)) if phc else 0.0
+
+
+def lub_core(L, comps, pre, d):
+    for name in ("oil_level", "oil_temperature", "oil_pressure", "oil_contamination_level", "oil_moisture_content",
+                 "oil_acidity_number", "oil_viscosity_change", "oil_operating_hours", "antioxidant_level",
+                 "anti_wear_additive_level", "corrosion_inhibitor_level", "lubrication_effectiveness",
+                 "system_health_factor", "operating_hours"):
+        d[pre + name] = float(getattr(L, name))
+    for i in range(6):
+        if i < len(comps):
+            d[f"{pre}component_wear[{i}]"] = float(L.component_wear[comps[i]])
+            d[f"{pre}component_perf[{i}]"] = float(L.component_performance_factors[comps[i]])
+        else:
+            d[f"{pre}component_wear[{i}]"] = 0.0
+            d[f"{pre}component_perf[{i}]"] = 0.0
+
+
+def feedwater(fw, d):
+    P = "fw."
+    pumps = list(fw.pump_system.pumps.values())
+    assert len(pumps) == 4
+    for k, pump in enumerate(pumps):
+        pre = f"{P}pump[{k}]."
+        st = pump.state
+        for name in ("speed_percent", "flow_rate", "speed_setpoint", "power_consumption", "suction_pressure",
+                     "discharge_pressure", "npsh_available", "motor_temperature", "motor_current", "motor_voltage",
+                     "vibration_level", "differential_pressure", "cavitation_intensity", "cavitation_damage",
+                     "cavitation_time", "cavitation_noise_level"):
+            d[pre + name] = float(getattr(st, name))
+        d[pre + "status"] = PUMP_STATUS[st.status.value]
+        d[pre + "available"] = float(st.available)
+        d[pre + "trip_active"] = float(st.trip_active)
+        reason = st.trip_reason
+        if reason.startswith("NPSH Violation"):
+            reason = "NPSH Violation"
+        d[pre + "trip_reason"] = float(PUMP_TRIP_CODES[reason])
+        d[pre + "flow_demand"] = float(pump.flow_demand)
+        d[pre + "ic_applied"] = float(hasattr(pump, "_initial_conditions_applied"))
+        L = pump.lubrication_system
+        lub_core(L, FW_LUB_COMPONENTS, pre + "lub.", d)
+        for name in ("pump_load_factor", "cavitation_lubrication_effect", "seal_leakage_rate",
+                     "pump_efficiency_degradation", "pump_flow_degradation", "pump_head_degradation",
+                     "npsh_margin_degradation", "vibration_increase"):
+            d[pre + name] = float(getattr(L, name))
+    for name in ("total_flow_rate", "total_power_consumption", "system_efficiency", "performance_factor",
+                 "maintenance_factor", "operating_hours", "load_demand"):
+        d[P + name] = float(getattr(fw, name))
+    d[P + "system_availability"] = float(fw.system_availability)
+    d[P + "n_running_prev"] = float(len(fw.pump_system.running_pumps))
+    d[P + "pump_system_available"] = float(fw.pump_system.system_available)
+    lc = fw.level_control
+    hist = lc.flow_demand_history
+    d[P + "total_flow_demand"] = float(hist[-1]) if hist else 0.0
+    for i in range(3):
+        d[f"{P}lc_level_errors[{i}]"] = float(lc.level_errors[i])
+        d[f"{P}lc_level_integral_errors[{i}]"] = float(lc.level_integral_errors[i])
+        d[f"{P}lc_previous_level_errors[{i}]"] = float(lc.previous_level_errors[i])
+    d[P + "lc_quality_integral_error"] = float(lc.quality_compensator.quality_integral_error)
+    d[P + "lc_control_performance"] = float(lc.control_performance)
+    cm = fw.diagnostics.cavitation_model
+    d[P + "cav_current_intensity"] = float(cm.current_intensity)
+    d[P + "cav_accumulated_damage"] = float(cm.accumulated_damage)
+    d[P + "cav_n_events"] = float(len(cm.cavitation_events))
+    d[P + "cav_time_in_cavitation"] = float(cm.time_in_cavitation)
+    d[P + "cav_acoustic_signature"] = float(cm.acoustic_signature)
+    d[P + "cav_noise_increase"] = float(cm.cavitation_noise_increase)
+    d[P + "cav_induced_vibration"] = float(cm.cavitation_induced_vibration)
+    d[P + "cav_risk_score"] = float(cm.cavitation_risk_score)
+    d[P + "cav_predicted_damage_rate"] = float(cm.predicted_damage_rate)
+    d[P + "diag_health_score"] = float(fw.diagnostics.overall_health_score)
+    pr = fw.protection_system
+    npr = pr.npsh_protection
+    d[P + "prot_npsh_low_alarm_active"] = float(npr.npsh_low_alarm_active)
+    d[P + "prot_npsh_low_low_trip_active"] = float(npr.npsh_low_low_trip_active)
+    d[P + "prot_npsh_critical_trip_active"] = float(npr.npsh_critical_trip_active)
+    d[P + "prot_npsh_low_low_timer"] = float(npr.npsh_low_low_timer)
+    d[P + "prot_timer_low_flow"] = float(pr.trip_timers["low_flow"])
+    d[P + "prot_timer_high_flow"] = float(pr.trip_timers["high_flow"])
+    d[P + "prot_timer_bearing_temp"] = float(pr.trip_timers["bearing_temp"])
+    d[P + "prot_timer_motor_temp"] = float(pr.trip_timers["motor_temp"])
+    d[P + "prot_timer_vibration"] = float(pr.trip_timers["vibration"])
+    d[P + "prot_system_trip_active"] = float(pr.system_trip_active)
+
+
+def feedwater_params(fw, d):
+    cfg = fw.config
+    d["fw_num_sg"] = float(cfg.num_steam_generators)
+    d["fw_design_total_flow"] = float(cfg.design_total_flow)
+    d["fw_design_sg_level"] = float(cfg.design_sg_level)
+    d["fw_design_pressure"] = float(cfg.design_pressure)
+    d["fw_design_feedwater_temperature"] = float(cfg.design_feedwater_temperature)
+    d["fw_auto_level_control"] = float(cfg.auto_level_control)
+    cc = fw.level_control.config
+    d["fw_lc_level_control_weight"] = float(getattr(cc, "level_control_weight", 0.4))
+    d["fw_lc_feedwater_flow_weight"] = float(getattr(cc, "feedwater_flow_weight", 0.1))
+    d["fw_lc_quality_gain"] = float(fw.level_control.quality_compensator.quality_control_gain)
+    pump = next(iter(fw.pump_system.pumps.values()))
+    d["fwp_rated_flow"] = float(pump.config.rated_flow)
+    d["fwp_rated_power"] = float(pump.config.rated_power)
+    pc = fw.protection_system.config
+    d["fw_prot_low_suction_pressure_trip"] = float(pc.low_suction_pressure_trip)
+    d["fw_prot_high_discharge_pressure_trip"] = float(pc.high_discharge_pressure_trip)
+    d["fw_prot_low_flow_trip"] = float(pc.low_flow_trip)
 
 
 def extract(sim, d):
     if not (sim.enable_secondary and sim.secondary_physics is not None):
         return
+    sec = sim.secondary_physics
+    water_chem(sec.water_chemistry, "wc_main.", d)
+    feedwater(sec.feedwater_system, d)
 
 
 def extract_params(sim, d):
-    return
+    if not (sim.enable_secondary and sim.secondary_physics is not None):
+        return
+    sec = sim.secondary_physics
+    feedwater_params(sec.feedwater_system, d)
