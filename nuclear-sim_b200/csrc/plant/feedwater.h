@@ -73,31 +73,31 @@ NPS_HD double fwp_component_wear_rate(const FWPumpState& u, int comp, double loa
         double cav_factor = 1.0 + cav * 3.0;
         double temp_factor = py_max(1.0, (temperature - 80.0) / 40.0);
         double brg_cpl = 1.0 + (max_brg / 100.0) * 0.3;
-        wear_rate = (c.base_wear_rate * pow(load_factor, c.load_wear_exponent) * pow(speed_factor, c.speed_wear_exponent) *
+        wear_rate = (c.base_wear_rate * py_pow(load_factor, c.load_wear_exponent) * py_pow(speed_factor, c.speed_wear_exponent) *
                      cav_factor * temp_factor * brg_cpl);
     } else if (comp == FWL_MOTOR_BRG) {
         double temp_factor = py_max(1.0, (temperature - 60.0) / 25.0);
         double imp_cpl = 1.0 + (impeller_wear / 100.0) * 0.2;
-        wear_rate = (c.base_wear_rate * pow(electrical_load_factor, c.load_wear_exponent) *
-                     pow(speed_factor, c.speed_wear_exponent) * temp_factor * imp_cpl);
+        wear_rate = (c.base_wear_rate * py_pow(electrical_load_factor, c.load_wear_exponent) *
+                     py_pow(speed_factor, c.speed_wear_exponent) * temp_factor * imp_cpl);
     } else if (comp == FWL_PUMP_BRG) {
         double cav_factor = 1.0 + cav * 2.0;
         double temp_factor = py_max(1.0, (temperature - 50.0) / 30.0);
         double imp_cpl = 1.0 + (impeller_wear / 100.0) * 0.4;
-        wear_rate = (c.base_wear_rate * pow(load_factor, c.load_wear_exponent) * pow(speed_factor, c.speed_wear_exponent) *
+        wear_rate = (c.base_wear_rate * py_pow(load_factor, c.load_wear_exponent) * py_pow(speed_factor, c.speed_wear_exponent) *
                      cav_factor * temp_factor * imp_cpl);
     } else if (comp == FWL_THRUST_BRG) {
         double axial = head_factor * load_factor;
         double imp_cpl = 1.0 + (impeller_wear / 100.0) * 0.25;
-        wear_rate = (c.base_wear_rate * pow(axial, c.load_wear_exponent) * pow(speed_factor, c.speed_wear_exponent) * imp_cpl);
+        wear_rate = (c.base_wear_rate * py_pow(axial, c.load_wear_exponent) * py_pow(speed_factor, c.speed_wear_exponent) * imp_cpl);
     } else if (comp == FWL_SEALS) {
         double cav_seal = 1.0 + cav * 5.0;
         double imp_cpl = 1.0 + (impeller_wear / 100.0) * 0.15;
         double brg_cpl = 1.0 + (max_brg / 100.0) * 0.2;
-        wear_rate = (c.base_wear_rate * pow(pressure_factor, c.load_wear_exponent) * 1.0 * cav_seal * imp_cpl * brg_cpl);
+        wear_rate = (c.base_wear_rate * py_pow(pressure_factor, c.load_wear_exponent) * 1.0 * cav_seal * imp_cpl * brg_cpl);
     } else {
         double brg_cpl = 1.0 + (max_brg / 100.0) * 0.3;
-        wear_rate = (c.base_wear_rate * 1.0 * 1.0 * pow(load_factor, c.load_wear_exponent) * brg_cpl);
+        wear_rate = (c.base_wear_rate * 1.0 * 1.0 * py_pow(load_factor, c.load_wear_exponent) * brg_cpl);
     }
     wear_rate *= 1.0;  // chemistry_wear_factor default
     return wear_rate;
@@ -279,7 +279,7 @@ NPS_HD void fwp_update(FWPumpState& u, const PlantParams& p, const PumpSysCond& 
     if (status == PUMP_RUNNING || status == PUMP_STARTING) {
         double speed_ratio = u.speed_percent / 100.0;
         double flow_ratio = u.flow_rate / p.fwp_rated_flow;
-        double head_ratio = speed_ratio * speed_ratio;  // speed_ratio ** 2
+        double head_ratio = py_pow(speed_ratio, 2.0);
         double base_power = p.fwp_rated_power * (flow_ratio * head_ratio);
         u.power_consumption = base_power / fwp_efficiency_factor(u);
         if (status == PUMP_STARTING) u.power_consumption = py_max(u.power_consumption, p.fwp_rated_power * 0.2);
@@ -333,7 +333,7 @@ NPS_HD void fwp_update(FWPumpState& u, const PlantParams& p, const PumpSysCond& 
             double deficit = thr - u.npsh_available;
             double severity = py_min(1.0, deficit / thr);
             double fr = u.flow_rate / p.fwp_rated_flow;
-            double flow_factor = fr * fr;  // ** 2
+            double flow_factor = py_pow(fr, 2.0);
             u.cavitation_intensity = severity * flow_factor;
             u.cavitation_time += dt * 60.0;
             u.cavitation_noise_level = 20.0 + u.cavitation_intensity * 30.0;
@@ -343,12 +343,12 @@ NPS_HD void fwp_update(FWPumpState& u, const PlantParams& p, const PumpSysCond& 
             u.cavitation_noise_level = 0.0;
             u.cavitation_time = py_max(0.0, u.cavitation_time - dt * 6.0);
         }
-        double damage_rate = (u.cavitation_intensity * u.cavitation_intensity) * dt / 60.0;
+        double damage_rate = py_pow(u.cavitation_intensity, 2.0) * dt / 60.0;
         u.cavitation_damage += damage_rate;
     }
     // _simulate_mechanical_wear: pump_system.py:603-617
     if (status == PUMP_RUNNING && u.cavitation_intensity > 0.1) {
-        double damage_rate = (u.cavitation_intensity * u.cavitation_intensity) * dt / 60.0;
+        double damage_rate = py_pow(u.cavitation_intensity, 2.0) * dt / 60.0;
         u.cavitation_damage += damage_rate;
     }
 }
@@ -458,8 +458,8 @@ NPS_HD void feedwater_update(FeedwaterState& fw, WaterChemState& wc, const Plant
         if (u.npsh_available < thr) {   // CavitationModel.update_cavitation_monitoring :113-202
             double deficit = thr - u.npsh_available;
             double severity = py_min(1.0, deficit / thr);
-            double ff = u.flow_rate / 555.0; ff = ff * ff;
-            double sf = pow(u.speed_percent / 100.0, 1.5);
+            double ff = py_pow(u.flow_rate / 555.0, 2.0);
+            double sf = py_pow(u.speed_percent / 100.0, 1.5);
             fw.cav_current_intensity = severity * ff * sf;
             fw.cav_time_in_cavitation += dt;
             if (fw.cav_current_intensity > 0.1) fw.cav_n_events = py_min(fw.cav_n_events + 1.0, 100.0);
@@ -467,7 +467,7 @@ NPS_HD void feedwater_update(FeedwaterState& fw, WaterChemState& wc, const Plant
             fw.cav_current_intensity = 0.0;
         }
         if (fw.cav_current_intensity > 0.1)
-            fw.cav_accumulated_damage += ((fw.cav_current_intensity * fw.cav_current_intensity) * 0.01) * dt;
+            fw.cav_accumulated_damage += (py_pow(fw.cav_current_intensity, 2.0) * 0.01) * dt;
         fw.cav_noise_increase = fw.cav_current_intensity * 30.0;
         fw.cav_acoustic_signature = 20.0 + fw.cav_noise_increase;
         fw.cav_induced_vibration = fw.cav_current_intensity * 2.0;
@@ -475,7 +475,7 @@ NPS_HD void feedwater_update(FeedwaterState& fw, WaterChemState& wc, const Plant
         double dr = py_min(1.0, fw.cav_accumulated_damage / 10.0);
         double fr = py_min(1.0, fw.cav_n_events / 50.0);
         fw.cav_risk_score = (ir * 0.4 + dr * 0.4 + fr * 0.2);
-        fw.cav_predicted_damage_rate = (fw.cav_current_intensity > 0) ? (fw.cav_current_intensity * fw.cav_current_intensity) * 0.01 : 0.0;
+        fw.cav_predicted_damage_rate = (fw.cav_current_intensity > 0) ? py_pow(fw.cav_current_intensity, 2.0) * 0.01 : 0.0;
         tot_risk += fw.cav_risk_score;
         double max_brg = py_max3(u.lub.component_wear[FWL_MOTOR_BRG], u.lub.component_wear[FWL_PUMP_BRG],
                                  u.lub.component_wear[FWL_THRUST_BRG]);

@@ -32,6 +32,9 @@ NPS_HD double np_clip(double x, double lo, double hi) {
     double t = (x < lo) ? lo : x;   // NaN: comparison false -> stays NaN
     return (t > hi) ? hi : t;
 }
+// Python/numpy scalar `x ** y` on floats is libm pow (even for y == 2: glibc pow(x, 2.0) differs from
+// x*x in ~0.08 % of cases, so the host build uses -fno-builtin-pow to keep the libm call).
+NPS_HD double py_pow(double x, double y) { return pow(x, y); }
 NPS_HD double py_abs(double x) { return fabs(x); }
 NPS_HD double np_sign(double x) { return (x > 0.0) ? 1.0 : ((x < 0.0) ? -1.0 : ((x == 0.0) ? 0.0 : x)); }
 NPS_HD bool   is_true(double flag) { return flag != 0.0; }

@@ -76,7 +76,7 @@ NPS_HD void lub_update_oil_quality(LubCore& L, int n_comp, const LubLimits& lim,
     double viscosity_factor = py_max(0.1, 1.0 - fabs(L.oil_viscosity_change) / lim.viscosity_change_limit);
     double antioxidant_factor = L.antioxidant_level / 100.0;
     double aw_factor = L.anti_wear_additive_level / 100.0;
-    double critical = pow(contamination_factor * antioxidant_factor * aw_factor, 1.0 / 3);
+    double critical = py_pow(contamination_factor * antioxidant_factor * aw_factor, 1.0 / 3);
     double secondary = (0.0 + acidity_factor + moisture_factor + viscosity_factor) / 3;
     L.lubrication_effectiveness = critical * 0.7 + secondary * 0.3;
     L.lubrication_effectiveness = py_max(0.3, py_min(1.0, L.lubrication_effectiveness));

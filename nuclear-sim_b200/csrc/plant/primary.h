@@ -153,7 +153,7 @@ NPS_HD double primary_overall_ua(double coolant_flow_rate) {
     double reynolds = density * velocity * fuel_rod_diameter / viscosity;
     reynolds = py_max(reynolds, 1000.0);
     double prandtl = viscosity * cp / k;
-    double nusselt = 0.023 * pow(reynolds, 0.8) * pow(prandtl, 0.4);
+    double nusselt = 0.023 * py_pow(reynolds, 0.8) * py_pow(prandtl, 0.4);
     double h = nusselt * k / fuel_rod_diameter;
     double ua = h * area;
     ua = ua * 0.1;

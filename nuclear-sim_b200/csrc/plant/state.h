@@ -202,11 +202,71 @@ struct FeedwaterState {
     double prot_system_trip_active;
 };
 
+// ---- steam generators ------------------------------------------------------------------------
+// SteamGenerator members (steam_generator/steam_generator.py:88-113), its TSPFoulingModel
+// (tsp_fouling_model.py:166-184, fouling_model_base.py:71-86; tsp_thickness[level][species] with
+// species 0 magnetite 1 copper 2 silica 3 biological) and TubeInteriorFouling
+// (tube_interior_fouling.py:62-75).  fouling_stage: 0 normal 1 significant 2 severe 3 critical.
+// shutdown_reasons bitmask: 1 fouling 2 heat-transfer 4 pressure-drop 8 maldistribution 16 design-life.
+struct SGState {
+    double primary_inlet_temp;
+    double primary_outlet_temp;
+    double secondary_pressure;
+    double secondary_temperature;
+    double steam_quality;
+    double water_level;
+    double steam_void_fraction;
+    double steam_flow_rate;
+    double feedwater_flow_rate;
+    double feedwater_temperature;
+    double tube_wall_temp;
+    double heat_transfer_rate;
+    double overall_htc;
+    double heat_flux;
+    double thermal_efficiency;
+    double tsp_operating_years;
+    double tsp_last_cleaning_time;
+    double tsp_total_cleaning_cycles;
+    double tsp_fouling_fraction;
+    double tsp_thickness[7][4];
+    double tsp_fouling_stage;
+    double tsp_heat_transfer_degradation;
+    double tsp_pressure_drop_ratio;
+    double tsp_flow_maldistribution;
+    double tsp_cumulative_power_loss;
+    double tsp_shutdown_required;
+    double tsp_shutdown_reasons;
+    double tsp_replacement_recommended;
+    double tif_operating_years;
+    double tif_last_cleaning_time;
+    double tif_scale_thickness;
+    double tif_scale_thermal_resistance;
+    double tif_scale_formation_rate;
+    double tif_comp[3];
+    double tif_fouling_fraction;
+    double tif_cumulative_performance_loss;
+    double tif_replacement_recommended;
+};
+
+// EnhancedSteamGeneratorPhysics members: steam_generator/enhanced_physics.py:133-150
+struct SGSystemState {
+    SGState sg[3];
+    double total_thermal_power;
+    double total_steam_flow;
+    double average_steam_pressure;
+    double average_steam_temperature;
+    double average_steam_quality;
+    double system_availability;
+    double operating_hours;
+    double load_demand;
+};
+
 struct PlantState {
     PrimaryState pri;
     SimState sim;
     WaterChemState wc_main;
     FeedwaterState fw;
+    SGSystemState sgs;
 };
 
 // ---- batch-uniform parameters ------------------------------------------------------------
@@ -233,6 +293,28 @@ struct PlantParams {
     double fw_prot_low_suction_pressure_trip;
     double fw_prot_high_discharge_pressure_trip;
     double fw_prot_low_flow_trip;
+    // steam generators (steam_generator/config.py:179-281) and the never-updated WAT-001 chemistry
+    double sg_heat_transfer_area;
+    double sg_primary_design_flow;
+    double sg_primary_htc;
+    double sg_secondary_htc;
+    double sg_design_pressure_secondary;
+    double sg_tube_wall_thickness;
+    double sg_tube_conductivity;
+    double sg_design_thermal_power_per_sg;
+    double sg_secondary_design_flow;
+    double sg_secondary_water_mass;
+    double sg_design_steam_flow_per_sg;
+    double sg_design_feedwater_flow_per_sg;
+    double sg_tube_inner_diameter;
+    double sg_tube_count;
+    double sg_design_total_steam_flow;
+    double sg_auto_load_balancing;
+    double sgwc_iron;
+    double sgwc_copper;
+    double sgwc_silica;
+    double sgwc_ph;
+    double sgwc_dissolved_oxygen;
 };
 
 }  // namespace nps

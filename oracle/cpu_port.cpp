@@ -61,3 +61,14 @@ extern "C" int nps_oracle_feedwater(double* state, const double* params, const d
     out5[3] = r.system_availability; out5[4] = r.sg_flow[0];
     return 0;
 }
+
+#include "sg.h"
+extern "C" int nps_oracle_sg_system(double* state, const double* params, const double* tin, const double* tout,
+                                    const double* flows, double ldf, double sys_ld, double fw_temp,
+                                    const double* fw_flows, double dt) {
+    PlantParams p; std::memcpy(&p, params, sizeof(p));
+    PlantState st; std::memcpy(&st, state, sizeof(st));
+    sg_system_update(st.sgs, p, tin, tout, flows, ldf, sys_ld, fw_temp, fw_flows, dt);
+    std::memcpy(state, &st, sizeof(st));
+    return 0;
+}

@@ -29,7 +29,7 @@ for k in range(300):
                              ctypes.c_double(7.4), ctypes.c_double(dt), ptr(out))
     bad, mx = compare(c, s1)
     worst = max(worst, mx)
-    if bad and mx > 1e-12:
+    if bad and mx > float(os.environ.get("TOL","1e-12")):
         print("step", k, "max", mx)
         for b in bad: print("   ", b)
         break

@@ -138,12 +138,90 @@ def feedwater_params(fw, d):
     d["fw_prot_low_flow_trip"] = float(pc.low_flow_trip)
 
 
+FOULING_STAGE = {"normal": 0.0, "significant": 1.0, "severe": 2.0, "critical": 3.0}
+SHUTDOWN_BITS = {"critical_tsp_fouling": 1, "excessive_heat_transfer_loss": 2, "excessive_pressure_drop": 4,
+                 "severe_flow_maldistribution": 8, "tube_integrity_risk": 0, "design_life_exceeded": 16}
+
+
+def steam_generators(sgs, d):
+    P = "sgs."
+    assert len(sgs.steam_generators) == 3
+    for i, sg in enumerate(sgs.steam_generators):
+        pre = f"{P}sg[{i}]."
+        for name in ("primary_inlet_temp", "primary_outlet_temp", "secondary_pressure", "secondary_temperature",
+                     "steam_quality", "water_level", "steam_void_fraction", "steam_flow_rate", "feedwater_flow_rate",
+                     "feedwater_temperature", "tube_wall_temp", "heat_transfer_rate", "overall_htc", "heat_flux"):
+            d[pre + name] = float(getattr(sg, name))
+        d[pre + "thermal_efficiency"] = float(sg.heat_transfer_rate / sg.config.design_thermal_power_per_sg)
+        t = sg.tsp_fouling
+        d[pre + "tsp_operating_years"] = float(t.operating_years)
+        d[pre + "tsp_last_cleaning_time"] = float(t.last_cleaning_time)
+        d[pre + "tsp_total_cleaning_cycles"] = float(t.total_cleaning_cycles)
+        d[pre + "tsp_fouling_fraction"] = float(t.fouling_fraction)
+        for lv in range(7):
+            d[f"{pre}tsp_thickness[{lv}][0]"] = float(t.deposits.magnetite_thickness[lv])
+            d[f"{pre}tsp_thickness[{lv}][1]"] = float(t.deposits.copper_thickness[lv])
+            d[f"{pre}tsp_thickness[{lv}][2]"] = float(t.deposits.silica_thickness[lv])
+            d[f"{pre}tsp_thickness[{lv}][3]"] = float(t.deposits.biological_thickness[lv])
+        d[pre + "tsp_fouling_stage"] = FOULING_STAGE[t.fouling_stage.value]
+        d[pre + "tsp_heat_transfer_degradation"] = float(t.heat_transfer_degradation)
+        d[pre + "tsp_pressure_drop_ratio"] = float(t.pressure_drop_ratio)
+        d[pre + "tsp_flow_maldistribution"] = float(t.flow_maldistribution)
+        d[pre + "tsp_cumulative_power_loss"] = float(t.cumulative_power_loss)
+        d[pre + "tsp_shutdown_required"] = float(t.shutdown_required)
+        d[pre + "tsp_shutdown_reasons"] = float(sum(SHUTDOWN_BITS[r.value] for r in t.shutdown_reasons))
+        d[pre + "tsp_replacement_recommended"] = float(t.replacement_recommended)
+        f = sg.tube_interior_fouling
+        d[pre + "tif_operating_years"] = float(f.operating_years)
+        d[pre + "tif_last_cleaning_time"] = float(f.last_cleaning_time)
+        d[pre + "tif_scale_thickness"] = float(f.scale_thickness)
+        d[pre + "tif_scale_thermal_resistance"] = float(f.scale_thermal_resistance)
+        d[pre + "tif_scale_formation_rate"] = float(f.scale_formation_rate)
+        d[pre + "tif_comp[0]"] = float(f.scale_composition["iron_oxide"])
+        d[pre + "tif_comp[1]"] = float(f.scale_composition["crud_deposits"])
+        d[pre + "tif_comp[2]"] = float(f.scale_composition["corrosion_products"])
+        d[pre + "tif_fouling_fraction"] = float(f.fouling_fraction)
+        d[pre + "tif_cumulative_performance_loss"] = float(f.cumulative_performance_loss)
+        d[pre + "tif_replacement_recommended"] = float(f.replacement_recommended)
+    for name in ("total_thermal_power", "total_steam_flow", "average_steam_pressure", "average_steam_temperature",
+                 "average_steam_quality", "operating_hours", "load_demand"):
+        d[P + name] = float(getattr(sgs, name))
+    d[P + "system_availability"] = float(sgs.system_availability)
+
+
+def steam_generator_params(sgs, d):
+    c = sgs.steam_generators[0].config
+    d["sg_heat_transfer_area"] = float(c.heat_transfer_area_per_sg)
+    d["sg_primary_design_flow"] = float(c.primary_design_flow)
+    d["sg_primary_htc"] = float(c.primary_htc)
+    d["sg_secondary_htc"] = float(c.secondary_htc)
+    d["sg_design_pressure_secondary"] = float(c.design_pressure_secondary)
+    d["sg_tube_wall_thickness"] = float(c.tube_wall_thickness)
+    d["sg_tube_conductivity"] = float(c.tube_material_conductivity)
+    d["sg_design_thermal_power_per_sg"] = float(c.design_thermal_power_per_sg)
+    d["sg_secondary_design_flow"] = float(c.secondary_design_flow)
+    d["sg_secondary_water_mass"] = float(c.secondary_water_mass)
+    d["sg_design_steam_flow_per_sg"] = float(c.design_steam_flow_per_sg)
+    d["sg_design_feedwater_flow_per_sg"] = float(c.design_feedwater_flow_per_sg)
+    d["sg_tube_inner_diameter"] = float(c.tube_inner_diameter)
+    d["sg_tube_count"] = float(c.tube_count_per_sg)
+    d["sg_design_total_steam_flow"] = float(sgs.config.design_total_steam_flow)
+    d["sg_auto_load_balancing"] = float(sgs.config.auto_load_balancing)
+    w = sgs.steam_generators[0].tsp_fouling.water_chemistry
+    d["sgwc_iron"] = float(w.iron_concentration)
+    d["sgwc_copper"] = float(w.copper_concentration)
+    d["sgwc_silica"] = float(w.silica_concentration)
+    d["sgwc_ph"] = float(w.ph)
+    d["sgwc_dissolved_oxygen"] = float(w.dissolved_oxygen)
+
+
 def extract(sim, d):
     if not (sim.enable_secondary and sim.secondary_physics is not None):
         return
     sec = sim.secondary_physics
     water_chem(sec.water_chemistry, "wc_main.", d)
     feedwater(sec.feedwater_system, d)
+    steam_generators(sec.steam_generator_system, d)
 
 
 def extract_params(sim, d):
@@ -151,3 +229,4 @@ def extract_params(sim, d):
         return
     sec = sim.secondary_physics
     feedwater_params(sec.feedwater_system, d)
+    steam_generator_params(sec.steam_generator_system, d)
