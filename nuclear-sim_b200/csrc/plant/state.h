@@ -261,12 +261,118 @@ struct SGSystemState {
     double load_demand;
 };
 
+// ---- turbine -----------------------------------------------------------------------------------
+// TurbineStage members: turbine/stage_system.py:57-96
+struct TurbineStageState {
+    double inlet_pressure;
+    double inlet_temperature;
+    double inlet_enthalpy;
+    double inlet_entropy;
+    double inlet_flow;
+    double outlet_pressure;
+    double outlet_temperature;
+    double outlet_enthalpy;
+    double outlet_flow;
+    double actual_efficiency;
+    double power_output;
+    double enthalpy_drop;
+    double extraction_flow;
+    double extraction_pressure;
+    double extraction_enthalpy;
+    double blade_condition_factor;
+    double fouling_factor;
+    double deposit_thickness;
+    double blade_wear_factor;
+    double operating_hours;
+    double efficiency_degradation;
+    double loading_factor;
+};
+
+// BearingModel members: turbine/rotor_dynamics.py:57-81
+struct TurbineBearingState {
+    double current_load;
+    double metal_temperature;
+    double vibration_displacement;
+    double operating_hours;
+    double wear_factor;
+    double efficiency_factor;
+    double clearance_increase;
+    double oil_temperature;
+    double oil_flow_rate;
+    double oil_contamination_level;
+    double external_oil_temp;
+};
+
+// EnhancedTurbinePhysics (turbine/enhanced_physics.py:520-541) with its TurbineStageSystem
+// (stage_system.py:693-704), RotorDynamicsModel (rotor_dynamics.py:806-829), VibrationMonitor
+// (:597-622), MetalTemperatureTracker (enhanced_physics.py:52-71), TurbineProtectionSystem (:215-236)
+// and TurbineBearingLubricationSystem (turbine_bearing_lubrication.py:191-202).
+// trip_reasons bitmask: 1 overspeed 2 vibration 4 bearing-temp 8 thrust 16 low-vacuum 32 thermal-stress.
+struct TurbineState {
+    TurbineStageState stage[14];
+    TurbineBearingState bearing[4];
+    double ss_total_power_output;
+    double ss_total_steam_flow;
+    double ss_overall_efficiency;
+    double ss_total_extraction_flow;
+    double ss_system_efficiency;
+    double ss_operating_hours;
+    double rotor_speed;
+    double rotor_acceleration;
+    double friction_torque;
+    double net_torque;
+    double rotor_temperature;
+    double thermal_expansion;
+    double thermal_bow;
+    double rotor_operating_hours;
+    double overspeed_events;
+    double vib_displacement_x;
+    double vib_displacement_y;
+    double vib_velocity_x;
+    double vib_velocity_y;
+    double vib_acceleration_x;
+    double vib_acceleration_y;
+    double vib_harmonic[3];
+    double vib_displacement_alarm;
+    double vib_velocity_alarm;
+    double vib_acceleration_alarm;
+    double vib_critical_speed_alarm;
+    double th_rotor_temperatures[8];
+    double th_casing_temperatures[6];
+    double th_blade_temperatures[14];
+    double th_rotor_gradients[7];
+    double th_casing_gradients[5];
+    double th_stress_levels[8];
+    double th_max_thermal_stress;
+    double th_temperature_rates[8];
+    double th_thermal_shock_risk;
+    double prot_timer_overspeed;
+    double prot_timer_vibration;
+    double prot_timer_bearing_temp;
+    double prot_trip_active;
+    double prot_trip_reasons;
+    LubCore lub;
+    double lub_turbine_efficiency_degradation;
+    double lub_vibration_increase;
+    double lub_oil_cooling_effectiveness;
+    double lub_bearing_housing_temperature;
+    double total_power_output;
+    double overall_efficiency;
+    double steam_rate;
+    double heat_rate;
+    double performance_factor;
+    double availability_factor;
+    double operating_hours;
+    double load_demand;
+};
+
 struct PlantState {
     PrimaryState pri;
     SimState sim;
     WaterChemState wc_main;
     FeedwaterState fw;
     SGSystemState sgs;
+    TurbineState turb;
 };
 
 // ---- batch-uniform parameters ------------------------------------------------------------
@@ -315,6 +421,52 @@ struct PlantParams {
     double sgwc_silica;
     double sgwc_ph;
     double sgwc_dissolved_oxygen;
+    // turbine (turbine/config.py:37-195,260-311; per-stage design tables from stage_system.py:706-758)
+    double ts_design_inlet_pressure[14];
+    double ts_design_outlet_pressure[14];
+    double ts_design_steam_flow[14];
+    double ts_design_efficiency[14];
+    double ts_has_extraction[14];
+    double ts_max_extraction_flow[14];
+    double ts_min_extraction_flow[14];
+    double ts_fouling_rate;
+    double ts_erosion_rate;
+    double ts_deposit_buildup_rate;
+    double rd_rotor_inertia;
+    double rd_max_speed;
+    double rd_thermal_expansion_coefficient;
+    double rd_rotor_length;
+    double rd_thermal_bow_limit;
+    double rd_rotor_mass;
+    double rd_design_load_capacity;
+    double rd_bearing_clearance;
+    double rd_bearing_stiffness;
+    double rd_bearing_damping;
+    double rd_friction_coefficient;
+    double rd_first_critical_speed;
+    double rd_second_critical_speed;
+    double rd_critical_speed_margin;
+    double rd_displacement_alarm;
+    double rd_velocity_alarm;
+    double rd_acceleration_alarm;
+    double tt_thermal_time_constant;
+    double tt_thermal_expansion_coeff;
+    double tt_elastic_modulus;
+    double tt_max_thermal_gradient;
+    double tt_max_thermal_stress;
+    double tp_overspeed_trip;
+    double tp_overspeed_delay;
+    double tp_vibration_trip;
+    double tp_vibration_delay;
+    double tp_bearing_temp_trip;
+    double tp_bearing_temp_delay;
+    double tp_thrust_bearing_trip;
+    double tp_low_vacuum_trip;
+    double tp_max_thermal_stress;
+    double tl_contamination_limit;
+    double tl_acidity_limit;
+    double tl_moisture_limit;
+    double tl_viscosity_change_limit;
 };
 
 }  // namespace nps

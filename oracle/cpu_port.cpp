@@ -72,3 +72,15 @@ extern "C" int nps_oracle_sg_system(double* state, const double* params, const d
     std::memcpy(state, &st, sizeof(st));
     return 0;
 }
+
+#include "turbine.h"
+extern "C" int nps_oracle_turbine(double* state, const double* params, double load_demand, double cond_p, double dt,
+                                  double* out11) {
+    PlantParams p; std::memcpy(&p, params, sizeof(p));
+    PlantState st; std::memcpy(&st, state, sizeof(st));
+    TurbineResult r;
+    turbine_update(st.turb, p, st.sgs, load_demand, cond_p, dt, r);
+    std::memcpy(state, &st, sizeof(st));
+    std::memcpy(out11, &r, sizeof(r));
+    return 0;
+}

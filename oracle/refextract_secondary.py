@@ -215,6 +215,140 @@ def steam_generator_params(sgs, d):
     d["sgwc_dissolved_oxygen"] = float(w.dissolved_oxygen)
 
 
+TURB_LUB_COMPONENTS = ["hp_journal_bearing", "lp_journal_bearing", "thrust_bearing", "seal_oil_system", "oil_coolers"]
+TURB_TRIP_BITS = {"Overspeed": 1, "High Vibration": 2, "High Bearing Temperature": 4,
+                  "Thrust Bearing Displacement": 8, "Low Vacuum": 16, "High Thermal Stress": 32}
+
+
+def _sorted_stages(turb):
+    st = sorted(turb.stage_system.stages.items(), key=lambda x: x[1].config.design_inlet_pressure, reverse=True)
+    ids = [k for k, _ in st]
+    assert ids == [f"HP-{i+1}" for i in range(8)] + [f"LP-{i+1}" for i in range(6)], ids
+    return [v for _, v in st]
+
+
+def turbine(turb, d):
+    P = "turb."
+    for k, stg in enumerate(_sorted_stages(turb)):
+        pre = f"{P}stage[{k}]."
+        for name in ("inlet_pressure", "inlet_temperature", "inlet_enthalpy", "inlet_entropy", "inlet_flow",
+                     "outlet_pressure", "outlet_temperature", "outlet_enthalpy", "outlet_flow", "actual_efficiency",
+                     "power_output", "enthalpy_drop", "extraction_flow", "extraction_pressure", "extraction_enthalpy",
+                     "blade_condition_factor", "fouling_factor", "deposit_thickness", "blade_wear_factor",
+                     "operating_hours", "efficiency_degradation", "loading_factor"):
+            d[pre + name] = float(getattr(stg, name))
+    rd = turb.rotor_dynamics
+    bearings = list(rd.bearings.items())
+    assert [b for b, _ in bearings] == ["TB-001", "TB-002", "TB-003", "TB-004"]
+    assert [b.config.bearing_type for _, b in bearings] == ["journal", "journal", "thrust", "journal"]
+    for b, (_, br) in enumerate(bearings):
+        pre = f"{P}bearing[{b}]."
+        for name in ("current_load", "metal_temperature", "vibration_displacement", "operating_hours", "wear_factor",
+                     "efficiency_factor", "clearance_increase", "oil_temperature", "oil_flow_rate",
+                     "oil_contamination_level"):
+            d[pre + name] = float(getattr(br, name))
+        d[pre + "external_oil_temp"] = float(br.external_oil_temp)
+    ss = turb.stage_system
+    d[P + "ss_total_power_output"] = float(ss.total_power_output)
+    d[P + "ss_total_steam_flow"] = float(ss.total_steam_flow)
+    d[P + "ss_overall_efficiency"] = float(ss.overall_efficiency)
+    d[P + "ss_total_extraction_flow"] = float(ss.total_extraction_flow)
+    d[P + "ss_system_efficiency"] = float(ss.system_efficiency)
+    d[P + "ss_operating_hours"] = float(ss.operating_hours)
+    for name in ("rotor_speed", "rotor_acceleration", "friction_torque", "net_torque", "rotor_temperature",
+                 "thermal_expansion", "thermal_bow", "overspeed_events"):
+        d[P + name] = float(getattr(rd, name))
+    d[P + "rotor_operating_hours"] = float(rd.operating_hours)
+    vm = rd.vibration_monitor
+    for a, b in (("vib_displacement_x", "displacement_x"), ("vib_displacement_y", "displacement_y"),
+                 ("vib_velocity_x", "velocity_x"), ("vib_velocity_y", "velocity_y"),
+                 ("vib_acceleration_x", "acceleration_x"), ("vib_acceleration_y", "acceleration_y"),
+                 ("vib_displacement_alarm", "displacement_alarm"), ("vib_velocity_alarm", "velocity_alarm"),
+                 ("vib_acceleration_alarm", "acceleration_alarm"), ("vib_critical_speed_alarm", "critical_speed_alarm")):
+        d[P + a] = float(getattr(vm, b))
+    for i in range(3):
+        d[f"{P}vib_harmonic[{i}]"] = float(vm.harmonic_amplitudes[i])
+    th = turb.thermal_tracker
+    for i in range(8):
+        d[f"{P}th_rotor_temperatures[{i}]"] = float(th.rotor_temperatures[i])
+        d[f"{P}th_stress_levels[{i}]"] = float(th.thermal_stress_levels[i])
+        d[f"{P}th_temperature_rates[{i}]"] = float(th.temperature_rates[i])
+    for i in range(6):
+        d[f"{P}th_casing_temperatures[{i}]"] = float(th.casing_temperatures[i])
+    for i in range(14):
+        d[f"{P}th_blade_temperatures[{i}]"] = float(th.blade_temperatures[i])
+    for i in range(7):
+        d[f"{P}th_rotor_gradients[{i}]"] = float(th.rotor_gradients[i])
+    for i in range(5):
+        d[f"{P}th_casing_gradients[{i}]"] = float(th.casing_gradients[i])
+    d[P + "th_max_thermal_stress"] = float(th.max_thermal_stress)
+    d[P + "th_thermal_shock_risk"] = float(th.thermal_shock_risk)
+    pr = turb.protection_system
+    d[P + "prot_timer_overspeed"] = float(pr.trip_timers["overspeed"])
+    d[P + "prot_timer_vibration"] = float(pr.trip_timers["vibration"])
+    d[P + "prot_timer_bearing_temp"] = float(pr.trip_timers["bearing_temp"])
+    d[P + "prot_trip_active"] = float(pr.trip_active)
+    d[P + "prot_trip_reasons"] = float(sum(TURB_TRIP_BITS[r] for r in pr.trip_reasons))
+    L = turb.bearing_lubrication_system
+    lub_core(L, TURB_LUB_COMPONENTS, P + "lub.", d)
+    d[P + "lub_turbine_efficiency_degradation"] = float(L.turbine_efficiency_degradation)
+    d[P + "lub_vibration_increase"] = float(L.vibration_increase)
+    d[P + "lub_oil_cooling_effectiveness"] = float(L.oil_cooling_effectiveness)
+    d[P + "lub_bearing_housing_temperature"] = float(L.bearing_housing_temperature)
+    for name in ("total_power_output", "overall_efficiency", "steam_rate", "heat_rate", "performance_factor",
+                 "availability_factor", "operating_hours", "load_demand"):
+        d[P + name] = float(getattr(turb, name))
+
+
+def turbine_params(turb, d):
+    for k, stg in enumerate(_sorted_stages(turb)):
+        c = stg.config
+        d[f"ts_design_inlet_pressure[{k}]"] = float(c.design_inlet_pressure)
+        d[f"ts_design_outlet_pressure[{k}]"] = float(c.design_outlet_pressure)
+        d[f"ts_design_steam_flow[{k}]"] = float(c.design_steam_flow)
+        d[f"ts_design_efficiency[{k}]"] = float(c.design_efficiency)
+        d[f"ts_has_extraction[{k}]"] = float(c.has_extraction)
+        d[f"ts_max_extraction_flow[{k}]"] = float(c.max_extraction_flow)
+        d[f"ts_min_extraction_flow[{k}]"] = float(c.min_extraction_flow)
+        assert getattr(c, "min_stage_efficiency", 0.7) == 0.7
+    c0 = _sorted_stages(turb)[0].config
+    d["ts_fouling_rate"] = float(c0.fouling_rate)
+    d["ts_erosion_rate"] = float(c0.erosion_rate)
+    d["ts_deposit_buildup_rate"] = float(c0.deposit_buildup_rate)
+    rc = turb.rotor_dynamics.config
+    for a, b in (("rd_rotor_inertia", "rotor_inertia"), ("rd_max_speed", "max_speed"),
+                 ("rd_thermal_expansion_coefficient", "thermal_expansion_coefficient"), ("rd_rotor_length", "rotor_length"),
+                 ("rd_thermal_bow_limit", "thermal_bow_limit"), ("rd_rotor_mass", "rotor_mass"),
+                 ("rd_first_critical_speed", "first_critical_speed"), ("rd_second_critical_speed", "second_critical_speed"),
+                 ("rd_critical_speed_margin", "critical_speed_margin"), ("rd_displacement_alarm", "displacement_alarm"),
+                 ("rd_velocity_alarm", "velocity_alarm"), ("rd_acceleration_alarm", "acceleration_alarm")):
+        d[a] = float(getattr(rc, b))
+    b0 = next(iter(turb.rotor_dynamics.bearings.values())).config
+    d["rd_design_load_capacity"] = float(b0.design_load_capacity)
+    d["rd_bearing_clearance"] = float(b0.bearing_clearance)
+    d["rd_bearing_stiffness"] = float(b0.stiffness_coefficient)
+    d["rd_bearing_damping"] = float(b0.damping_coefficient)
+    d["rd_friction_coefficient"] = float(b0.friction_coefficient)
+    tc = turb.thermal_tracker.config
+    d["tt_thermal_time_constant"] = float(tc.thermal_time_constant)
+    d["tt_thermal_expansion_coeff"] = float(tc.thermal_expansion_coeff)
+    d["tt_elastic_modulus"] = float(tc.elastic_modulus)
+    d["tt_max_thermal_gradient"] = float(tc.max_thermal_gradient)
+    d["tt_max_thermal_stress"] = float(tc.max_thermal_stress)
+    pc = turb.protection_system.config
+    for a, b in (("tp_overspeed_trip", "overspeed_trip"), ("tp_overspeed_delay", "overspeed_delay"),
+                 ("tp_vibration_trip", "vibration_trip"), ("tp_vibration_delay", "vibration_delay"),
+                 ("tp_bearing_temp_trip", "bearing_temp_trip"), ("tp_bearing_temp_delay", "bearing_temp_delay"),
+                 ("tp_thrust_bearing_trip", "thrust_bearing_trip"), ("tp_low_vacuum_trip", "low_vacuum_trip"),
+                 ("tp_max_thermal_stress", "max_thermal_stress")):
+        d[a] = float(getattr(pc, b))
+    lc = turb.bearing_lubrication_system.config
+    d["tl_contamination_limit"] = float(lc.contamination_limit)
+    d["tl_acidity_limit"] = float(lc.acidity_limit)
+    d["tl_moisture_limit"] = float(lc.moisture_limit)
+    d["tl_viscosity_change_limit"] = float(lc.viscosity_change_limit)
+
+
 def extract(sim, d):
     if not (sim.enable_secondary and sim.secondary_physics is not None):
         return
@@ -222,6 +356,7 @@ def extract(sim, d):
     water_chem(sec.water_chemistry, "wc_main.", d)
     feedwater(sec.feedwater_system, d)
     steam_generators(sec.steam_generator_system, d)
+    turbine(sec.turbine, d)
 
 
 def extract_params(sim, d):
@@ -230,3 +365,4 @@ def extract_params(sim, d):
     sec = sim.secondary_physics
     feedwater_params(sec.feedwater_system, d)
     steam_generator_params(sec.steam_generator_system, d)
+    turbine_params(sec.turbine, d)
