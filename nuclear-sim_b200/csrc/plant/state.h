@@ -366,6 +366,84 @@ struct TurbineState {
     double load_demand;
 };
 
+// ---- condenser ---------------------------------------------------------------------------------
+// SteamJetEjector members: condenser/vacuum_pump.py:56-95
+struct EjectorState {
+    double is_operating;
+    double operating_hours;
+    double current_capacity;
+    double suction_pressure;
+    double motive_steam_flow;
+    double motive_steam_pressure_actual;
+    double motive_steam_temp_actual;
+    double first_stage_capacity;
+    double second_stage_capacity;
+    double intercondenser_load;
+    double nozzle_fouling_factor;
+    double diffuser_fouling_factor;
+    double nozzle_erosion_factor;
+    double overall_performance_factor;
+    double steam_consumption_rate;
+    double compression_ratio_actual;
+    double entrainment_ratio;
+};
+
+// EnhancedCondenserPhysics (condenser/physics.py:536-560) with TubeDegradationModel (:56-71),
+// AdvancedFoulingModel (:151-165), VacuumSystem + VacuumControlLogic (vacuum_system.py:46-58,256-306)
+// and its own WaterChemistry (WAT-002).  lead/lag ejector: index, -1 = None.
+struct CondenserState {
+    WaterChemState wc;
+    EjectorState ejector[2];
+    double steam_inlet_pressure;
+    double steam_inlet_temperature;
+    double steam_inlet_flow;
+    double steam_inlet_quality;
+    double cooling_water_inlet_temp;
+    double cooling_water_outlet_temp;
+    double cooling_water_flow;
+    double heat_rejection_rate;
+    double overall_htc;
+    double condensate_temperature;
+    double condensate_flow;
+    double thermal_performance_factor;
+    double operating_hours;
+    double td_active_tube_count;
+    double td_plugged_tube_count;
+    double td_average_wall_thickness;
+    double td_tube_leak_rate;
+    double td_vibration_damage_accumulation;
+    double td_corrosion_damage_accumulation;
+    double td_operating_hours;
+    double td_area_factor;
+    double td_pressure_drop_factor;
+    double fl_biofouling_thickness;
+    double fl_scale_thickness;
+    double fl_corrosion_product_thickness;
+    double fl_distribution_factor;
+    double fl_time_since_cleaning;
+    double fl_total_fouling_resistance;
+    double vs_condenser_pressure;
+    double vs_air_partial_pressure;
+    double vs_steam_partial_pressure;
+    double vs_total_air_removal_rate;
+    double vs_total_steam_consumption;
+    double vs_current_air_leakage;
+    double vs_air_mass_in_condenser;
+    double vs_motive_steam_pressure;
+    double vs_motive_steam_temperature;
+    double vs_motive_steam_available;
+    double vs_system_efficiency;
+    double vs_operating_hours;
+    double vs_alarm_high_pressure;
+    double vs_alarm_low_motive_pressure;
+    double vs_alarm_ejector_failure;
+    double vs_alarm_excessive_air_leakage;
+    double vs_trip_high_pressure;
+    double vc_lead_ejector;
+    double vc_lag_ejector;
+    double vc_rotation_timer;
+};
+
 struct PlantState {
     PrimaryState pri;
     SimState sim;
@@ -373,6 +451,7 @@ struct PlantState {
     FeedwaterState fw;
     SGSystemState sgs;
     TurbineState turb;
+    CondenserState cond;
 };
 
 // ---- batch-uniform parameters ------------------------------------------------------------
@@ -467,6 +546,55 @@ struct PlantParams {
     double tl_acidity_limit;
     double tl_moisture_limit;
     double tl_viscosity_change_limit;
+    // condenser (condenser/config.py:37-215)
+    double cd_design_heat_duty;
+    double cd_design_cooling_water_flow;
+    double cd_heat_transfer_area;
+    double cd_tube_inner_diameter;
+    double cd_tube_wall_thickness;
+    double cd_steam_side_htc;
+    double cd_water_side_htc;
+    double cd_tube_wall_conductivity;
+    double cd_td_initial_tube_count;
+    double cd_td_tube_failure_rate;
+    double cd_td_vibration_damage_threshold;
+    double cd_td_wall_thickness_initial;
+    double cd_td_wall_thickness_minimum;
+    double cd_td_corrosion_rate;
+    double cd_fl_biofouling_base_rate;
+    double cd_fl_biofouling_temp_coefficient;
+    double cd_fl_biofouling_nutrient_factor;
+    double cd_fl_scale_base_rate;
+    double cd_fl_scale_hardness_coefficient;
+    double cd_fl_scale_temp_coefficient;
+    double cd_fl_corrosion_base_rate;
+    double cd_fl_corrosion_oxygen_coefficient;
+    double cd_fl_corrosion_ph_optimum;
+    double cd_vs_base_air_leakage;
+    double cd_vs_auto_start_pressure;
+    double cd_vs_auto_stop_pressure;
+    double cd_vs_rotation_interval;
+    double cd_vs_leakage_degradation_rate;
+    double cd_vs_condenser_volume;
+    double cd_vs_steam_pressure_drop;
+    double cd_vs_high_pressure_alarm;
+    double cd_vs_high_pressure_trip;
+    double cd_vs_low_motive_pressure_alarm;
+    double ej_two_stage[2];
+    double ej_design_capacity[2];
+    double ej_design_suction_pressure[2];
+    double ej_motive_steam_pressure[2];
+    double ej_motive_steam_temperature[2];
+    double ej_base_steam_consumption[2];
+    double ej_steam_consumption_exponent[2];
+    double ej_pressure_effect_coefficient[2];
+    double ej_min_suction_pressure[2];
+    double ej_max_suction_pressure[2];
+    double ej_min_motive_pressure[2];
+    double ej_intercondenser_pressure[2];
+    double ej_nozzle_fouling_rate[2];
+    double ej_diffuser_fouling_rate[2];
+    double ej_erosion_rate[2];
 };
 
 }  // namespace nps

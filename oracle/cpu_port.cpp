@@ -84,3 +84,14 @@ extern "C" int nps_oracle_turbine(double* state, const double* params, double lo
     std::memcpy(out11, &r, sizeof(r));
     return 0;
 }
+
+#include "condenser.h"
+extern "C" int nps_oracle_condenser(double* state, const double* params, const double* in8, double dt, double* out7) {
+    PlantParams p; std::memcpy(&p, params, sizeof(p));
+    PlantState st; std::memcpy(&st, state, sizeof(st));
+    CondenserResult r;
+    condenser_update(st.cond, p, in8[0], in8[1], in8[2], in8[3], in8[4], in8[5], in8[6], in8[7], dt, r);
+    std::memcpy(state, &st, sizeof(st));
+    std::memcpy(out7, &r, sizeof(r));
+    return 0;
+}

@@ -349,6 +349,121 @@ def turbine_params(turb, d):
     d["tl_viscosity_change_limit"] = float(lc.viscosity_change_limit)
 
 
+def condenser(cond, d):
+    P = "cond."
+    water_chem(cond.water_chemistry, P + "wc.", d)
+    vs = cond.vacuum_system
+    ej_ids = list(vs.ejectors.keys())
+    assert len(ej_ids) == 2
+    for i, eid in enumerate(ej_ids):
+        e = vs.ejectors[eid]
+        pre = f"{P}ejector[{i}]."
+        d[pre + "is_operating"] = float(e.is_operating)
+        for name in ("operating_hours", "current_capacity", "suction_pressure", "motive_steam_flow",
+                     "motive_steam_pressure_actual", "motive_steam_temp_actual", "nozzle_fouling_factor",
+                     "diffuser_fouling_factor", "nozzle_erosion_factor", "overall_performance_factor",
+                     "steam_consumption_rate", "compression_ratio_actual", "entrainment_ratio"):
+            d[pre + name] = float(getattr(e, name))
+        for name in ("first_stage_capacity", "second_stage_capacity", "intercondenser_load"):
+            d[pre + name] = float(getattr(e, name, 0.0))
+        assert e.motive_steam_available
+    for name in ("steam_inlet_pressure", "steam_inlet_temperature", "steam_inlet_flow", "steam_inlet_quality",
+                 "cooling_water_inlet_temp", "cooling_water_outlet_temp", "cooling_water_flow", "heat_rejection_rate",
+                 "overall_htc", "condensate_temperature", "condensate_flow", "thermal_performance_factor",
+                 "operating_hours"):
+        d[P + name] = float(getattr(cond, name))
+    td = cond.tube_degradation
+    for a, b in (("td_active_tube_count", "active_tube_count"), ("td_plugged_tube_count", "plugged_tube_count"),
+                 ("td_average_wall_thickness", "average_wall_thickness"), ("td_tube_leak_rate", "tube_leak_rate"),
+                 ("td_vibration_damage_accumulation", "vibration_damage_accumulation"),
+                 ("td_corrosion_damage_accumulation", "corrosion_damage_accumulation"),
+                 ("td_operating_hours", "operating_hours"), ("td_area_factor", "effective_heat_transfer_area_factor"),
+                 ("td_pressure_drop_factor", "tube_side_pressure_drop_factor")):
+        d[P + a] = float(getattr(td, b))
+    fl = cond.fouling_model
+    for a, b in (("fl_biofouling_thickness", "biofouling_thickness"), ("fl_scale_thickness", "scale_thickness"),
+                 ("fl_corrosion_product_thickness", "corrosion_product_thickness"),
+                 ("fl_distribution_factor", "fouling_distribution_factor"),
+                 ("fl_time_since_cleaning", "time_since_cleaning"),
+                 ("fl_total_fouling_resistance", "total_fouling_resistance")):
+        d[P + a] = float(getattr(fl, b))
+    for a, b in (("vs_condenser_pressure", "condenser_pressure"), ("vs_air_partial_pressure", "air_partial_pressure"),
+                 ("vs_steam_partial_pressure", "steam_partial_pressure"),
+                 ("vs_total_air_removal_rate", "total_air_removal_rate"),
+                 ("vs_total_steam_consumption", "total_steam_consumption"),
+                 ("vs_current_air_leakage", "current_air_leakage"), ("vs_air_mass_in_condenser", "air_mass_in_condenser"),
+                 ("vs_motive_steam_pressure", "motive_steam_pressure"),
+                 ("vs_motive_steam_temperature", "motive_steam_temperature"),
+                 ("vs_motive_steam_available", "motive_steam_available"), ("vs_system_efficiency", "system_efficiency"),
+                 ("vs_operating_hours", "operating_hours")):
+        d[P + a] = float(getattr(vs, b))
+    d[P + "vs_alarm_high_pressure"] = float(vs.alarms["high_pressure"])
+    d[P + "vs_alarm_low_motive_pressure"] = float(vs.alarms["low_motive_pressure"])
+    d[P + "vs_alarm_ejector_failure"] = float(vs.alarms["ejector_failure"])
+    d[P + "vs_alarm_excessive_air_leakage"] = float(vs.alarms["excessive_air_leakage"])
+    d[P + "vs_trip_high_pressure"] = float(vs.trips["high_pressure_trip"])
+    cl = vs.control_logic
+    assert not cl.manual_override
+    d[P + "vc_lead_ejector"] = float(ej_ids.index(cl.lead_ejector_id)) if cl.lead_ejector_id is not None else -1.0
+    d[P + "vc_lag_ejector"] = float(ej_ids.index(cl.lag_ejector_id)) if cl.lag_ejector_id is not None else -1.0
+    d[P + "vc_rotation_timer"] = float(cl.rotation_timer)
+
+
+def condenser_params(cond, d):
+    c = cond.config
+    ht = c.heat_transfer
+    d["cd_design_heat_duty"] = float(c.design_heat_duty)
+    d["cd_design_cooling_water_flow"] = float(c.design_cooling_water_flow)
+    d["cd_heat_transfer_area"] = float(ht.heat_transfer_area)
+    d["cd_tube_inner_diameter"] = float(ht.tube_inner_diameter)
+    d["cd_tube_wall_thickness"] = float(ht.tube_wall_thickness)
+    d["cd_steam_side_htc"] = float(ht.steam_side_htc)
+    d["cd_water_side_htc"] = float(ht.water_side_htc)
+    d["cd_tube_wall_conductivity"] = float(ht.tube_wall_conductivity)
+    tc = cond.tube_degradation.config
+    for a, b in (("cd_td_initial_tube_count", "initial_tube_count"), ("cd_td_tube_failure_rate", "tube_failure_rate"),
+                 ("cd_td_vibration_damage_threshold", "vibration_damage_threshold"),
+                 ("cd_td_wall_thickness_initial", "wall_thickness_initial"),
+                 ("cd_td_wall_thickness_minimum", "wall_thickness_minimum"), ("cd_td_corrosion_rate", "corrosion_rate")):
+        d[a] = float(getattr(tc, b))
+    fc = cond.fouling_model.config
+    for a, b in (("cd_fl_biofouling_base_rate", "biofouling_base_rate"),
+                 ("cd_fl_biofouling_temp_coefficient", "biofouling_temp_coefficient"),
+                 ("cd_fl_biofouling_nutrient_factor", "biofouling_nutrient_factor"),
+                 ("cd_fl_scale_base_rate", "scale_base_rate"),
+                 ("cd_fl_scale_hardness_coefficient", "scale_hardness_coefficient"),
+                 ("cd_fl_scale_temp_coefficient", "scale_temp_coefficient"),
+                 ("cd_fl_corrosion_base_rate", "corrosion_base_rate"),
+                 ("cd_fl_corrosion_oxygen_coefficient", "corrosion_oxygen_coefficient"),
+                 ("cd_fl_corrosion_ph_optimum", "corrosion_ph_optimum")):
+        d[a] = float(getattr(fc, b))
+    vc = cond.vacuum_system.config
+    assert vc.control_strategy == "lead_lag", vc.control_strategy
+    for a, b in (("cd_vs_base_air_leakage", "base_air_leakage"), ("cd_vs_auto_start_pressure", "auto_start_pressure"),
+                 ("cd_vs_auto_stop_pressure", "auto_stop_pressure"), ("cd_vs_rotation_interval", "rotation_interval"),
+                 ("cd_vs_leakage_degradation_rate", "leakage_degradation_rate"),
+                 ("cd_vs_condenser_volume", "condenser_volume"), ("cd_vs_steam_pressure_drop", "steam_pressure_drop"),
+                 ("cd_vs_high_pressure_alarm", "high_pressure_alarm"), ("cd_vs_high_pressure_trip", "high_pressure_trip"),
+                 ("cd_vs_low_motive_pressure_alarm", "low_motive_pressure_alarm")):
+        d[a] = float(getattr(vc, b))
+    for i, e in enumerate(cond.vacuum_system.ejectors.values()):
+        ec = e.config
+        d[f"ej_two_stage[{i}]"] = float(ec.ejector_type == "two_stage")
+        assert ec.ejector_type in ("two_stage", "single_stage")
+        assert e.discharge_pressure == 0.101
+        for a, b in (("ej_design_capacity", "design_capacity"), ("ej_design_suction_pressure", "design_suction_pressure"),
+                     ("ej_motive_steam_pressure", "motive_steam_pressure"),
+                     ("ej_motive_steam_temperature", "motive_steam_temperature"),
+                     ("ej_base_steam_consumption", "base_steam_consumption"),
+                     ("ej_steam_consumption_exponent", "steam_consumption_exponent"),
+                     ("ej_pressure_effect_coefficient", "pressure_effect_coefficient"),
+                     ("ej_min_suction_pressure", "min_suction_pressure"), ("ej_max_suction_pressure", "max_suction_pressure"),
+                     ("ej_min_motive_pressure", "min_motive_pressure"), ("ej_intercondenser_pressure", "intercondenser_pressure"),
+                     ("ej_nozzle_fouling_rate", "nozzle_fouling_rate"), ("ej_diffuser_fouling_rate", "diffuser_fouling_rate"),
+                     ("ej_erosion_rate", "erosion_rate")):
+            d[f"{a}[{i}]"] = float(getattr(ec, b))
+
+
 def extract(sim, d):
     if not (sim.enable_secondary and sim.secondary_physics is not None):
         return
@@ -357,6 +472,7 @@ def extract(sim, d):
     feedwater(sec.feedwater_system, d)
     steam_generators(sec.steam_generator_system, d)
     turbine(sec.turbine, d)
+    condenser(sec.condenser, d)
 
 
 def extract_params(sim, d):
@@ -366,3 +482,4 @@ def extract_params(sim, d):
     feedwater_params(sec.feedwater_system, d)
     steam_generator_params(sec.steam_generator_system, d)
     turbine_params(sec.turbine, d)
+    condenser_params(sec.condenser, d)
