@@ -1,0 +1,140 @@
+// Secondary-system orchestration: feedwater -> steam generators -> turbine -> condenser ->
+// water chemistry / pH control -> electrical-power gating.
+// Restates SecondaryReactorPhysics.update_system
+// (reference: nuclear_simulator/systems/secondary/__init__.py:340-1021).
+// The heat-flow and chemistry-flow trackers (:668-744) are read-only aggregators that feed
+// nothing back into component state; their derived columns are not carried in PlantState.
+#pragma once
+#include "hd.h"
+#include "state.h"
+#include "feedwater.h"
+#include "sg.h"
+#include "turbine.h"
+#include "condenser.h"
+#include "ph_control.h"
+
+namespace nps {
+
+struct PrimaryConditions { double inlet_temp[3], outlet_temp[3], flow[3], thermal_power[3]; };
+
+// _saturation_temperature (Clausius-Clapeyron variant): systems/secondary/__init__.py:1455-1492
+NPS_HD double secondary_sat_temp(double p_mpa) {
+    if (p_mpa <= 0.001) return 10.0;
+    const double p_ref = 0.101325, t_ref = 100.0, h_fg = 2257.0, r_v = 0.4615;
+    double t_ref_k = t_ref + 273.15;
+    double ratio = p_mpa / p_ref;
+    double t;
+    if (ratio > 0) {
+        double tk = 1.0 / (1.0 / t_ref_k - (r_v / h_fg) * log(ratio));
+        t = tk - 273.15;
+    } else {
+        t = t_ref;
+    }
+    return np_clip(t, 10.0, 374.0);
+}
+
+NPS_HD void secondary_update(PlantState& st, const PlantParams& p, const PrimaryConditions& pc, double load_demand,
+                             double cooling_water_temp, double dt, const StepInput& in) {
+    SecondaryState& S = st.sec;
+    S.load_demand = load_demand;
+    S.feedwater_temperature = 227.0;
+    S.cooling_water_temperature = cooling_water_temp;
+    const double cooling_water_flow = 45000.0;
+
+    // feedwater-temperature smoothing: :384-398
+    if (!is_true(S.has_previous_feedwater_temp)) { S.has_previous_feedwater_temp = 1.0; S.previous_feedwater_temp = S.feedwater_temperature; }
+    const double estimated_fw_temp = 40.0 + 187.0;
+    const double alpha = 0.1;
+    double actual_fw_temp = (alpha * estimated_fw_temp + (1 - alpha) * S.previous_feedwater_temp);
+    S.previous_feedwater_temp = actual_fw_temp;
+
+    // thermal power / load fraction: :420-440 (sg_i_thermal_power keys take precedence)
+    double total_thermal_mw = 0.0 + pc.thermal_power[0]; total_thermal_mw += pc.thermal_power[1]; total_thermal_mw += pc.thermal_power[2];
+    double load_fraction = py_min(1.0, total_thermal_mw / 3000.0);
+    load_fraction = py_max(load_fraction, 0.2);
+    double est_flow_per_sg = 555.0 * load_fraction;
+    double est_total_flow = est_flow_per_sg * 3;
+    if (!is_true(S.has_previous_sg_conditions)) {
+        S.has_previous_sg_conditions = 1.0;
+        for (int i = 0; i < 3; ++i) {
+            S.prev_sg_levels[i] = 12.5; S.prev_sg_pressures[i] = 6.895;
+            S.prev_sg_steam_flows[i] = est_flow_per_sg; S.prev_sg_steam_qualities[i] = 0.99;
+        }
+    }
+    // STEP 1 feedwater: :445-491
+    FeedwaterResult fwr;
+    feedwater_update(st.fw, st.wc_main, p, S.prev_sg_levels, S.prev_sg_steam_flows, S.prev_sg_steam_qualities,
+                     est_total_flow, 40.0, 0.5, 7.4, dt, fwr);
+    // STEP 2 steam generators: :493-535 ('sg_i' keys are absent from sg_flow_distribution -> equal split)
+    double fw_flows[3];
+    for (int i = 0; i < 3; ++i) fw_flows[i] = fwr.total_flow_rate / 3;
+    sg_system_update(st.sgs, p, pc.inlet_temp, pc.outlet_temp, pc.flow, load_fraction, S.load_demand / 100.0,
+                     actual_fw_temp, fw_flows, dt * 60);
+    for (int i = 0; i < 3; ++i) {
+        S.prev_sg_levels[i] = st.sgs.sg[i].water_level;
+        S.prev_sg_pressures[i] = st.sgs.sg[i].secondary_pressure;
+        S.prev_sg_steam_flows[i] = st.sgs.sg[i].steam_flow_rate;
+        S.prev_sg_steam_qualities[i] = st.sgs.sg[i].steam_quality;
+    }
+    const double total_heat_transfer = st.sgs.total_thermal_power;
+    const double avg_p = st.sgs.average_steam_pressure;
+    double avg_t = st.sgs.average_steam_temperature;
+    avg_t = py_max(avg_t, secondary_sat_temp(avg_p));
+    double total_steam_flow = 0.0 + st.sgs.sg[0].steam_flow_rate; total_steam_flow += st.sgs.sg[1].steam_flow_rate;
+    total_steam_flow += st.sgs.sg[2].steam_flow_rate;
+
+    // STEP 5 turbine: :565-570
+    TurbineResult tr;
+    turbine_update(st.turb, p, st.sgs, S.load_demand, 0.007, dt / 60.0, tr);
+
+    // LP-6 exhaust quality: :591-607
+    double lp_quality = 0.90;
+    {
+        double h_f = cond_h_f(tr.condenser_pressure), h_g = cond_h_g(tr.condenser_pressure);
+        double h_fg = h_g - h_f;
+        if (h_fg > 0) {
+            lp_quality = (tr.lp6_outlet_enthalpy - h_f) / h_fg;
+            lp_quality = py_max(0.0, py_min(1.0, lp_quality));
+        }
+    }
+    CondenserResult cr;
+    condenser_update(st.cond, p, tr.condenser_pressure, tr.condenser_temperature, tr.effective_steam_flow, lp_quality,
+                     cooling_water_flow, S.cooling_water_temperature, 1.2, 185.0, dt / 60.0, cr);
+
+    S.total_feedwater_flow = fwr.total_flow_rate;
+    S.operating_hours += dt / 3600.0;
+
+    // chemistry: :634-665
+    const MakeupWater mk = {7.2, 100.0, 300.0, 30.0, 8.0};
+    wc_update(st.wc_main, true, mk, 0.02, dt);
+    ph_control_update(st.ph, st.wc_main.ph, dt, in.z_ph, in.u_ph);
+    wc_queue_effects(st.wc_main, st.ph.ph_setpoint, st.ph.ammonia_dose_rate, st.ph.morpholine_dose_rate);
+
+    S.total_steam_flow = total_steam_flow;
+    S.total_heat_transfer = total_heat_transfer;
+
+    // energy bookkeeping and electrical-power gating: :759-932
+    double primary_thermal = 0.0;
+    for (int i = 0; i < 3; ++i) primary_thermal += pc.thermal_power[i];
+    const double thermal_power_mw = primary_thermal;
+    const double turbine_electrical = tr.electrical_power_net;
+    S.total_system_heat_rejection = (primary_thermal - turbine_electrical) * 1e6;
+    const double actual_fw_flow = fwr.total_flow_rate;
+    double factor = 1.0;
+    if (actual_fw_flow < 300.0) factor = 0.0;
+    if (factor > 0.0) {
+        if (total_steam_flow < (300.0 * 0.5)) factor *= 0.1;
+        if (avg_p < (1.0 * 0.5)) factor *= 0.1;
+        if (thermal_power_mw > (primary_thermal * 1.1)) factor = 0.0;
+    }
+    S.power_reduction_factor = factor;
+    S.electrical_power_output = turbine_electrical * factor;
+    S.thermal_efficiency = (primary_thermal > 0) ? S.electrical_power_output / primary_thermal : 0.0;
+    S.heat_rate_kj_kwh = (S.electrical_power_output > 0)
+                             ? (total_heat_transfer / 1000.0) / (S.electrical_power_output * 1000.0) * 3600.0 : 0.0;
+    S.sg_avg_pressure = avg_p;
+    S.sg_avg_temperature = avg_t;
+    S.condenser_pressure = cr.condenser_pressure;
+}
+
+}  // namespace nps

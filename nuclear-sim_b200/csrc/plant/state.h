@@ -444,6 +444,77 @@ struct CondenserState {
     double vc_rotation_timer;
 };
 
+// ---- pH control --------------------------------------------------------------------------------
+// PHControllerState + PHController/PHControlSystem internals: secondary/ph_control_system.py:139-190,
+// 199-217, 521-532.  control_mode: 0 AUTO 1 MANUAL 2 FAILED 3 MAINTENANCE.
+// dev_hist is the sliding window of the last 100 |pH error| values (oldest at dev_head).
+struct PHControlState {
+    double control_mode;
+    double controller_enabled;
+    double manual_output;
+    double measured_ph;
+    double ph_setpoint;
+    double ph_error;
+    double controller_output;
+    double ammonia_dose_rate;
+    double morpholine_dose_rate;
+    double proportional_term;
+    double integral_term;
+    double derivative_term;
+    double previous_error;
+    double integral_sum;
+    double ammonia_tank_level;
+    double morpholine_tank_level;
+    double ammonia_supply_available;
+    double morpholine_supply_available;
+    double ammonia_pump_status;
+    double morpholine_pump_status;
+    double ph_sensor_status;
+    double ph_low_alarm;
+    double ph_high_alarm;
+    double low_chemical_alarm;
+    double equipment_failure_alarm;
+    double control_deviation_rms;
+    double chemical_consumption_rate;
+    double time_in_control;
+    double operating_hours;
+    double tic_initialized;
+    double tic_sum;
+    double tic_total_time;
+    double total_chemical_consumed;
+    double control_actions_count;
+    double dev_count;
+    double dev_head;
+    double dev_hist[100];
+};
+
+// ---- secondary system orchestrator -------------------------------------------------------------
+// SecondaryReactorPhysics members: systems/secondary/__init__.py:296-337,384-442
+struct SecondaryState {
+    double total_steam_flow;
+    double total_heat_transfer;
+    double electrical_power_output;
+    double thermal_efficiency;
+    double total_feedwater_flow;
+    double load_demand;
+    double feedwater_temperature;
+    double cooling_water_temperature;
+    double operating_hours;
+    double total_system_heat_rejection;
+    double has_previous_feedwater_temp;
+    double previous_feedwater_temp;
+    double has_previous_sg_conditions;
+    double prev_sg_levels[3];
+    double prev_sg_pressures[3];
+    double prev_sg_steam_flows[3];
+    double prev_sg_steam_qualities[3];
+    double sg_avg_pressure;
+    double sg_avg_temperature;
+    double condenser_pressure;
+    double heat_rate_kj_kwh;
+    double power_reduction_factor;
+};
+
 struct PlantState {
     PrimaryState pri;
     SimState sim;
@@ -452,6 +523,8 @@ struct PlantState {
     SGSystemState sgs;
     TurbineState turb;
     CondenserState cond;
+    PHControlState ph;
+    SecondaryState sec;
 };
 
 // ---- batch-uniform parameters ------------------------------------------------------------

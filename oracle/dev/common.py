@@ -15,8 +15,19 @@ def dvec(x):
     return np.ascontiguousarray(np.asarray(x, dtype=np.float64))
 
 
+def canonicalize(v):
+    """Rotate the pH deviation ring buffer so that its oldest entry sits at index 0 (representation only)."""
+    L = R._layout(); ix = L.field_index()
+    v = v.copy()
+    h = int(v[ix['ph.dev_head']]); b = ix['ph.dev_hist[0]']
+    if h:
+        v[b:b + 100] = np.roll(v[b:b + 100], -h); v[ix['ph.dev_head']] = 0.0
+    return v
+
+
 def compare(c, ref, prefix=None, tol=0.0, top=12, names=None):
     L = R._layout()
+    c = canonicalize(c); ref = canonicalize(ref)
     names = names or L.field_names()
     err = np.abs(c - ref) / np.maximum(np.abs(ref), 1e-300)
     err[c == ref] = 0.0

@@ -464,6 +464,59 @@ def condenser_params(cond, d):
             d[f"{a}[{i}]"] = float(getattr(ec, b))
 
 
+PH_MODE = {"AUTO": 0.0, "MANUAL": 1.0, "FAILED": 2.0, "MAINTENANCE": 3.0}
+
+
+def ph_control(ph, d):
+    P = "ph."
+    c = ph.controller
+    st = c.state
+    d[P + "control_mode"] = PH_MODE[st.control_mode.value]
+    for name in ("controller_enabled", "manual_output", "measured_ph", "ph_setpoint", "ph_error", "controller_output",
+                 "ammonia_dose_rate", "morpholine_dose_rate", "proportional_term", "integral_term", "derivative_term",
+                 "previous_error", "integral_sum", "ammonia_tank_level", "morpholine_tank_level",
+                 "ammonia_supply_available", "morpholine_supply_available", "ammonia_pump_status",
+                 "morpholine_pump_status", "ph_sensor_status", "ph_low_alarm", "ph_high_alarm", "low_chemical_alarm",
+                 "equipment_failure_alarm", "control_deviation_rms", "chemical_consumption_rate", "time_in_control",
+                 "operating_hours"):
+        d[P + name] = float(getattr(st, name))
+    assert not c._output_history
+    d[P + "tic_initialized"] = float(hasattr(c, "_time_in_control_sum"))
+    d[P + "tic_sum"] = float(getattr(c, "_time_in_control_sum", 0.0))
+    d[P + "tic_total_time"] = float(getattr(c, "_total_time", 0.0))
+    d[P + "total_chemical_consumed"] = float(ph.total_chemical_consumed)
+    d[P + "control_actions_count"] = float(ph.control_actions_count)
+    h = c._deviation_history
+    d[P + "dev_count"] = float(len(h))
+    d[P + "dev_head"] = 0.0
+    for i in range(100):
+        d[f"{P}dev_hist[{i}]"] = float(h[i]) if i < len(h) else 0.0
+
+
+def secondary(sec, d):
+    P = "sec."
+    for name in ("total_steam_flow", "total_heat_transfer", "electrical_power_output", "thermal_efficiency",
+                 "total_feedwater_flow", "load_demand", "feedwater_temperature", "cooling_water_temperature",
+                 "operating_hours", "total_system_heat_rejection"):
+        d[P + name] = float(getattr(sec, name))
+    d[P + "has_previous_feedwater_temp"] = float(hasattr(sec, "_previous_feedwater_temp"))
+    d[P + "previous_feedwater_temp"] = float(getattr(sec, "_previous_feedwater_temp", 0.0))
+    prev = getattr(sec, "_previous_sg_conditions", None)
+    d[P + "has_previous_sg_conditions"] = float(prev is not None)
+    for i in range(3):
+        d[f"{P}prev_sg_levels[{i}]"] = float(prev["levels"][i]) if prev else 0.0
+        d[f"{P}prev_sg_pressures[{i}]"] = float(prev["pressures"][i]) if prev else 0.0
+        d[f"{P}prev_sg_steam_flows[{i}]"] = float(prev["steam_flows"][i]) if prev else 0.0
+        d[f"{P}prev_sg_steam_qualities[{i}]"] = float(prev["steam_qualities"][i]) if prev else 0.0
+    last = getattr(sec, "_nps_last_result", None)
+    d[P + "sg_avg_pressure"] = float(last["sg_avg_pressure"]) if last else 0.0
+    d[P + "sg_avg_temperature"] = float(last["sg_avg_temperature"]) if last else 0.0
+    d[P + "condenser_pressure"] = float(last["condenser_pressure"]) if last else 0.0
+    d[P + "heat_rate_kj_kwh"] = float(last["heat_rate_kj_kwh"]) if last else 0.0
+    tnet = float(last["turbine_electrical_power_net"]) if last else 0.0
+    d[P + "power_reduction_factor"] = (float(last["electrical_power_mw"]) / tnet if tnet else (1.0 if not last else 0.0))
+
+
 def extract(sim, d):
     if not (sim.enable_secondary and sim.secondary_physics is not None):
         return
@@ -473,6 +526,8 @@ def extract(sim, d):
     steam_generators(sec.steam_generator_system, d)
     turbine(sec.turbine, d)
     condenser(sec.condenser, d)
+    ph_control(sec.ph_control_system, d)
+    secondary(sec, d)
 
 
 def extract_params(sim, d):

@@ -198,6 +198,15 @@ def make_reference_plant(config: Optional[dict] = None, *, dt: float = 5.0, heat
             sim.state = sim.primary_physics.state
         if power_setpoint is not None and heat_source == "constant":
             hs.set_power_setpoint(power_setpoint)
+    if enable_secondary:   # keep the last result dict so derived outputs can be extracted
+        sec = sim.secondary_physics
+        orig = sec.update_system
+
+        def _wrapped(*a, **k):
+            r = orig(*a, **k)
+            sec._nps_last_result = r
+            return r
+        sec.update_system = _wrapped
     return ReferencePlant(sim, heat_rng, ph_random)
 
 
