@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py — plant-steps/sec of the batched plant-dynamics hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Workload (config.workload): BASELINE config #3 — 65,536 plants PER GPU with randomised initial
+conditions, ReactorHeatSource at equilibrium, load-following / power-ramp rod actions plus the
+(inert) feedwater actions, dt = 1.0.  One bench "step" = ONE launch of the fused step kernel
+advancing every plant by SUBSTEPS (=8) timesteps, i.e. plants x 8 plant-steps.  Plants shard over
+ranks with no data-path collective (weak scaling); an NCCL all-gather of trajectory summaries runs
+after the timed region.
+
+value  : plant-steps/s with the per-step inputs already resident in HBM (CUDA events, max over ranks)
+e2e    : the same metric through the host-buffer C-ABI call (nps_step_host): pinned host inputs are
+         copied in and observation/reward/done copied out inside the timed region, every step
+roofline / cpu_baseline: see DESIGN.md §Measurement.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PLANTS_PER_GPU = 65536
+SUBSTEPS = 8
+FLOP_PER_PLANT_STEP = 2.0e4          # SURVEY.md §8d canonical figure (FP64 flop-equivalents)
+METRIC = "plant-steps/sec"
+UNIT = "plant-steps/s"
+WORKLOAD = ("cfg3: 65,536 plants per GPU, randomized ICs, reactor heat source, load-following/power-ramp "
+            "rod + feedwater actions, dt=1.0, 8 fused substeps per launch")
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.tmp,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        rows = [r.strip().split(", ") for r in open(self.tmp.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.tmp.name)
+        sm, reasons, mx = [], set(), None
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def cpu_baseline(steps_cpu: int = 4, threads: int = 1, target_seconds: float = 12.0):
+    """Host oracle (C port of the reference step, oracle/cpu_port.cpp) on a bounded sample of the same workload."""
+    import ctypes
+    from concurrent.futures import ThreadPoolExecutor
+    from nuclear_sim_b200 import load_snapshot
+    from nuclear_sim_b200 import scenarios as sc
+    from tests import _util as U
+    L = U.oracle_lib()
+    s0, params = load_snapshot("pwr3000_reactor_dt1")
+    params = np.ascontiguousarray(params)
+    # calibrate on a small sample, then size the timed sample for ~target_seconds of work
+    n_cal = 64 * threads
+    pid = np.arange(n_cal)
+
+    def run(pid, k):
+        st = np.ascontiguousarray(sc.randomized_states(s0, pid))
+        acts, mags = sc.load_following_inputs(pid, 0, k)
+        noise = sc.noise_inputs(pid, 0, k)
+        a = np.ascontiguousarray(acts.T); m = np.ascontiguousarray(mags.T)
+        z = np.ascontiguousarray(noise.transpose(2, 0, 1))      # [n, k, 5]
+        chunks = np.array_split(np.arange(len(pid)), threads)
+
+        def work(c):
+            if len(c) == 0:
+                return
+            lo, hi = c[0], c[-1] + 1
+            L.nps_oracle_step(U.ptr(st[lo:hi]), U.ptr(params), U.ptr(a[lo:hi]), U.ptr(m[lo:hi]), U.ptr(z[lo:hi]),
+                              ctypes.c_int64(hi - lo), int(k))
+        t = time.perf_counter()
+        if threads == 1:
+            work(chunks[0])
+        else:
+            with ThreadPoolExecutor(threads) as ex:
+                list(ex.map(work, chunks))
+        return time.perf_counter() - t
+    tcal = run(pid, steps_cpu)
+    rate = n_cal * steps_cpu / tcal
+    n = int(max(n_cal, min(PLANTS_PER_GPU, rate * target_seconds / steps_cpu)))
+    n -= n % threads
+    el = run(np.arange(n), steps_cpu)
+    return {"value": n * steps_cpu / el, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n} plants x {steps_cpu} steps of the cfg3 workload ({el:.1f} s), oracle/cpu_port.cpp (C restatement "
+                      f"of the reference step; the Python reference itself cannot travel to this box)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    vals = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_baseline(steps_cpu=SUBSTEPS, threads=threads, target_seconds=max(2.0, 60.0 / max(1, args.warmup + args.steps)))
+        if i >= args.warmup:
+            vals.append(r)
+    v = float(np.mean([r["value"] for r in vals]))
+    n_plants = int(vals[-1]["sample"].split(" plants")[0])
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * n_plants * SUBSTEPS / v, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "plants_per_step_sample": n_plants, "substeps_per_step": SUBSTEPS},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": vals[-1]["sample"]},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--plants-per-gpu", type=int, default=PLANTS_PER_GPU)
+    ap.add_argument("--substeps", type=int, default=SUBSTEPS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from nuclear_sim_b200 import BatchedNuclearPlantSimulator, N_STATE, load_snapshot
+    from nuclear_sim_b200 import scenarios as sc
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(3, args.warmup)
+    K = args.steps
+    n = args.plants_per_gpu
+    ksub = args.substeps
+
+    s0, params = load_snapshot("pwr3000_reactor_dt1")
+    pid = np.arange(rank * n, (rank + 1) * n)
+    sim = BatchedNuclearPlantSimulator(n, sc.randomized_states(s0, pid), params, device=str(dev))
+    state_bytes = sim.slab.numel() * 8
+
+    # per-step inputs for every warm-up and timed step (distinct per step), resident in HBM and mirrored in pinned host memory
+    total = W + K
+    acts_h = torch.empty((total, ksub, n), dtype=torch.int8).pin_memory()
+    mags_h = torch.empty((total, ksub, n), dtype=torch.float64).pin_memory()
+    noise_h = torch.empty((total, ksub, 5, n), dtype=torch.float64).pin_memory()
+    for i in range(total):
+        a, m = sc.load_following_inputs(pid, i * ksub, ksub)
+        acts_h[i] = torch.from_numpy(a); mags_h[i] = torch.from_numpy(m)
+        noise_h[i] = torch.from_numpy(sc.noise_inputs(pid, i * ksub, ksub))
+    acts_d, mags_d, noise_d = acts_h.to(dev), mags_h.to(dev), noise_h.to(dev)
+    obs_h = torch.empty((22, n), dtype=torch.float64).pin_memory()
+    rew_h = torch.empty(n, dtype=torch.float64).pin_memory()
+    done_h = torch.empty(n, dtype=torch.uint8).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ------------------------------------------------------------------ device-resident arm (value)
+    for i in range(W):
+        sim.step(actions=acts_d[i], magnitudes=mags_d[i], noise=noise_d[i], K=ksub)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    launches0 = sim.n_launches
+    barrier()
+    ev[0].record()
+    for i in range(K):
+        sim.step(actions=acts_d[W + i], magnitudes=mags_d[W + i], noise=noise_d[W + i], K=ksub)
+        ev[i + 1].record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = sim.n_launches - launches0
+    t_total_ms = ev[0].elapsed_time(ev[K])
+    per_launch_ms = np.array([ev[i].elapsed_time(ev[i + 1]) for i in range(K)])
+    t = torch.tensor([t_total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_ms = float(t.item())
+    value = world * n * ksub * K / (t_ms * 1e-3)
+
+    # ------------------------------------------------------------------ end-to-end arm (host buffers through the C ABI)
+    sim.reset()
+    for i in range(W):
+        sim.step_host(acts_h[i], mags_h[i], noise_h[i], None, ksub, obs_h, rew_h, done_h)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        sim.step_host(acts_h[W + i], mags_h[W + i], noise_h[W + i], None, ksub, obs_h, rew_h, done_h)
+    e1.record()
+    barrier()
+    te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * ksub * K / (float(te.item()) * 1e-3)
+    h2d = ksub * n * (1 + 8 + 5 * 8)
+    d2h = n * (22 * 8 + 8 + 1)
+    loss_check = float(rew_h.mean())
+
+    # ------------------------------------------------------------------ trajectory summaries: the only collective
+    summary = torch.stack([sim.state.power_level, sim.state.electrical_power_output, sim.state.fuel_temperature,
+                           sim.state.scram_status]).t().contiguous()
+    if world > 1:
+        gathered = [torch.empty_like(summary) for _ in range(world)]
+        dist.all_gather(gathered, summary)
+        summary = torch.cat(gathered)
+    mean_power = float(summary[:, 0].mean())
+
+    if rank == 0:
+        peak, peak_src = _peaks()
+        # algorithmic bytes of one launch: state slab read + written once, per-substep inputs read, outputs written
+        bytes_per_launch = 2 * state_bytes + ksub * n * (1 + 8 + 40) + n * (22 * 8 + 8 + 1)
+        avg_launch_s = float(per_launch_ms.mean()) * 1e-3
+        achieved = bytes_per_launch / avg_launch_s / 1e9
+        fp64_tflops = n * ksub * FLOP_PER_PLANT_STEP / avg_launch_s / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": t_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "plants_per_gpu": n, "substeps_per_step": ksub, "n_state_fields": N_STATE,
+                       "state_bytes_per_gpu": state_bytes,
+                       "l2": "inputs larger than L2 (state slab %.0f MB per GPU is streamed every launch)" % (state_bytes / 1e6),
+                       "mean_power_percent_after_run": mean_power},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "mean_reward_readback": loss_check},
+            "gpu_launches": launches,
+            "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
+                       "samples": clocks["samples"]},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "nps_step_kernel",
+                         "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_launch_s * 1e3,
+                         "fp64_tflops_at_2e4_flop_per_plant_step": fp64_tflops},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

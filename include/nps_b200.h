@@ -1,0 +1,99 @@
+/* nps_b200 — C ABI of the B200-native batched plant-dynamics engine.
+ *
+ * Drop-in boundary for the per-timestep hot path of NuclearnAI/nuclear-sim:
+ *   NuclearPlantSimulator.step()            nuclear_simulator/simulator/core/sim.py:130-258
+ *   get_observation() / calculate_reward()  nuclear_simulator/simulator/core/sim.py:290-333, 500-544
+ *   StateManager threshold monitoring       nuclear_simulator/simulator/state/state_manager.py:1307-1369
+ *   StateManager row collection / export    nuclear_simulator/simulator/state/state_manager.py:152-233
+ * The reference has no FFI of its own (it is pure Python); these are the entry points a ctypes
+ * binding on the reference side would call.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; the CALLER owns every buffer, the library borrows it for the call;
+ *   - plant state is one FP64 structure-of-arrays slab in device memory: field f of plant p is
+ *     slab[f * n_plants + p]; field order = struct PlantState in nuclear-sim_b200/csrc/plant/state.h
+ *     (nps_field_name(i) returns the flat name of field i);
+ *   - device entry points are asynchronous on the given CUDA stream (cudaStream_t passed as void*),
+ *     no hidden synchronisation; *_host entry points take host buffers and synchronise;
+ *   - return 0 on success, negative on error (nps_last_error() gives the message);
+ *   - one handle per device per process; a handle is not thread-safe.
+ */
+#ifndef NPS_B200_H
+#define NPS_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nps_handle nps_handle;
+
+#define NPS_ABI_VERSION 1
+#define NPS_OBS_DIM 22          /* get_observation(): 12 primary + 6 secondary + 4 feedwater (sim.py:290-333) */
+#define NPS_NOISE_PER_STEP 5    /* z_heat, z_ph, u_ph[3] (constant_heat_source.py:178; ph_control_system.py:278-420) */
+
+int nps_abi_version(void);
+const char* nps_last_error(void);
+
+/* layout introspection (PlantState / PlantParams of csrc/plant/state.h) */
+int nps_n_state(void);
+int nps_n_params(void);
+const char* nps_field_name(int field);        /* e.g. "fw.pump[0].lub.oil_level" */
+const char* nps_param_name(int param);
+
+/* lifetime: replaces NuclearPlantSimulator.__init__ for n_plants plants (sim.py:30-87) */
+int nps_create(int64_t n_plants, int device, nps_handle** out);
+void nps_destroy(nps_handle* h);
+int64_t nps_n_plants(const nps_handle* h);
+
+/* batch-uniform parameters (config dataclasses of systems/secondary/<subsystem>/config.py); host array of nps_n_params() */
+int nps_set_params(nps_handle* h, const double* params_host, int n_params);
+
+/* One launch = k_substeps calls of NuclearPlantSimulator.step() for every plant (sim.py:130-258).
+ *   d_state      [n_state][n_plants]            in/out
+ *   d_action     [k_substeps][n_plants] int8    ControlAction values (primary/__init__.py:28-45), may be NULL = NO_ACTION
+ *   d_magnitude  [k_substeps][n_plants]         may be NULL = 1.0
+ *   d_noise      [k_substeps][5][n_plants]      host-supplied random streams, may be NULL = (0,0,1,1,1)
+ *   d_setpoint   [k_substeps][n_plants]         heat_source.set_power_setpoint(%) applied before each substep
+ *                                               (maintenance_scenario_runner.py:651-671); NaN entries / NULL = unchanged
+ *   d_obs        [22][n_plants]   observation after the last substep, may be NULL
+ *   d_reward     [n_plants]       calculate_reward after the last substep, may be NULL
+ *   d_done       [n_plants] uint8 1 if a scram was activated in any substep of this launch, may be NULL */
+int nps_step(nps_handle* h, double* d_state, const int8_t* d_action, const double* d_magnitude,
+             const double* d_noise, const double* d_setpoint, int k_substeps, double* d_obs, double* d_reward,
+             uint8_t* d_done, void* cuda_stream);
+
+/* Same step with HOST buffers for the per-step inputs and outputs (pinned or pageable): the
+ * host->device copies of action/magnitude/noise and the device->host copies of obs/reward/done are
+ * issued on the stream inside the call, which returns after they complete. State stays on device. */
+int nps_step_host(nps_handle* h, double* d_state, const int8_t* h_action, const double* h_magnitude,
+                  const double* h_noise, const double* h_setpoint, int k_substeps, double* h_obs, double* h_reward,
+                  uint8_t* h_done, void* cuda_stream);
+
+/* get_observation()/calculate_reward() of the current state without stepping */
+int nps_observe(nps_handle* h, const double* d_state, double* d_obs, double* d_reward, void* cuda_stream);
+
+/* --- threshold monitoring (StateManager._check_maintenance_thresholds, state_manager.py:1307-1369) ---
+ * A threshold row is (field, comparator, value, cooldown_minutes); comparator: 0 '>', 1 '<', 2 '>=', 3 '<=', 4 '=='(±1e-3).
+ * d_last_fired [n_thresholds][n_plants] holds the time (minutes) each threshold last fired (-inf = never).
+ * Output: d_flags [n_words][n_plants] uint32 bit t%32 of word t/32 set when threshold t fired at time
+ * now; d_any_warp [ceil(n_plants/32)] uint32 = warp ballot of "plant has any flag" (host drain index). */
+int nps_set_thresholds(nps_handle* h, const int32_t* field, const int32_t* comparator, const double* value,
+                       const double* cooldown_minutes, int n_thresholds);
+int nps_check_thresholds(nps_handle* h, const double* d_state, double* d_last_fired, uint32_t* d_flags,
+                         uint32_t* d_any_warp, void* cuda_stream);
+
+/* --- trajectory ring buffer (StateManager.collect_states/_add_row, state_manager.py:152-233) ---
+ * Appends the selected fields of every plant as row (write_index % ring_rows) of
+ * d_ring [ring_rows][n_logged][n_plants]; staged through shared memory so both the gather from the
+ * state slab and the row store are coalesced. */
+int nps_set_logged_fields(nps_handle* h, const int32_t* fields, int n_logged);
+int nps_log_row(nps_handle* h, const double* d_state, double* d_ring, int64_t ring_rows, int64_t write_index,
+                void* cuda_stream);
+
+/* gather selected fields of all plants to a host array out[n_fields][n_plants] (synchronous) */
+int nps_read_fields(nps_handle* h, const double* d_state, const int32_t* fields, int n_fields, double* out_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

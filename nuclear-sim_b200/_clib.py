@@ -1,0 +1,68 @@
+"""ctypes binding of the C ABI in include/nps_b200.h (libnps_b200.so, built in-tree).
+
+There is no CPU fallback: importing this module without the built library, or creating a handle
+without a CUDA device, raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_uint8, c_uint32, c_void_p
+
+from . import _build
+
+_LIB = None
+
+
+class NpsError(RuntimeError):
+    pass
+
+
+def lib() -> ctypes.CDLL:
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.LIB_PATH
+    if not os.path.exists(path):
+        raise NpsError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(nvcc, sm_100a). nuclear_sim_b200 has no CPU fallback.")
+    L = ctypes.CDLL(path)
+    L.nps_abi_version.restype = c_int
+    L.nps_last_error.restype = c_char_p
+    L.nps_n_state.restype = c_int
+    L.nps_n_params.restype = c_int
+    L.nps_field_name.restype = c_char_p
+    L.nps_field_name.argtypes = [c_int]
+    L.nps_param_name.restype = c_char_p
+    L.nps_param_name.argtypes = [c_int]
+    L.nps_create.argtypes = [c_int64, c_int, POINTER(c_void_p)]
+    L.nps_destroy.argtypes = [c_void_p]
+    L.nps_destroy.restype = None
+    L.nps_n_plants.argtypes = [c_void_p]
+    L.nps_n_plants.restype = c_int64
+    L.nps_set_params.argtypes = [c_void_p, c_void_p, c_int]
+    L.nps_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                           c_void_p, c_void_p]
+    L.nps_step_host.argtypes = L.nps_step.argtypes
+    L.nps_observe.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.nps_set_thresholds.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int]
+    L.nps_check_thresholds.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.nps_set_logged_fields.argtypes = [c_void_p, c_void_p, c_int]
+    L.nps_log_row.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]
+    L.nps_read_fields.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p]
+    if L.nps_abi_version() != 1:
+        raise NpsError("libnps_b200.so ABI version mismatch")
+    _LIB = L
+    return L
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise NpsError(lib().nps_last_error().decode())
+
+
+EXPORTED_SYMBOLS = [
+    "nps_abi_version", "nps_last_error", "nps_n_state", "nps_n_params", "nps_field_name", "nps_param_name",
+    "nps_create", "nps_destroy", "nps_n_plants", "nps_set_params", "nps_step", "nps_step_host", "nps_observe",
+    "nps_set_thresholds", "nps_check_thresholds", "nps_set_logged_fields", "nps_log_row", "nps_read_fields",
+]

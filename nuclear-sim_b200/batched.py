@@ -1,0 +1,256 @@
+"""BatchedNuclearPlantSimulator — N independent plants advanced in lockstep on one B200.
+
+Keeps the step()/state/action semantics of the reference ``NuclearPlantSimulator``
+(nuclear_simulator/simulator/core/sim.py:27-258) with a leading plant axis:
+
+    sim = BatchedNuclearPlantSimulator(n_plants, initial_state, params, device="cuda:0")
+    out = sim.step(actions, magnitudes, noise=noise)         # dict of tensors
+    sim.state.power_level                                     # Tensor[N] view into the SoA slab
+
+PyTorch is used for device memory, streams and (in bench.py) torch.distributed only; all physics
+runs in the hand-written CUDA step kernel behind the C ABI (include/nps_b200.h).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _clib
+from ._layout import N_PARAMS, N_STATE, field_index, field_names
+
+OBS_DIM = 22
+NOISE_PER_STEP = 5
+NO_ACTION = 8   # ControlAction.NO_ACTION (systems/primary/__init__.py:37)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class _StateView:
+    """``sim.state.<field>`` -> Tensor[N] view (ReactorState attribute names map to the ``pri.`` block)."""
+
+    def __init__(self, sim: "BatchedNuclearPlantSimulator"):
+        object.__setattr__(self, "_sim", sim)
+
+    def _resolve(self, name: str) -> int:
+        ix = field_index()
+        for cand in (name, "pri." + name, "sec." + name, "sim." + name):
+            if cand in ix:
+                return ix[cand]
+        raise AttributeError(name)
+
+    def __getattr__(self, name: str) -> torch.Tensor:
+        return self._sim.slab[self._resolve(name)]
+
+    def __setattr__(self, name: str, value) -> None:
+        self._sim.slab[self._resolve(name)] = torch.as_tensor(value, dtype=torch.float64, device=self._sim.device)
+
+    def __getitem__(self, name: str) -> torch.Tensor:
+        return self._sim.slab[field_index()[name]]
+
+
+class _HeatSourceView:
+    """``sim.primary_physics.heat_source.set_power_setpoint`` (constant_heat_source.py:94-102), batched."""
+
+    def __init__(self, sim):
+        self._sim = sim
+
+    def set_power_setpoint(self, power_percent) -> None:
+        sim = self._sim
+        sp = torch.clamp(torch.as_tensor(power_percent, dtype=torch.float64, device=sim.device).expand(sim.n_plants), 0.0, 150.0)
+        ix = field_index()
+        sim.slab[ix["pri.hs_setpoint_percent"]] = sp
+        sim.slab[ix["pri.hs_current_power_mw"]] = (sp / 100.0) * float(sim.params[field_index("PlantParams")["rated_power_mw"]])
+
+
+class BatchedNuclearPlantSimulator:
+    def __init__(self, n_plants: int, initial_state: np.ndarray, params: np.ndarray, device: str = "cuda:0"):
+        if not torch.cuda.is_available():
+            raise _clib.NpsError("BatchedNuclearPlantSimulator needs a CUDA device (no CPU fallback)")
+        self.device = torch.device(device)
+        self.n_plants = int(n_plants)
+        self.L = _clib.lib()
+        if self.L.nps_n_state() != N_STATE or self.L.nps_n_params() != N_PARAMS:
+            raise _clib.NpsError("libnps_b200.so was built from a different state.h; rebuild")
+        initial_state = np.asarray(initial_state, dtype=np.float64)
+        if initial_state.ndim == 1:
+            initial_state = np.broadcast_to(initial_state[None, :], (self.n_plants, N_STATE))
+        if initial_state.shape != (self.n_plants, N_STATE):
+            raise ValueError(f"initial_state must be [{N_STATE}] or [{self.n_plants}, {N_STATE}]")
+        self.params = np.ascontiguousarray(np.asarray(params, dtype=np.float64))
+        if self.params.shape != (N_PARAMS,):
+            raise ValueError(f"params must be [{N_PARAMS}]")
+        self.dt = float(self.params[field_index("PlantParams")["dt"]])
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        with torch.cuda.device(dev_index):
+            # SoA slab: field-major [n_state, n_plants]
+            self.slab = torch.from_numpy(np.ascontiguousarray(initial_state.T)).to(self.device)
+            self._initial = self.slab.clone()
+            h = ctypes.c_void_p()
+            _clib.check(self.L.nps_create(self.n_plants, dev_index, ctypes.byref(h)))
+            self._h = h
+            _clib.check(self.L.nps_set_params(self._h, self.params.ctypes.data_as(ctypes.c_void_p), N_PARAMS))
+            self._obs = torch.empty((OBS_DIM, self.n_plants), dtype=torch.float64, device=self.device)
+            self._reward = torch.empty(self.n_plants, dtype=torch.float64, device=self.device)
+            self._done = torch.empty(self.n_plants, dtype=torch.uint8, device=self.device)
+        self.state = _StateView(self)
+        self.heat_source = _HeatSourceView(self)
+        self.n_launches = 0
+        self._thr = None
+        self._logged = None
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                self.L.nps_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    # -- stepping -----------------------------------------------------------------------------
+    def _prep(self, x, dtype, k, inner=None):
+        if x is None:
+            return None
+        t = torch.as_tensor(x, dtype=dtype, device=self.device)
+        shape = (k, self.n_plants) if inner is None else (k, inner, self.n_plants)
+        if t.dim() == len(shape) - 1:
+            t = t.unsqueeze(0)
+        if tuple(t.shape) != shape:
+            t = t.expand(shape)
+        return t.contiguous()
+
+    def step(self, actions=None, magnitudes=None, noise=None, power_setpoint=None, K: int = 1) -> Dict[str, torch.Tensor]:
+        """K fused calls of NuclearPlantSimulator.step (sim.py:130-258) for every plant.
+
+        actions [K,N] or [N] int8 (ControlAction values; None = NO_ACTION); magnitudes [K,N] f64;
+        noise [K,5,N] f64 = (z_heat, z_ph, u0, u1, u2) host-supplied streams; power_setpoint [K,N] (NaN = keep).
+        Returns observation [N,22], reward [N], done [N] (bool) of the last substep.
+        """
+        a = self._prep(actions, torch.int8, K)
+        m = self._prep(magnitudes, torch.float64, K)
+        z = self._prep(noise, torch.float64, K, NOISE_PER_STEP)
+        sp = self._prep(power_setpoint, torch.float64, K)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _clib.check(self.L.nps_step(self._h, _ptr(self.slab), _ptr(a), _ptr(m), _ptr(z), _ptr(sp), int(K),
+                                    _ptr(self._obs), _ptr(self._reward), _ptr(self._done), ctypes.c_void_p(stream)))
+        self.n_launches += 1
+        return {"observation": self._obs.t(), "reward": self._reward, "done": self._done.bool()}
+
+    def step_host(self, h_actions, h_magnitudes, h_noise, h_setpoint, K, h_obs, h_reward, h_done) -> None:
+        """Reference-facing call with HOST (pinned) per-step buffers: copies in, K substeps, copies out."""
+        def hp(t):
+            return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _clib.check(self.L.nps_step_host(self._h, _ptr(self.slab), hp(h_actions), hp(h_magnitudes), hp(h_noise),
+                                         hp(h_setpoint), int(K), hp(h_obs), hp(h_reward), hp(h_done),
+                                         ctypes.c_void_p(stream)))
+        self.n_launches += 1
+
+    def get_observation(self) -> torch.Tensor:
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _clib.check(self.L.nps_observe(self._h, _ptr(self.slab), _ptr(self._obs), _ptr(self._reward), ctypes.c_void_p(stream)))
+        self.n_launches += 1
+        return self._obs.t()
+
+    def reset(self, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if mask is None:
+            self.slab.copy_(self._initial)
+        else:
+            m = torch.as_tensor(mask, dtype=torch.bool, device=self.device)
+            self.slab[:, m] = self._initial[:, m]
+        return self.get_observation()
+
+    # -- state access -------------------------------------------------------------------------
+    def state_numpy(self) -> np.ndarray:
+        """[n_plants, n_state] host copy in PlantState field order."""
+        return self.slab.t().contiguous().cpu().numpy()
+
+    def read_fields(self, names: Sequence[str]) -> np.ndarray:
+        ix = field_index()
+        ids = np.array([ix[n] for n in names], dtype=np.int32)
+        out = np.empty((len(ids), self.n_plants), dtype=np.float64)
+        _clib.check(self.L.nps_read_fields(self._h, _ptr(self.slab), ids.ctypes.data_as(ctypes.c_void_p), len(ids),
+                                           out.ctypes.data_as(ctypes.c_void_p)))
+        return out
+
+    # -- threshold monitoring (state_manager.py:1307-1369) --------------------------------------
+    def set_thresholds(self, rows) -> None:
+        """rows: iterable of (field_name_or_None, comparator, value, cooldown_hours)."""
+        cmp_code = {">": 0, "greater_than": 0, "<": 1, "less_than": 1, ">=": 2, "greater_equal": 2,
+                    "<=": 3, "less_equal": 3, "==": 4, "equals": 4}
+        ix = field_index()
+        rows = list(rows)
+        f = np.array([ix[r[0]] if r[0] is not None else -1 for r in rows], dtype=np.int32)
+        c = np.array([cmp_code[r[1]] for r in rows], dtype=np.int32)
+        v = np.array([r[2] for r in rows], dtype=np.float64)
+        cd = np.array([r[3] * 60.0 for r in rows], dtype=np.float64)
+        _clib.check(self.L.nps_set_thresholds(self._h, f.ctypes.data_as(ctypes.c_void_p), c.ctypes.data_as(ctypes.c_void_p),
+                                              v.ctypes.data_as(ctypes.c_void_p), cd.ctypes.data_as(ctypes.c_void_p), len(rows)))
+        n = len(rows)
+        self._thr = {
+            "n": n,
+            "last": torch.full((n, self.n_plants), -float("inf"), dtype=torch.float64, device=self.device),
+            "flags": torch.zeros(((n + 31) // 32, self.n_plants), dtype=torch.int32, device=self.device),
+            "any": torch.zeros(((self.n_plants + 31) // 32,), dtype=torch.int32, device=self.device),
+        }
+
+    def check_thresholds(self):
+        """Returns (flags [n_words, N] int32 bitmask tensor, any_warp [ceil(N/32)] int32 ballot words)."""
+        t = self._thr
+        if t is None:
+            raise _clib.NpsError("set_thresholds() first")
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _clib.check(self.L.nps_check_thresholds(self._h, _ptr(self.slab), _ptr(t["last"]), _ptr(t["flags"]), _ptr(t["any"]),
+                                                ctypes.c_void_p(stream)))
+        self.n_launches += 1
+        return t["flags"], t["any"]
+
+    def drain_events(self):
+        """Host drain: list of (plant, threshold_index) that fired in the last check_thresholds()."""
+        t = self._thr
+        anyw = t["any"].cpu().numpy().view(np.uint32)
+        if not anyw.any():
+            return []
+        flags = t["flags"].cpu().numpy().view(np.uint32)
+        ev = []
+        for w in np.nonzero(anyw)[0]:
+            for lane in range(32):
+                if anyw[w] >> lane & 1:
+                    p = int(w) * 32 + lane
+                    for word in range(flags.shape[0]):
+                        bits = int(flags[word, p])
+                        while bits:
+                            b = (bits & -bits).bit_length() - 1
+                            ev.append((p, word * 32 + b))
+                            bits &= bits - 1
+        return ev
+
+    # -- trajectory ring buffer (state_manager.py:152-233) --------------------------------------
+    def set_logged_fields(self, names: Sequence[str], ring_rows: int) -> None:
+        ix = field_index()
+        ids = np.array([ix[n] for n in names], dtype=np.int32)
+        _clib.check(self.L.nps_set_logged_fields(self._h, ids.ctypes.data_as(ctypes.c_void_p), len(ids)))
+        self._logged = {"names": list(names), "rows": int(ring_rows), "n": 0,
+                        "ring": torch.empty((ring_rows, len(ids), self.n_plants), dtype=torch.float64, device=self.device)}
+
+    def log_row(self) -> None:
+        g = self._logged
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _clib.check(self.L.nps_log_row(self._h, _ptr(self.slab), _ptr(g["ring"]), g["rows"], g["n"], ctypes.c_void_p(stream)))
+        g["n"] += 1
+        self.n_launches += 1
+
+    def drain_log(self) -> np.ndarray:
+        """[rows_available, n_logged, n_plants] oldest-first host copy of the ring buffer."""
+        g = self._logged
+        n, rows = g["n"], g["rows"]
+        ring = g["ring"].cpu().numpy()
+        if n <= rows:
+            return ring[:n]
+        start = n % rows
+        return np.concatenate([ring[start:], ring[:start]], axis=0)

@@ -1,0 +1,369 @@
+// nps_b200: CUDA kernels (sm_100a) and the C ABI declared in include/nps_b200.h.
+//
+// Execution model: plants are independent, so the step path is pure data parallelism — one
+// thread advances one plant through k fused substeps.  Plant state lives in HBM as an FP64
+// structure-of-arrays slab (field-major), so every load/store of a field by a warp is one fully
+// coalesced 256-byte transaction.  There is no dense contraction anywhere on this path: no tensor
+// cores, the bounds are the FP64 pipe and HBM.
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <cmath>
+
+#include "../../include/nps_b200.h"
+#include "plant/plant_step.h"
+#include "fields_gen.inc"
+
+using namespace nps;
+
+static thread_local std::string g_last_error;
+static int fail(const char* what, cudaError_t e = cudaSuccess) {
+    g_last_error = what;
+    if (e != cudaSuccess) { g_last_error += ": "; g_last_error += cudaGetErrorString(e); }
+    return -1;
+}
+#define NPS_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail(#call, e__); } while (0)
+
+constexpr int kNState = (int)(sizeof(PlantState) / sizeof(double));
+constexpr int kNParams = (int)(sizeof(PlantParams) / sizeof(double));
+static_assert(kNState == NPS_GEN_N_STATE, "state.h and fields_gen.inc disagree; rerun the build");
+static_assert(kNParams == NPS_GEN_N_PARAMS, "state.h and fields_gen.inc disagree; rerun the build");
+
+struct Threshold { int field; int cmp; double value; double cooldown; };
+
+struct nps_handle {
+    int64_t n = 0;
+    int device = 0;
+    PlantParams params;
+    // staging buffers for nps_step_host
+    int8_t* d_action = nullptr; double* d_mag = nullptr; double* d_noise = nullptr; double* d_setpoint = nullptr;
+    double* d_obs = nullptr; double* d_reward = nullptr; uint8_t* d_done = nullptr;
+    int staged_k = 0;
+    Threshold* d_thresholds = nullptr; int n_thresholds = 0;
+    int32_t* d_logged = nullptr; int n_logged = 0;
+    int32_t* d_gather_fields = nullptr; double* d_gather_out = nullptr; int gather_cap = 0;
+};
+
+// ------------------------------------------------------------------------------------------------
+// step kernel: thread-per-plant, state register/local resident across k substeps
+// ------------------------------------------------------------------------------------------------
+constexpr int kStepBlock = 64;
+
+__global__ void __launch_bounds__(kStepBlock)
+nps_step_kernel(double* __restrict__ slab, const __grid_constant__ PlantParams prm, const int8_t* __restrict__ action,
+                const double* __restrict__ magnitude, const double* __restrict__ noise,
+                const double* __restrict__ setpoint, int k_substeps, int64_t n,
+                double* __restrict__ obs, double* __restrict__ reward, uint8_t* __restrict__ done) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    PlantState st;
+    double* sv = reinterpret_cast<double*>(&st);
+#pragma unroll 8
+    for (int f = 0; f < kNState; ++f) sv[f] = slab[(int64_t)f * n + p];
+    bool scrammed = false;
+    for (int k = 0; k < k_substeps; ++k) {
+        StepInput in;
+        in.action = action ? (int)action[(int64_t)k * n + p] : (int)ACT_NO_ACTION;
+        in.magnitude = magnitude ? magnitude[(int64_t)k * n + p] : 1.0;
+        if (noise) {
+            const double* z = noise + (int64_t)k * NPS_NOISE_PER_STEP * n + p;
+            in.z_heat = z[0]; in.z_ph = z[n]; in.u_ph[0] = z[2 * n]; in.u_ph[1] = z[3 * n]; in.u_ph[2] = z[4 * n];
+        } else {
+            in.z_heat = 0.0; in.z_ph = 0.0; in.u_ph[0] = 1.0; in.u_ph[1] = 1.0; in.u_ph[2] = 1.0;
+        }
+        in.power_setpoint = setpoint ? setpoint[(int64_t)k * n + p] : NAN;
+        plant_step(st, prm, in);
+        scrammed |= is_true(st.pri.scram_activated);
+    }
+#pragma unroll 8
+    for (int f = 0; f < kNState; ++f) slab[(int64_t)f * n + p] = sv[f];
+    if (obs) {
+        struct ObsOut { double* o; int64_t n; int64_t p; struct Ref { double* a; NPS_HD void operator=(double v) { *a = v; } };
+                        __device__ Ref operator[](int i) { return Ref{o + (int64_t)i * n + p}; } } out{obs, n, p};
+        plant_observe(st, prm, out);
+    }
+    if (reward) reward[p] = plant_reward(st, prm);
+    if (done) done[p] = scrammed ? 1 : 0;
+}
+
+template <class T>
+__device__ __forceinline__ void load_member(T& dst, const PlantState& base, const double* __restrict__ slab, int64_t n, int64_t p) {
+    const int f0 = (int)(reinterpret_cast<const double*>(&dst) - reinterpret_cast<const double*>(&base));
+    double* d = reinterpret_cast<double*>(&dst);
+    for (int f = 0; f < (int)(sizeof(T) / sizeof(double)); ++f) d[f] = slab[(int64_t)(f0 + f) * n + p];
+}
+
+__global__ void nps_observe_kernel(const double* __restrict__ slab, const __grid_constant__ PlantParams prm, int64_t n,
+                                   double* __restrict__ obs, double* __restrict__ reward) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    PlantState st;   // only the members read by plant_observe / plant_reward are loaded
+    load_member(st.pri, st, slab, n, p);
+    load_member(st.sim, st, slab, n, p);
+    load_member(st.sec, st, slab, n, p);
+    load_member(st.fw.total_flow_rate, st, slab, n, p);
+    load_member(st.fw.total_power_consumption, st, slab, n, p);
+    load_member(st.fw.system_availability, st, slab, n, p);
+    if (obs) {
+        struct ObsOut { double* o; int64_t n; int64_t p; struct Ref { double* a; NPS_HD void operator=(double v) { *a = v; } };
+                        __device__ Ref operator[](int i) { return Ref{o + (int64_t)i * n + p}; } } out{obs, n, p};
+        plant_observe(st, prm, out);
+    }
+    if (reward) reward[p] = plant_reward(st, prm);
+}
+
+// ------------------------------------------------------------------------------------------------
+// threshold flag kernel: one thread per plant evaluates every threshold row; cooldown stamps in SoA;
+// __ballot_sync compacts "this plant fired something" into one word per warp for the host drain.
+// ------------------------------------------------------------------------------------------------
+__global__ void nps_threshold_kernel(const double* __restrict__ slab, const Threshold* __restrict__ thr, int n_thr,
+                                     double now_minutes_field_unused, int time_field, double* __restrict__ last_fired,
+                                     uint32_t* __restrict__ flags, uint32_t* __restrict__ any_warp, int64_t n) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = p < n;
+    bool any = false;
+    if (live) {
+        const double now = slab[(int64_t)time_field * n + p];
+        uint32_t word = 0;
+        for (int t = 0; t < n_thr; ++t) {
+            const Threshold th = thr[t];
+            bool fire = false;
+            if (th.field >= 0) {
+                const double last = last_fired[(int64_t)t * n + p];
+                // _is_threshold_in_cooldown: state_manager.py:1267-1305
+                const bool cooling = (now - last) < th.cooldown;
+                if (!cooling) {
+                    const double v = slab[(int64_t)th.field * n + p];
+                    switch (th.cmp) {   // _check_threshold_condition: state_manager.py:1412-1442
+                        case 0: fire = v > th.value; break;
+                        case 1: fire = v < th.value; break;
+                        case 2: fire = v >= th.value; break;
+                        case 3: fire = v <= th.value; break;
+                        default: fire = fabs(v - th.value) < 1e-3; break;
+                    }
+                    if (fire) last_fired[(int64_t)t * n + p] = now;
+                }
+            }
+            if (fire) { word |= (1u << (t & 31)); any = true; }
+            if ((t & 31) == 31 || t == n_thr - 1) { flags[(int64_t)(t >> 5) * n + p] = word; word = 0; }
+        }
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, any);
+    if ((threadIdx.x & 31) == 0 && any_warp) {
+        const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+        any_warp[w] = ballot;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// trajectory ring-buffer row: gather the logged fields of a tile of plants through shared memory
+// ------------------------------------------------------------------------------------------------
+constexpr int kLogTilePlants = 128;
+constexpr int kLogTileFields = 32;
+__global__ void nps_log_row_kernel(const double* __restrict__ slab, const int32_t* __restrict__ fields, int n_logged,
+                                   double* __restrict__ ring_row, int64_t n) {
+    __shared__ double tile[kLogTileFields][kLogTilePlants + 1];
+    const int64_t p0 = (int64_t)blockIdx.x * kLogTilePlants;
+    const int f0 = blockIdx.y * kLogTileFields;
+    const int tx = threadIdx.x;   // plant within tile
+    for (int j = 0; j < kLogTileFields; ++j) {
+        const int lf = f0 + j;
+        if (lf < n_logged && p0 + tx < n) tile[j][tx] = slab[(int64_t)fields[lf] * n + p0 + tx];
+    }
+    __syncthreads();
+    for (int j = 0; j < kLogTileFields; ++j) {
+        const int lf = f0 + j;
+        if (lf < n_logged && p0 + tx < n) ring_row[(int64_t)lf * n + p0 + tx] = tile[j][tx];
+    }
+}
+
+__global__ void nps_gather_kernel(const double* __restrict__ slab, const int32_t* __restrict__ fields, int n_fields,
+                                  double* __restrict__ out, int64_t n) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    for (int j = 0; j < n_fields; ++j) out[(int64_t)j * n + p] = slab[(int64_t)fields[j] * n + p];
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int nps_abi_version(void) { return NPS_ABI_VERSION; }
+const char* nps_last_error(void) { return g_last_error.c_str(); }
+int nps_n_state(void) { return kNState; }
+int nps_n_params(void) { return kNParams; }
+const char* nps_field_name(int f) { return (f >= 0 && f < kNState) ? kStateFieldNames[f] : nullptr; }
+const char* nps_param_name(int f) { return (f >= 0 && f < kNParams) ? kParamFieldNames[f] : nullptr; }
+
+int nps_create(int64_t n_plants, int device, nps_handle** out) {
+    if (!out || n_plants <= 0) return fail("nps_create: bad arguments");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) return fail("nps_create: no CUDA device (this library has no CPU fallback)", e);
+    if (device < 0 || device >= count) return fail("nps_create: device index out of range");
+    NPS_CUDA(cudaSetDevice(device));
+    nps_handle* h = new nps_handle();
+    h->n = n_plants; h->device = device;
+    std::memset(&h->params, 0, sizeof(PlantParams));
+    // the step kernel keeps one PlantState per thread in local memory
+    NPS_CUDA(cudaFuncSetCacheConfig(nps_step_kernel, cudaFuncCachePreferL1));
+    *out = h;
+    return 0;
+}
+
+void nps_destroy(nps_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaFree(h->d_setpoint); cudaFree(h->d_action); cudaFree(h->d_mag); cudaFree(h->d_noise);
+    cudaFree(h->d_obs); cudaFree(h->d_reward); cudaFree(h->d_done); cudaFree(h->d_thresholds);
+    cudaFree(h->d_logged); cudaFree(h->d_gather_fields); cudaFree(h->d_gather_out);
+    delete h;
+}
+
+int64_t nps_n_plants(const nps_handle* h) { return h ? h->n : 0; }
+
+int nps_set_params(nps_handle* h, const double* params_host, int n_params) {
+    if (!h || !params_host) return fail("nps_set_params: null argument");
+    if (n_params != kNParams) return fail("nps_set_params: parameter count mismatch");
+    std::memcpy(&h->params, params_host, sizeof(PlantParams));   // passed to kernels by value (constant bank)
+    return 0;
+}
+
+int nps_step(nps_handle* h, double* d_state, const int8_t* d_action, const double* d_magnitude, const double* d_noise,
+             const double* d_setpoint, int k_substeps, double* d_obs, double* d_reward, uint8_t* d_done,
+             void* cuda_stream) {
+    if (!h || !d_state) return fail("nps_step: null argument");
+    if (k_substeps <= 0) return fail("nps_step: k_substeps must be positive");
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    const int grid = (int)((h->n + kStepBlock - 1) / kStepBlock);
+    nps_step_kernel<<<grid, kStepBlock, 0, s>>>(d_state, h->params, d_action, d_magnitude, d_noise, d_setpoint,
+                                                k_substeps, h->n, d_obs, d_reward, d_done);
+    NPS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int ensure_staging(nps_handle* h, int k) {
+    if (h->staged_k >= k && h->d_obs) return 0;
+    cudaFree(h->d_action); cudaFree(h->d_mag); cudaFree(h->d_noise); cudaFree(h->d_setpoint);
+    h->d_action = nullptr; h->d_mag = nullptr; h->d_noise = nullptr; h->d_setpoint = nullptr;
+    NPS_CUDA(cudaMalloc(&h->d_action, (size_t)k * h->n));
+    NPS_CUDA(cudaMalloc(&h->d_mag, (size_t)k * h->n * sizeof(double)));
+    NPS_CUDA(cudaMalloc(&h->d_noise, (size_t)k * NPS_NOISE_PER_STEP * h->n * sizeof(double)));
+    NPS_CUDA(cudaMalloc(&h->d_setpoint, (size_t)k * h->n * sizeof(double)));
+    if (!h->d_obs) {
+        NPS_CUDA(cudaMalloc(&h->d_obs, (size_t)NPS_OBS_DIM * h->n * sizeof(double)));
+        NPS_CUDA(cudaMalloc(&h->d_reward, (size_t)h->n * sizeof(double)));
+        NPS_CUDA(cudaMalloc(&h->d_done, (size_t)h->n));
+    }
+    h->staged_k = k;
+    return 0;
+}
+
+int nps_step_host(nps_handle* h, double* d_state, const int8_t* h_action, const double* h_magnitude,
+                  const double* h_noise, const double* h_setpoint, int k_substeps, double* h_obs, double* h_reward,
+                  uint8_t* h_done, void* cuda_stream) {
+    if (!h || !d_state) return fail("nps_step_host: null argument");
+    if (k_substeps <= 0) return fail("nps_step_host: k_substeps must be positive");
+    NPS_CUDA(cudaSetDevice(h->device));
+    if (ensure_staging(h, k_substeps)) return -1;
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    const size_t kn = (size_t)k_substeps * h->n;
+    if (h_action) NPS_CUDA(cudaMemcpyAsync(h->d_action, h_action, kn, cudaMemcpyHostToDevice, s));
+    if (h_magnitude) NPS_CUDA(cudaMemcpyAsync(h->d_mag, h_magnitude, kn * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (h_noise) NPS_CUDA(cudaMemcpyAsync(h->d_noise, h_noise, kn * NPS_NOISE_PER_STEP * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (h_setpoint) NPS_CUDA(cudaMemcpyAsync(h->d_setpoint, h_setpoint, kn * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (nps_step(h, d_state, h_action ? h->d_action : nullptr, h_magnitude ? h->d_mag : nullptr,
+                 h_noise ? h->d_noise : nullptr, h_setpoint ? h->d_setpoint : nullptr, k_substeps, h_obs ? h->d_obs : nullptr,
+                 h_reward ? h->d_reward : nullptr, h_done ? h->d_done : nullptr, cuda_stream)) return -1;
+    if (h_obs) NPS_CUDA(cudaMemcpyAsync(h_obs, h->d_obs, (size_t)NPS_OBS_DIM * h->n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (h_reward) NPS_CUDA(cudaMemcpyAsync(h_reward, h->d_reward, (size_t)h->n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (h_done) NPS_CUDA(cudaMemcpyAsync(h_done, h->d_done, (size_t)h->n, cudaMemcpyDeviceToHost, s));
+    NPS_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int nps_observe(nps_handle* h, const double* d_state, double* d_obs, double* d_reward, void* cuda_stream) {
+    if (!h || !d_state) return fail("nps_observe: null argument");
+    const int block = 64;
+    const int grid = (int)((h->n + block - 1) / block);
+    nps_observe_kernel<<<grid, block, 0, (cudaStream_t)cuda_stream>>>(d_state, h->params, h->n, d_obs, d_reward);
+    NPS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int nps_set_thresholds(nps_handle* h, const int32_t* field, const int32_t* comparator, const double* value,
+                       const double* cooldown_minutes, int n_thresholds) {
+    if (!h || n_thresholds < 0) return fail("nps_set_thresholds: bad arguments");
+    NPS_CUDA(cudaSetDevice(h->device));
+    cudaFree(h->d_thresholds); h->d_thresholds = nullptr; h->n_thresholds = 0;
+    if (n_thresholds == 0) return 0;
+    std::vector<Threshold> t(n_thresholds);
+    for (int i = 0; i < n_thresholds; ++i) {
+        if (field[i] >= kNState) return fail("nps_set_thresholds: field index out of range");
+        t[i] = Threshold{field[i], comparator[i], value[i], cooldown_minutes[i]};
+    }
+    NPS_CUDA(cudaMalloc(&h->d_thresholds, sizeof(Threshold) * n_thresholds));
+    NPS_CUDA(cudaMemcpy(h->d_thresholds, t.data(), sizeof(Threshold) * n_thresholds, cudaMemcpyHostToDevice));
+    h->n_thresholds = n_thresholds;
+    return 0;
+}
+
+int nps_check_thresholds(nps_handle* h, const double* d_state, double* d_last_fired, uint32_t* d_flags,
+                         uint32_t* d_any_warp, void* cuda_stream) {
+    if (!h || !d_state || !d_last_fired || !d_flags) return fail("nps_check_thresholds: null argument");
+    if (h->n_thresholds == 0) return fail("nps_check_thresholds: no thresholds set");
+    const int block = 128;
+    const int grid = (int)((h->n + block - 1) / block);
+    const int time_field = kTimeMinutesField;
+    nps_threshold_kernel<<<grid, block, 0, (cudaStream_t)cuda_stream>>>(d_state, h->d_thresholds, h->n_thresholds, 0.0,
+                                                                       time_field, d_last_fired, d_flags, d_any_warp, h->n);
+    NPS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int nps_set_logged_fields(nps_handle* h, const int32_t* fields, int n_logged) {
+    if (!h || n_logged < 0) return fail("nps_set_logged_fields: bad arguments");
+    NPS_CUDA(cudaSetDevice(h->device));
+    cudaFree(h->d_logged); h->d_logged = nullptr; h->n_logged = 0;
+    if (n_logged == 0) return 0;
+    for (int i = 0; i < n_logged; ++i) if (fields[i] < 0 || fields[i] >= kNState) return fail("nps_set_logged_fields: field index out of range");
+    NPS_CUDA(cudaMalloc(&h->d_logged, sizeof(int32_t) * n_logged));
+    NPS_CUDA(cudaMemcpy(h->d_logged, fields, sizeof(int32_t) * n_logged, cudaMemcpyHostToDevice));
+    h->n_logged = n_logged;
+    return 0;
+}
+
+int nps_log_row(nps_handle* h, const double* d_state, double* d_ring, int64_t ring_rows, int64_t write_index,
+                void* cuda_stream) {
+    if (!h || !d_state || !d_ring || ring_rows <= 0) return fail("nps_log_row: bad arguments");
+    if (h->n_logged == 0) return fail("nps_log_row: no logged fields set");
+    double* row = d_ring + (write_index % ring_rows) * (int64_t)h->n_logged * h->n;
+    dim3 grid((unsigned)((h->n + kLogTilePlants - 1) / kLogTilePlants), (unsigned)((h->n_logged + kLogTileFields - 1) / kLogTileFields));
+    nps_log_row_kernel<<<grid, kLogTilePlants, 0, (cudaStream_t)cuda_stream>>>(d_state, h->d_logged, h->n_logged, row, h->n);
+    NPS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int nps_read_fields(nps_handle* h, const double* d_state, const int32_t* fields, int n_fields, double* out_host) {
+    if (!h || !d_state || !fields || !out_host || n_fields <= 0) return fail("nps_read_fields: bad arguments");
+    NPS_CUDA(cudaSetDevice(h->device));
+    for (int i = 0; i < n_fields; ++i) if (fields[i] < 0 || fields[i] >= kNState) return fail("nps_read_fields: field index out of range");
+    if (h->gather_cap < n_fields) {
+        cudaFree(h->d_gather_fields); cudaFree(h->d_gather_out);
+        NPS_CUDA(cudaMalloc(&h->d_gather_fields, sizeof(int32_t) * n_fields));
+        NPS_CUDA(cudaMalloc(&h->d_gather_out, sizeof(double) * n_fields * h->n));
+        h->gather_cap = n_fields;
+    }
+    NPS_CUDA(cudaMemcpy(h->d_gather_fields, fields, sizeof(int32_t) * n_fields, cudaMemcpyHostToDevice));
+    const int block = 128;
+    nps_gather_kernel<<<(int)((h->n + block - 1) / block), block>>>(d_state, h->d_gather_fields, n_fields, h->d_gather_out, h->n);
+    NPS_CUDA(cudaGetLastError());
+    NPS_CUDA(cudaMemcpy(out_host, h->d_gather_out, sizeof(double) * n_fields * h->n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+}  // extern "C"

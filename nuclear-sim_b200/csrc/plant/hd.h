@@ -2,7 +2,7 @@
 //
 // Every function under csrc/plant/ is plain scalar FP64 written once and compiled
 //   * by nvcc for sm_100a  (the product: one thread advances one plant), and
-//   * by g++ for the host  (test infrastructure only: oracle/cpu_port.cpp).
+//   * by g++ for the host  (test infrastructure only; the product never links that build).
 // Arithmetic must match CPython/numpy scalar semantics bit for bit, so:
 //   - no FMA contraction (nvcc -fmad=false, g++ -ffp-contract=off),
 //   - py_max/py_min/np_clip reproduce Python's and numpy's NaN/ordering behaviour,

@@ -80,8 +80,9 @@ NPS_HD void plant_step(PlantState& st, const PlantParams& p, const StepInput& in
     st.sim.time_minutes += dt;
 }
 
-// get_observation: sim.py:290-333 (first 12 entries are primary-only)
-NPS_HD void plant_observe_primary(const PlantState& st, double* obs) {
+// get_observation: sim.py:290-333
+template <class Obs>
+NPS_HD void plant_observe(const PlantState& st, const PlantParams& p, Obs&& obs) {
     const PrimaryState& s = st.pri;
     obs[0] = s.neutron_flux / 1e12;
     obs[1] = s.fuel_temperature / 1000;
@@ -95,6 +96,42 @@ NPS_HD void plant_observe_primary(const PlantState& st, double* obs) {
     obs[9] = s.steam_valve_position / 100;
     obs[10] = s.power_level / 100;
     obs[11] = is_true(s.scram_status) ? 1.0 : 0.0;
+    if (is_true(p.enable_secondary)) {
+        obs[12] = st.sec.electrical_power_output / 1100;
+        obs[13] = st.sec.thermal_efficiency / 0.35;
+        obs[14] = st.sec.total_steam_flow / 1665;
+        obs[15] = st.sec.load_demand / 100;
+        obs[16] = st.sec.feedwater_temperature / 250;
+        obs[17] = st.sec.cooling_water_temperature / 35;
+        obs[18] = st.fw.total_flow_rate / 1665;
+        obs[19] = st.fw.total_power_consumption / 40;
+        obs[20] = is_true(st.fw.system_availability) ? 1.0 : 0.0;
+        obs[21] = st.fw.total_flow_rate / 1665;
+    } else {
+        for (int i = 12; i < 22; ++i) obs[i] = 0.0;
+    }
+}
+
+// calculate_reward: sim.py:500-544 (secondary terms use the step's secondary_result)
+NPS_HD double plant_reward(const PlantState& st, const PlantParams& p) {
+    const PrimaryState& s = st.pri;
+    double power_reward = -fabs(s.power_level - 100) / 100;
+    double temp_penalty = 0;
+    if (s.fuel_temperature > 800) temp_penalty = -(s.fuel_temperature - 800) / 100;
+    double pressure_penalty = 0;
+    if (s.coolant_pressure > 16) pressure_penalty = -(s.coolant_pressure - 16);
+    double scram_penalty = is_true(s.scram_status) ? -100.0 : 0.0;
+    double base = power_reward + temp_penalty + pressure_penalty + scram_penalty;
+    if (!is_true(p.enable_secondary)) return base;
+    double eff_reward = (st.sec.thermal_efficiency - 0.30) * 10;
+    double target_el = st.sim.load_demand / 100.0 * 1100.0;
+    double el_reward = -fabs(st.sec.electrical_power_output - target_el) / 100;
+    double sp_pen = 0;
+    if (st.sec.sg_avg_pressure < 5.0 || st.sec.sg_avg_pressure > 8.0) sp_pen = -fabs(st.sec.sg_avg_pressure - 6.895) * 5;
+    double cond_pen = 0;
+    if (st.sec.condenser_pressure > 0.01) cond_pen = -(st.sec.condenser_pressure - 0.007) * 100;
+    double sec_reward = eff_reward + el_reward + sp_pen + cond_pen;
+    return base + sec_reward * 0.5;
 }
 
 }  // namespace nps

@@ -23,6 +23,7 @@ struct StepInput {
     double z_heat;     // standard-normal draw for ConstantHeatSource noise (constant_heat_source.py:178)
     double z_ph;       // standard-normal draw for the pH sensor noise (ph_control_system.py:288)
     double u_ph[3];    // uniform draws for pH equipment failures (ph_control_system.py:409,414,420)
+    double power_setpoint;  // heat_source.set_power_setpoint(%) applied before the step; NaN = unchanged
 };
 
 // _apply_control_actions: systems/primary/__init__.py:289-359 with the action routing of
@@ -218,6 +219,10 @@ NPS_HD bool primary_check_scram(PrimaryState& s) {
 
 // PrimaryReactorPhysics.update_system: systems/primary/__init__.py:178-287
 NPS_HD void primary_update(PrimaryState& s, const PlantParams& p, const StepInput& in, double dt) {
+    if (!isnan(in.power_setpoint)) {   // ConstantHeatSource.set_power_setpoint: constant_heat_source.py:94-102
+        s.hs_setpoint_percent = np_clip(in.power_setpoint, 0.0, 150.0);
+        s.hs_current_power_mw = (s.hs_setpoint_percent / 100.0) * p.rated_power_mw;
+    }
     primary_apply_control(s, in.action, in.magnitude, dt);
     double thermal_mw, power_pct, rho_pcm = 0.0;
     if (p.heat_source_type == 0.0) {

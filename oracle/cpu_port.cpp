@@ -10,6 +10,7 @@
 //
 // Layout here is array-of-structs: state[p * n_state + f]  (one contiguous PlantState per plant).
 #include <cstring>
+#include <cmath>
 #include <cstdint>
 #include "plant_step.h"
 
@@ -21,8 +22,8 @@ int nps_oracle_n_state(void) { return (int)(sizeof(PlantState) / sizeof(double))
 int nps_oracle_n_params(void) { return (int)(sizeof(PlantParams) / sizeof(double)); }
 
 // noise: [n_plants][k_steps][5] = z_heat, z_ph, u0, u1, u2 ; action/magnitude: [n_plants][k_steps]
-int nps_oracle_step(double* state, const double* params, const int8_t* action, const double* magnitude,
-                    const double* noise, int64_t n_plants, int k_steps) {
+int nps_oracle_step_sp(double* state, const double* params, const int8_t* action, const double* magnitude,
+                       const double* noise, const double* setpoint, int64_t n_plants, int k_steps) {
     PlantParams p;
     std::memcpy(&p, params, sizeof(p));
     const int ns = nps_oracle_n_state();
@@ -37,9 +38,27 @@ int nps_oracle_step(double* state, const double* params, const int8_t* action, c
             in.z_heat = z ? z[0] : 0.0;
             in.z_ph = z ? z[1] : 0.0;
             in.u_ph[0] = z ? z[2] : 1.0; in.u_ph[1] = z ? z[3] : 1.0; in.u_ph[2] = z ? z[4] : 1.0;
+            in.power_setpoint = setpoint ? setpoint[i * k_steps + k] : NAN;
             plant_step(st, p, in);
         }
         std::memcpy(state + i * ns, &st, sizeof(st));
+    }
+    return 0;
+}
+
+int nps_oracle_step(double* state, const double* params, const int8_t* action, const double* magnitude,
+                    const double* noise, int64_t n_plants, int k_steps) {
+    return nps_oracle_step_sp(state, params, action, magnitude, noise, nullptr, n_plants, k_steps);
+}
+
+// observation [22] + reward for each plant (array-of-structs state)
+int nps_oracle_observe(const double* state, const double* params, int64_t n_plants, double* obs, double* reward) {
+    PlantParams p; std::memcpy(&p, params, sizeof(p));
+    const int ns = nps_oracle_n_state();
+    for (int64_t i = 0; i < n_plants; ++i) {
+        PlantState st; std::memcpy(&st, state + i * ns, sizeof(st));
+        plant_observe(st, p, obs + i * 22);
+        reward[i] = plant_reward(st, p);
     }
     return 0;
 }

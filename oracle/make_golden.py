@@ -1,0 +1,194 @@
+"""TEST INFRASTRUCTURE — generate committed fixtures from the LIVE reference (/root/reference).
+
+Run in the build container (the reference is absent on the GPU box):
+    python oracle/make_golden.py            # all scenarios
+    python oracle/make_golden.py cfg1 cfg4  # selected
+
+Writes
+  nuclear-sim_b200/data/<snapshot>.npz   initial PlantState + PlantParams vectors (engine starting points)
+  tests/golden/<scenario>.npz            inputs + reference states/observations at checkpoint steps
+
+Every array is produced by stepping the unmodified reference ``NuclearPlantSimulator.step``
+(nuclear_simulator/simulator/core/sim.py:130-258) with host-controlled random streams
+(oracle/refplant.py); nothing here goes through the C/CUDA restatement.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import time
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_REPO = os.path.dirname(_HERE)
+sys.path.insert(0, _REPO)
+from oracle import refplant as R  # noqa: E402
+
+GOLDEN = os.path.join(_REPO, "tests", "golden")
+DATA = os.path.join(_REPO, "nuclear-sim_b200", "data")
+
+
+def _names():
+    L = R._layout()
+    return np.array(L.field_names("PlantState")), np.array(L.field_names("PlantParams"))
+
+
+def save_snapshot(name, sim):
+    os.makedirs(DATA, exist_ok=True)
+    sn, pn = _names()
+    np.savez_compressed(os.path.join(DATA, name + ".npz"), state=R.extract_state(sim), params=R.extract_params(sim),
+                        state_names=sn, param_names=pn)
+
+
+def run_scenario(name, plants, T, checkpoints, policy, *, inject=None, seed_base=1000):
+    """plants: list of ReferencePlant; policy(p, t, sim) -> (action, magnitude, setpoint_or_nan)."""
+    P = len(plants)
+    L = R._layout()
+    NS = L.N_STATE
+    params = [R.extract_params(rp.sim) for rp in plants]
+    for q in params[1:]:
+        assert np.array_equal(q, params[0]), "plants of one golden must share PlantParams"
+    state0 = np.stack([R.extract_state(rp.sim) for rp in plants])
+    actions = np.full((T, P), 8, dtype=np.int8)
+    mags = np.ones((T, P))
+    noise = np.zeros((T, P, 5))
+    setp = np.full((T, P), np.nan)
+    inj = np.full((T, P, 2), np.nan)   # (field index, value) written to the state BEFORE step t
+    cps = sorted(set(int(c) for c in checkpoints if c <= T))
+    states = np.zeros((len(cps), P, NS))
+    obs = np.zeros((len(cps), P, 22))
+    rew = np.zeros((len(cps), P))
+    done_step = np.full(P, -1, dtype=np.int64)
+    power = np.zeros((T, P))
+    elec = np.zeros((T, P))
+    ix = L.field_index()
+    t0 = time.time()
+    for p, rp in enumerate(plants):
+        rng = np.random.RandomState(seed_base + p)
+        sim = rp.sim
+        for t in range(T):
+            a, m, sp = policy(p, t, sim)
+            z = np.array([rng.standard_normal(), rng.standard_normal(), rng.random_sample(), rng.random_sample(),
+                          rng.random_sample()])
+            actions[t, p], mags[t, p], noise[t, p], setp[t, p] = a, m, z, sp
+            if inject is not None:
+                ev = inject(p, t)
+                if ev is not None:
+                    fname, val = ev
+                    assert fname.startswith("pri.")
+                    setattr(sim.primary_physics.state, fname[4:], val)
+                    inj[t, p] = (ix[fname], val)
+            if not np.isnan(sp):
+                sim.primary_physics.heat_source.set_power_setpoint(sp)
+            out = rp.step(int(a), float(m), z)
+            power[t, p] = sim.state.power_level
+            elec[t, p] = sim.secondary_physics.electrical_power_output if sim.secondary_physics else 0.0
+            if out["done"] and done_step[p] < 0:
+                done_step[p] = t
+            if (t + 1) in cps:
+                c = cps.index(t + 1)
+                states[c, p] = R.extract_state(sim)
+                obs[c, p] = out["observation"]
+                rew[c, p] = out["reward"]
+    os.makedirs(GOLDEN, exist_ok=True)
+    sn, pn = _names()
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), state0=state0, params=params[0], actions=actions,
+                        magnitudes=mags, noise=noise, setpoint=setp, inject=inj, checkpoints=np.array(cps),
+                        states=states, obs=obs, reward=rew, done_step=done_step, power_level=power, electrical=elec,
+                        state_names=sn, param_names=pn)
+    print(f"[golden] {name}: P={P} T={T} checkpoints={cps} done_step={done_step.tolist()} ({time.time()-t0:.1f}s)")
+
+
+NO = (8, 1.0, np.nan)
+
+
+def cfg1():
+    """BASELINE config #1: oil_top_off, dt = 5 min, 12 steps, ConstantHeatSource noise 0.1 % (seed-42 stream),
+    runner-style setpoint ramp 90 % -> target at 0.02 %/step (maintenance_scenario_runner.py:651-671)."""
+    cfg = R.compose_config("oil_top_off")
+    rp = R.make_reference_plant(cfg, dt=5.0, heat_source="constant", noise_enabled=True, noise_std_percent=0.1)
+    save_snapshot("pwr3000_oil_top_off_dt5", rp.sim)
+    rp.sim.primary_physics.heat_source.set_power_setpoint(90.0)
+
+    def policy(p, t, sim):
+        return 8, 1.0, 90.0 + 0.02 * (t + 1)
+    run_scenario("cfg1_oil_top_off", [rp], 12, range(1, 13), policy, seed_base=42)
+
+
+def _plants(actions, **kw):
+    out = []
+    for a in actions:
+        out.append(R.make_reference_plant(R.compose_config(a), **kw))
+    return out
+
+
+IC_ACTIONS = ["oil_top_off", "tsp_chemical_cleaning", "scale_removal", "oil_change"]
+
+
+def cfg2():
+    """BASELINE config #2: steady 100 %, constant heat source (noise off), NO_ACTION, 1 h at dt = 1.0 (3 600 steps)."""
+    plants = _plants(IC_ACTIONS[:2], dt=1.0, heat_source="constant", noise_enabled=False)
+    save_snapshot("pwr3000_steady_dt1", plants[0].sim)
+    run_scenario("cfg2_steady", plants, 3600, [1, 2, 10, 100, 1000, 3600], lambda p, t, sim: NO)
+
+
+def cfg3():
+    """BASELINE config #3: ReactorHeatSource at create_equilibrium_state(); load-following rods
+    (data/gen_training_data.py:401-406), power ramp 20xINSERT then 30xWITHDRAW (tests/test_scenarios.py:56-74),
+    boron / flow / valve actions mixed in; dt = 1.0, 3 600 steps; per-plant ICs from the action catalog."""
+    plants = _plants(IC_ACTIONS[:3], dt=1.0, heat_source="reactor")
+    save_snapshot("pwr3000_reactor_dt1", plants[0].sim)
+
+    def policy(p, t, sim):
+        mag = 0.2 + 0.8 * ((p * 37 + 11) % 100) / 100.0
+        if p == 0:
+            s = np.sin(t / 100.0)
+            return (1 if s > 0.5 else (0 if s < -0.5 else 8)), mag, np.nan
+        if p == 1:
+            u = t % 200
+            return (0 if u < 20 else (1 if u < 50 else 8)), mag, np.nan
+        seq = [10, 8, 8, 9, 8, 2, 3, 4, 5, 6, 7, 8]
+        return seq[(t // 25) % len(seq)], mag, np.nan
+    run_scenario("cfg3_loadfollow", plants, 3600, [1, 10, 100, 500, 1000, 2000, 3600], policy)
+
+
+def cfg4():
+    """BASELINE config #4: scram / shutdown transients — injected coolant pressure 17.3 MPa (> 17.2 trip,
+    scram_logic.py:20), injected fuel temperature 1600 C (tests/test_scenarios.py:98-110), flow reduction to the
+    5 000 kg/s clamp (scram_logic.py:21,37: the clamp value itself does not trip) and a boration shutdown
+    (power falls 10 %/s through the point-kinetics rate clamp, no scram)."""
+    plants = _plants(["oil_top_off"] * 4, dt=1.0, heat_source="reactor")
+
+    def policy(p, t, sim):
+        if p == 2 and t >= 20:
+            return 3, 1.0, np.nan
+        if p == 3 and 30 <= t < 60:
+            return 10, 1.0, np.nan
+        return NO
+
+    def inject(p, t):
+        if p == 0 and t == 50:
+            return ("pri.coolant_pressure", 17.3)
+        if p == 1 and t == 100:
+            return ("pri.fuel_temperature", 1600.0)
+        return None
+    run_scenario("cfg4_scram", plants, 300, [1, 50, 52, 54, 56, 60, 100, 101, 102, 150, 300], policy, inject=inject)
+
+
+def cfg5():
+    """BASELINE config #5 (one day of it): long-horizon degradation at dt = 5 min, 288 steps, ICs near
+    maintenance thresholds, physics only (work-order effects are a 'next' row)."""
+    plants = _plants(["tsp_chemical_cleaning", "oil_change", "scale_removal"], dt=5.0, heat_source="constant",
+                     noise_enabled=False)
+    run_scenario("cfg5_degradation", plants, 288, [1, 12, 144, 288], lambda p, t, sim: NO)
+
+
+ALL = {"cfg1": cfg1, "cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5}
+
+if __name__ == "__main__":
+    if not R.reference_available():
+        sys.exit("reference not found at " + R.REF_ROOT)
+    sel = sys.argv[1:] or list(ALL)
+    for k in sel:
+        ALL[k]()

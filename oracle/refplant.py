@@ -109,6 +109,8 @@ class ReferencePlant:
         if self.heat_rng is not None:
             self.heat_rng.z = float(noise[0])
         if self.ph_random is not None:
+            import systems.secondary.ph_control_system as phmod
+            phmod.np.random = self.ph_random   # the patch is module-global: re-point it at THIS plant's stream
             self.ph_random.z = float(noise[1])
             self.ph_random.u = [float(noise[2]), float(noise[3]), float(noise[4])]
             self.ph_random.n_normal = 0

@@ -1,0 +1,113 @@
+"""Shared helpers for the test-suite: golden loading, the host oracle library, comparisons."""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+ORACLE_SO = os.path.join(ROOT, "oracle", "_build", "libnps_oracle.so")
+
+# Tolerances from BASELINE.json: continuous state within 1e-9 relative per step and 1e-6 after 3 600 steps;
+# discrete fields (flags, enums, counters, latches) bit-exact.
+TOL_STEP = 1e-9
+TOL_LONG = 1e-6
+ABS_FLOOR = 1e-12   # |x| below this is compared absolutely (quantities that are exactly zero in steady state)
+
+
+def oracle_lib() -> ctypes.CDLL:
+    if not os.path.exists(ORACLE_SO):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
+    L = ctypes.CDLL(ORACLE_SO)
+    L.nps_oracle_n_state.restype = ctypes.c_int
+    L.nps_oracle_n_params.restype = ctypes.c_int
+    return L
+
+
+def ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+def load_golden(name):
+    from nuclear_sim_b200 import field_names
+    z = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+    g = {k: z[k] for k in z.files}
+    assert tuple(str(s) for s in g["state_names"]) == field_names("PlantState"), \
+        f"{name}: fixture was generated for a different state.h (rerun oracle/make_golden.py)"
+    assert tuple(str(s) for s in g["param_names"]) == field_names("PlantParams")
+    return g
+
+
+def discrete_mask():
+    """Fields that hold flags / enums / counters / latches: compared bit-exactly."""
+    from nuclear_sim_b200 import field_names
+    keys = ("status", "scram", "available", "trip", "alarm", "_active", "is_operating", "ic_applied", "fouling_stage",
+            "shutdown", "replacement", "recommended", "mode", "enabled", "events", "cycles", "n_running", "n_events",
+            "lead_ejector", "lag_ejector", "dev_count", "dev_head", "external_oil_temp", "has_", "pending_effects",
+            "initialized", "control_actions_count", "feedwater_pump_status", "num_running")
+    names = field_names("PlantState")
+    not_discrete = ("npsh_available", "td_active_tube_count", "prot_timer", "feedwater_pump_speed", "feedwater_pump_power")
+    return np.array([any(k in n for k in keys) and not any(x in n for x in not_discrete) for n in names])
+
+
+def canonicalize(v):
+    """Rotate the pH deviation ring so its oldest entry sits at index 0 (storage detail, not state)."""
+    from nuclear_sim_b200 import field_index
+    ix = field_index()
+    v = np.array(v, dtype=np.float64, copy=True)
+    flat = v.reshape(-1, v.shape[-1])
+    b = ix["ph.dev_hist[0]"]
+    for row in flat:
+        h = int(row[ix["ph.dev_head"]])
+        if h:
+            row[b:b + 100] = np.roll(row[b:b + 100], -h)
+            row[ix["ph.dev_head"]] = 0.0
+    return flat.reshape(v.shape)
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    den = np.maximum(np.abs(b), ABS_FLOOR)
+    e = np.abs(a - b) / den
+    e[a == b] = 0.0
+    e[np.isnan(a) & np.isnan(b)] = 0.0
+    return e
+
+
+def assert_states_close(got, ref, tol, what=""):
+    from nuclear_sim_b200 import field_names
+    got = canonicalize(got)
+    ref = canonicalize(ref)
+    names = field_names("PlantState")
+    dm = discrete_mask()
+    bad_d = np.argwhere((got != ref) & dm[None, :] if got.ndim == 2 else (got != ref) & dm)
+    assert bad_d.size == 0, f"{what}: discrete field mismatch, e.g. " + ", ".join(
+        f"{names[i[-1]]} got {got[tuple(i)]} ref {ref[tuple(i)]}" for i in bad_d[:5])
+    e = rel_err(got, ref)
+    worst = np.unravel_index(np.argmax(e), e.shape)
+    assert e.max() <= tol, (f"{what}: max rel err {e.max():.3e} > {tol:g} at {names[worst[-1]]} "
+                            f"(got {got[worst]!r}, ref {ref[worst]!r})")
+    return float(e.max())
+
+
+def oracle_run(L, state0, params, actions, mags, noise, setpoint, inject, t0, t1):
+    """Advance array-of-structs states [P, NS] from step t0 to t1 with the host oracle, honouring injections."""
+    st = np.ascontiguousarray(state0, dtype=np.float64).copy()
+    P = st.shape[0]
+    params = np.ascontiguousarray(params, dtype=np.float64)
+    for t in range(t0, t1):
+        if inject is not None:
+            for p in range(P):
+                if not np.isnan(inject[t, p, 0]):
+                    st[p, int(inject[t, p, 0])] = inject[t, p, 1]
+        a = np.ascontiguousarray(actions[t], dtype=np.int8)
+        m = np.ascontiguousarray(mags[t], dtype=np.float64)
+        z = np.ascontiguousarray(noise[t], dtype=np.float64)
+        sp = np.ascontiguousarray(setpoint[t], dtype=np.float64)
+        rc = L.nps_oracle_step_sp(ptr(st), ptr(params), ptr(a), ptr(m), ptr(z), ptr(sp), ctypes.c_int64(P), 1)
+        assert rc == 0
+    return st

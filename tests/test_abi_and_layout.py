@@ -1,0 +1,67 @@
+"""CPU: the C-ABI library loads and exports every symbol include/nps_b200.h declares; the Python layout
+parser, the generated field table and the compiled structs agree; creating a handle without a GPU fails loudly."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from tests import _util as U
+
+ROOT = U.ROOT
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "nps_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(nps_[a-z_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported():
+    from nuclear_sim_b200 import _clib
+    L = _clib.lib()
+    declared = _declared_symbols()
+    assert declared, "no declarations parsed"
+    for sym in declared:
+        assert hasattr(L, sym), f"libnps_b200.so does not export {sym}"
+    assert sorted(_clib.EXPORTED_SYMBOLS) == declared
+
+
+def test_layout_agrees_with_compiled_structs(oracle_lib):
+    from nuclear_sim_b200 import N_PARAMS, N_STATE, _clib, field_names
+    L = _clib.lib()
+    assert L.nps_n_state() == N_STATE == oracle_lib.nps_oracle_n_state()
+    assert L.nps_n_params() == N_PARAMS == oracle_lib.nps_oracle_n_params()
+    names = field_names("PlantState")
+    assert [L.nps_field_name(i).decode() for i in range(N_STATE)] == list(names)
+    pn = field_names("PlantParams")
+    assert [L.nps_param_name(i).decode() for i in range(N_PARAMS)] == list(pn)
+    assert L.nps_field_name(N_STATE) is None
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from nuclear_sim_b200 import _clib
+    L = _clib.lib()
+    h = ctypes.c_void_p()
+    assert L.nps_create(4, 0, ctypes.byref(h)) != 0
+    assert b"no CUDA device" in L.nps_last_error()
+    from nuclear_sim_b200 import BatchedNuclearPlantSimulator, load_snapshot
+    s, p = load_snapshot()
+    with pytest.raises(_clib.NpsError):
+        BatchedNuclearPlantSimulator(4, s, p)
+
+
+def test_product_does_not_touch_oracle():
+    """The product path must never import / link / call anything under oracle/."""
+    pkg = os.path.join(ROOT, "nuclear-sim_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cuh", ".inc")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "libnps_oracle" not in text and "cpu_port" not in text, f"{f} references the oracle library"
+                for line in text.splitlines():
+                    if re.match(r"\s*(from|import)\s+oracle\b", line):
+                        raise AssertionError(f"{f} imports oracle: {line}")

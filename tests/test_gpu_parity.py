@@ -1,0 +1,165 @@
+"""GPU: the CUDA path, called through the C ABI, against (a) the committed reference fixtures and
+(b) the host oracle on seeded batches; plus size-independent properties at BASELINE sizes."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from tests import _util as U
+
+pytestmark = pytest.mark.gpu
+
+SCENARIOS = ["cfg1_oil_top_off", "cfg2_steady", "cfg3_loadfollow", "cfg4_scram", "cfg5_degradation"]
+
+
+def _sim(state0, params):
+    from nuclear_sim_b200 import BatchedNuclearPlantSimulator
+    return BatchedNuclearPlantSimulator(state0.shape[0], state0, params, device="cuda:0")
+
+
+def _advance(sim, g, t0, t1, kmax=64):
+    """Advance with fused substeps, splitting launches at injection points."""
+    import torch
+    t = t0
+    inj = g["inject"]
+    while t < t1:
+        for p in range(sim.n_plants):
+            if not np.isnan(inj[t, p, 0]):
+                sim.slab[int(inj[t, p, 0]), p] = float(inj[t, p, 1])
+        k = 1
+        while t + k < t1 and k < kmax and np.isnan(inj[t + k, :, 0]).all():
+            k += 1
+        sim.step(actions=torch.from_numpy(np.ascontiguousarray(g["actions"][t:t + k])),
+                 magnitudes=torch.from_numpy(np.ascontiguousarray(g["magnitudes"][t:t + k])),
+                 noise=torch.from_numpy(np.ascontiguousarray(g["noise"][t:t + k].transpose(0, 2, 1))),
+                 power_setpoint=torch.from_numpy(np.ascontiguousarray(g["setpoint"][t:t + k])), K=k)
+        t += k
+
+
+@pytest.mark.parametrize("name", SCENARIOS)
+def test_cuda_matches_reference_fixture(name):
+    g = U.load_golden(name)
+    sim = _sim(g["state0"], g["params"])
+    t = 0
+    for c, cp in enumerate(g["checkpoints"]):
+        _advance(sim, g, t, int(cp))
+        t = int(cp)
+        tol = U.TOL_STEP * max(1, min(t, 1000)) if t < 3600 else U.TOL_LONG
+        U.assert_states_close(sim.state_numpy(), g["states"][c], tol, f"{name} step {t}")
+        obs = sim.get_observation().cpu().numpy()
+        assert U.rel_err(obs, g["obs"][c]).max() <= 1e-9
+
+
+def test_cuda_scram_steps_bit_exact():
+    import torch
+    g = U.load_golden("cfg4_scram")
+    sim = _sim(g["state0"], g["params"])
+    T = g["actions"].shape[0]
+    first = np.full(sim.n_plants, -1)
+    for t in range(T):
+        for p in range(sim.n_plants):
+            if not np.isnan(g["inject"][t, p, 0]):
+                sim.slab[int(g["inject"][t, p, 0]), p] = float(g["inject"][t, p, 1])
+        out = sim.step(actions=torch.from_numpy(g["actions"][t]), magnitudes=torch.from_numpy(g["magnitudes"][t]),
+                       noise=torch.from_numpy(np.ascontiguousarray(g["noise"][t].T)))
+        d = out["done"].cpu().numpy()
+        first[(first < 0) & d] = t
+        np.testing.assert_allclose(sim.state.power_level.cpu().numpy(), g["power_level"][t], rtol=1e-9, atol=1e-12)
+    assert first.tolist() == g["done_step"].tolist()
+
+
+@pytest.mark.parametrize("n,steps,k", [(1, 20, 1), (33, 16, 4), (4096, 12, 6)])
+def test_cuda_matches_host_oracle_on_random_batch(oracle_lib, n, steps, k):
+    """Seeded, ragged batch sizes (1, non-multiple-of-warp, config-#2 size): perturbed ICs, random actions."""
+    import torch
+    from nuclear_sim_b200 import field_index, load_snapshot
+    s0, params = load_snapshot("pwr3000_reactor_dt1")
+    ix = field_index()
+    rng = np.random.RandomState(123 + n)
+    st = np.tile(s0, (n, 1))
+    for f, lo, hi in (("pri.control_rod_position", 80, 100), ("pri.fuel_temperature", 540, 620),
+                      ("fw.pump[0].lub.oil_level", 20, 95), ("fw.pump[1].lub.component_wear[2]", 0, 8),
+                      ("sgs.sg[0].tif_scale_thickness", 0, 1.0), ("turb.lub.oil_contamination_level", 2, 12),
+                      ("cond.fl_biofouling_thickness", 0, 1.0), ("sgs.sg[1].water_level", 11.5, 13.5)):
+        st[:, ix[f]] = rng.uniform(lo, hi, n)
+    acts = rng.choice([0, 1, 2, 3, 4, 5, 8, 9, 10], size=(steps, n)).astype(np.int8)
+    mags = rng.uniform(0.2, 1.0, (steps, n))
+    noise = np.stack([rng.standard_normal((steps, n)), rng.standard_normal((steps, n)), rng.random_sample((steps, n)),
+                      rng.random_sample((steps, n)), rng.random_sample((steps, n))], axis=2)   # [T, n, 5]
+    setp = np.full((steps, n), np.nan)
+    ref = U.oracle_run(oracle_lib, st, params, acts, mags, noise, setp, None, 0, steps)
+    sim = _sim(st, params)
+    for t in range(0, steps, k):
+        sim.step(actions=torch.from_numpy(acts[t:t + k]), magnitudes=torch.from_numpy(mags[t:t + k]),
+                 noise=torch.from_numpy(np.ascontiguousarray(noise[t:t + k].transpose(0, 2, 1))), K=k)
+    U.assert_states_close(sim.state_numpy(), ref, U.TOL_STEP * steps, f"n={n}")
+
+
+def test_fused_substeps_equal_single_steps():
+    """K fused substeps in one launch == K launches of one step (bitwise)."""
+    import torch
+    from nuclear_sim_b200 import load_snapshot
+    s0, params = load_snapshot("pwr3000_oil_top_off_dt5")
+    n, K = 257, 8
+    rng = np.random.RandomState(5)
+    noise = torch.from_numpy(np.stack([rng.standard_normal((K, n)), rng.standard_normal((K, n)), rng.random_sample((K, n)),
+                                       rng.random_sample((K, n)), rng.random_sample((K, n))], axis=1))
+    a = _sim(np.tile(s0, (n, 1)), params)
+    b = _sim(np.tile(s0, (n, 1)), params)
+    a.step(noise=noise, K=K)
+    for k in range(K):
+        b.step(noise=noise[k], K=1)
+    assert torch.equal(a.slab, b.slab)
+
+
+def test_identical_plants_stay_identical_at_65536():
+    """BASELINE size property: plants are independent, so identical ICs + identical inputs give identical
+    trajectories for every plant, and permuting plants permutes results."""
+    import torch
+    from nuclear_sim_b200 import load_snapshot
+    s0, params = load_snapshot("pwr3000_reactor_dt1")
+    n = 65536
+    sim = _sim(np.tile(s0, (n, 1)), params)
+    act = torch.full((4, n), 1, dtype=torch.int8)
+    sim.step(actions=act, K=4)
+    assert bool((sim.slab == sim.slab[:, :1]).all())
+    one = _sim(s0[None, :], params)
+    one.step(actions=torch.full((4, 1), 1, dtype=torch.int8), K=4)
+    assert torch.equal(sim.slab[:, 12345], one.slab[:, 0])
+
+
+def test_threshold_flags_and_ring_buffer():
+    import torch
+    from nuclear_sim_b200 import field_index, load_snapshot
+    s0, params = load_snapshot("pwr3000_oil_top_off_dt5")
+    ix = field_index()
+    n = 1000
+    st = np.tile(s0, (n, 1))
+    rng = np.random.RandomState(0)
+    st[:, ix["fw.pump[0].lub.oil_level"]] = rng.uniform(55, 65, n)
+    sim = _sim(st, params)
+    rows = [("fw.pump[0].lub.oil_level", "<", 58.0, 168.0), (None, ">", 1.0, 1.0),
+            ("sgs.sg[0].tsp_fouling_fraction", ">", 0.3, 1.0), ("pri.power_level", ">=", 50.0, 0.25)]
+    sim.set_thresholds(rows)
+    sim.set_logged_fields(["pri.power_level", "fw.pump[0].lub.oil_level", "sec.electrical_power_output"], ring_rows=4)
+    fired_total = np.zeros(n, dtype=int)
+    for step in range(6):
+        sim.step()
+        sim.log_row()
+        flags, anyw = sim.check_thresholds()
+        ev = sim.drain_events()
+        lvl = sim.state["fw.pump[0].lub.oil_level"].cpu().numpy()
+        f0 = {p for p, t in ev if t == 0}
+        fired_total[list(f0)] += 1
+        # a plant fires threshold 0 exactly once (cooldown 168 h) and only when below 58 %
+        assert all(lvl[p] < 58.0 for p in f0)
+        assert not any(t == 1 for _, t in ev)            # unbound threshold is inert
+        f3 = {p for p, t in ev if t == 3}
+        # power >= 50 with a 15-minute cooldown at dt = 5 min fires on steps 0, 3
+        assert (len(f3) == n) == (step % 3 == 0)
+    lvl = sim.state["fw.pump[0].lub.oil_level"].cpu().numpy()
+    assert ((fired_total == 1) == (lvl < 58.0)).all() and fired_total.max() == 1
+    log = sim.drain_log()
+    assert log.shape == (4, 3, n)
+    np.testing.assert_array_equal(log[-1, 1], lvl)
+    np.testing.assert_array_equal(log[-1, 0], sim.state.power_level.cpu().numpy())
