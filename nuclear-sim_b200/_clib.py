@@ -22,7 +22,7 @@ def lib() -> ctypes.CDLL:
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.LIB_PATH
+    path = os.environ.get("NPS_B200_LIB", _build.LIB_PATH)   # tuning variants only; default is the in-tree build
     if not os.path.exists(path):
         raise NpsError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                        "(nvcc, sm_100a). nuclear_sim_b200 has no CPU fallback.")

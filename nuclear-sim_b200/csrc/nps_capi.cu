@@ -50,9 +50,15 @@ struct nps_handle {
 // ------------------------------------------------------------------------------------------------
 // step kernel: thread-per-plant, state register/local resident across k substeps
 // ------------------------------------------------------------------------------------------------
-constexpr int kStepBlock = 64;
+#ifndef NPS_STEP_BLOCK
+#define NPS_STEP_BLOCK 64
+#endif
+#ifndef NPS_STEP_MINBLOCKS
+#define NPS_STEP_MINBLOCKS 7   /* <=128 registers: 448 threads/SM, so 65,536 plants are ONE wave on 148 SMs */
+#endif
+constexpr int kStepBlock = NPS_STEP_BLOCK;
 
-__global__ void __launch_bounds__(kStepBlock)
+__global__ void __launch_bounds__(kStepBlock, NPS_STEP_MINBLOCKS)
 nps_step_kernel(double* __restrict__ slab, const __grid_constant__ PlantParams prm, const int8_t* __restrict__ action,
                 const double* __restrict__ magnitude, const double* __restrict__ noise,
                 const double* __restrict__ setpoint, int k_substeps, int64_t n,

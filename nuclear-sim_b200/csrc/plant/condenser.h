@@ -136,6 +136,7 @@ NPS_HD void vacuum_update(CondenserState& C, const PlantParams& p, double target
     }
     for (int i = 0; i < 2; ++i) if (cmd[i] >= 0) ejector_command(C.ejector[i], p, i, cmd[i], C.vs_motive_steam_pressure);
     double total_capacity = 0.0, total_steam = 0.0;
+    NPS_UNIT_LOOP
     for (int i = 0; i < 2; ++i) {
         int n_running = (is_true(C.ejector[0].is_operating) ? 1 : 0) + (is_true(C.ejector[1].is_operating) ? 1 : 0);
         double req = is_true(C.ejector[i].is_operating) ? required / (double)(n_running > 1 ? n_running : 1) : 0.0;

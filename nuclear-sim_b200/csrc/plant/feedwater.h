@@ -426,6 +426,7 @@ NPS_HD void feedwater_update(FeedwaterState& fw, WaterChemState& wc, const Plant
     double total_flow = 0.0, total_power = 0.0;
     int n_running = 0;
     double speed_sum = 0.0, perf_sum = 0.0;
+    NPS_UNIT_LOOP
     for (int k = 0; k < 4; ++k) {
         FWPumpState& u = fw.pump[k];
         if ((int)u.status == PUMP_RUNNING && n_prev > 0) {
@@ -451,6 +452,7 @@ NPS_HD void feedwater_update(FeedwaterState& fw, WaterChemState& wc, const Plant
     // PerformanceDiagnostics.update_diagnostics: feedwater/performance_monitoring.py:423-542
     double tot_risk = 0.0, tot_wear = 0.0, tot_vib = 0.0;
     double wear_for_protection = 0.0;
+    NPS_UNIT_LOOP
     for (int k = 0; k < 4; ++k) {
         FWPumpState& u = fw.pump[k];
         double npsh_req = fwp_dynamic_npsh_required(u, p);

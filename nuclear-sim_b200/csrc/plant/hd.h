@@ -19,6 +19,14 @@
 #define NPS_HD_NOINLINE
 #endif
 
+// Loops over repeated plant units (4 pumps, 3 SGs, 14 stages, 4 bearings) stay rolled on the device unless
+// NPS_UNROLL_UNITS is defined: the step kernel is ~36 K SASS instructions and instruction-cache bound otherwise.
+#if defined(__CUDA_ARCH__) && !defined(NPS_UNROLL_UNITS)
+#define NPS_UNIT_LOOP _Pragma("unroll 1")
+#else
+#define NPS_UNIT_LOOP
+#endif
+
 namespace nps {
 
 // Python builtin max(a, b): returns a unless b > a.  (max(0, nan) == 0, max(nan, 0) is nan)

@@ -306,6 +306,7 @@ NPS_HD void sg_system_update(SGSystemState& S, const PlantParams& p, const doubl
         if (tpf > 0) { for (int i = 0; i < 3; ++i) demands[i] = total_steam * (flow_rates[i] / tpf); }
         else { for (int i = 0; i < 3; ++i) demands[i] = total_steam / 3; }
     }
+    NPS_UNIT_LOOP
     for (int i = 0; i < 3; ++i)
         sg_update(S.sg[i], p, inlet_temps[i], outlet_temps[i], flow_rates[i], demands[i], actual_feedwater_flows[i],
                   feedwater_temperature, dt);

@@ -290,6 +290,7 @@ NPS_HD void turbine_update(TurbineState& T, const PlantParams& p, const SGSystem
     {
         double cur_p = steam_pressure, cur_t = steam_temperature_in, cur_f = steam_flow;
         const double final_pressure = 0.007;
+        NPS_UNIT_LOOP
         for (int k = 0; k < 14; ++k) {
             double ratio = stage_dynamic_pressure_ratio(p, k, 14, cur_p, steam_flow);
             double outp = cur_p * ratio;
@@ -361,6 +362,7 @@ NPS_HD void turbine_update(TurbineState& T, const PlantParams& p, const SGSystem
         }
         const double weight_per_bearing = p.rd_rotor_mass * 9.81 / 1000.0 / 4;
         const double steam_thrust = (100.0 * load_demand) / 4;
+        NPS_UNIT_LOOP
         for (int b = 0; b < 4; ++b) {
             TurbineBearingState& B = T.bearing[b];
             // calculate_bearing_loads: rotor_dynamics.py:83-130 (TB-003 is the thrust bearing)

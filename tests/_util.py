@@ -68,10 +68,30 @@ def canonicalize(v):
     return flat.reshape(v.shape)
 
 
+def field_scales():
+    """Natural magnitude below which a field is compared absolutely.  Default ABS_FLOOR; fields computed by
+    catastrophic cancellation get their physical scale: tsp_flow_maldistribution is std/mean of seven nearly equal
+    restrictions (a 0..1 factor tested against 0.30, tsp_fouling_model.py:369-392), so a 1-ulp libm difference
+    in the restrictions is an absolute 1e-14 error on a quantity that may itself be 1e-7."""
+    from nuclear_sim_b200 import field_names
+    names = field_names("PlantState")
+    sc = np.full(len(names), ABS_FLOOR)
+    for i, n in enumerate(names):
+        if n.endswith("tsp_flow_maldistribution"):
+            sc[i] = 1.0
+        # restriction = 1 - A_eff/A_orig with A_eff ~ A_orig for a clean plate (tsp_fouling_model.py:302-340): the
+        # fouling fraction and everything proportional to it carry an absolute ~1e-16 rounding error, whatever
+        # their size; their physical scale is 0..1 (stage thresholds 0.4 / 0.7 / 0.85).
+        elif n.endswith(("tsp_fouling_fraction", "tsp_heat_transfer_degradation", "tsp_cumulative_power_loss")):
+            sc[i] = 1e-6
+    return sc
+
+
 def rel_err(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
-    den = np.maximum(np.abs(b), ABS_FLOOR)
+    floor = field_scales() if a.shape[-1] == len(field_scales()) else ABS_FLOOR
+    den = np.maximum(np.abs(b), floor)
     e = np.abs(a - b) / den
     e[a == b] = 0.0
     e[np.isnan(a) & np.isnan(b)] = 0.0
