@@ -56,6 +56,12 @@ struct nps_handle {
 #ifndef NPS_STEP_MINBLOCKS
 #define NPS_STEP_MINBLOCKS 7   /* <=128 registers: 448 threads/SM, so 65,536 plants are ONE wave on 148 SMs */
 #endif
+#ifndef NPS_COPY_UNROLL
+#define NPS_COPY_UNROLL 8   /* loads in flight per thread while the slab is copied in / out; 2, 4, 24 and 48 all
+                               measured slower on B200 (profiles/r01_tuning_variants.txt) */
+#endif
+#define NPS_STR_(x) #x
+#define NPS_PRAGMA_UNROLL(n) _Pragma(NPS_STR_(unroll n))
 constexpr int kStepBlock = NPS_STEP_BLOCK;
 
 __global__ void __launch_bounds__(kStepBlock, NPS_STEP_MINBLOCKS)
@@ -67,7 +73,7 @@ nps_step_kernel(double* __restrict__ slab, const __grid_constant__ PlantParams p
     if (p >= n) return;
     PlantState st;
     double* sv = reinterpret_cast<double*>(&st);
-#pragma unroll 8
+NPS_PRAGMA_UNROLL(NPS_COPY_UNROLL)
     for (int f = 0; f < kNState; ++f) sv[f] = slab[(int64_t)f * n + p];
     bool scrammed = false;
     for (int k = 0; k < k_substeps; ++k) {
@@ -84,7 +90,7 @@ nps_step_kernel(double* __restrict__ slab, const __grid_constant__ PlantParams p
         plant_step(st, prm, in);
         scrammed |= is_true(st.pri.scram_activated);
     }
-#pragma unroll 8
+NPS_PRAGMA_UNROLL(NPS_COPY_UNROLL)
     for (int f = 0; f < kNState; ++f) slab[(int64_t)f * n + p] = sv[f];
     if (obs) {
         struct ObsOut { double* o; int64_t n; int64_t p; struct Ref { double* a; NPS_HD void operator=(double v) { *a = v; } };

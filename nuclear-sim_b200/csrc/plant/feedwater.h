@@ -5,6 +5,7 @@
 #pragma once
 #include "hd.h"
 #include "state.h"
+#include "prefetch.h"
 #include "lubrication.h"
 #include "water_chemistry.h"
 
@@ -362,7 +363,8 @@ struct FeedwaterResult {
 NPS_HD void feedwater_update(FeedwaterState& fw, WaterChemState& wc, const PlantParams& p,
                              const double* sg_levels, const double* sg_steam_flows, const double* sg_steam_qualities,
                              double manual_total_flow, double fw_temperature, double suction_pressure,
-                             double discharge_pressure, double dt, FeedwaterResult& out) {
+                             double discharge_pressure, double dt, FeedwaterResult& out,
+                             const SGState* prefetch_next = nullptr) {
     const int nsg = 3;
     const MakeupWater mk = {7.2, 100.0, 300.0, 30.0, 8.0};
     wc_update(wc, true, mk, 0.02, dt);
@@ -429,6 +431,8 @@ NPS_HD void feedwater_update(FeedwaterState& fw, WaterChemState& wc, const Plant
     NPS_UNIT_LOOP
     for (int k = 0; k < 4; ++k) {
         FWPumpState& u = fw.pump[k];
+        if (k < 3) NPS_PREFETCH_FAR(fw.pump[k + 1]);
+        else if (prefetch_next) NPS_PREFETCH_FAR(*prefetch_next);   // what runs after the feedwater system
         if ((int)u.status == PUMP_RUNNING && n_prev > 0) {
             if (n_running < n_prev) {
                 if (!(flow_per_pump < p.fwp_rated_flow * 0.2)) fwp_set_flow_demand(u, p, flow_per_pump);

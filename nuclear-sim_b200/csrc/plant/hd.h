@@ -27,6 +27,34 @@
 #define NPS_UNIT_LOOP
 #endif
 
+// Software prefetch of plant state (device only).  A thread's PlantState lives in local memory and streams
+// through L1/L2 from HBM every substep (10 KB per plant x 448 plants per SM does not fit on chip), so loads issued
+// at the point of use expose the full DRAM latency.  NPS_PREFETCH(obj) issues prefetch.L1 for the fields of obj that
+// are live on entry to a step (live_gen.inc) a few thousand instructions ahead of their first use; local memory
+// interleaves 32-bit words across the warp, so each double needs both of its words prefetched.
+// NPS_PREFETCH: short distance (about one turbine stage, < 3 K instructions) into L1.  NPS_PREFETCH_FAR: one whole
+// pump / steam generator / subsystem ahead; an L1 line does not survive that long under 14 warps of streaming
+// traffic per SM, so the far variant targets L2 (NPS_PF_FAR_LEVEL: 0 off, 1 L1, 2 L2).
+#ifndef NPS_PF_NEAR_LEVEL
+#define NPS_PF_NEAR_LEVEL 1
+#endif
+#ifndef NPS_PF_FAR_LEVEL
+#define NPS_PF_FAR_LEVEL 0   /* measured on B200 (profiles/r01_prefetch_variants.txt): far prefetch costs 12-25 %, near is neutral */
+#endif
+#if defined(__CUDA_ARCH__) && !defined(NPS_NO_PREFETCH)
+#define NPS_PF2_L1(a, off) do { asm volatile("prefetch.L1 [%0];" ::"l"((a) + (off))); \
+                                asm volatile("prefetch.L1 [%0];" ::"l"((a) + (off) + 4)); } while (0)
+#define NPS_PF2_L2(a, off) do { asm volatile("prefetch.L2 [%0];" ::"l"((a) + (off))); \
+                                asm volatile("prefetch.L2 [%0];" ::"l"((a) + (off) + 4)); } while (0)
+#define NPS_PF2(a, off) do { if (LEVEL == 1) NPS_PF2_L1(a, off); else if (LEVEL == 2) NPS_PF2_L2(a, off); } while (0)
+#define NPS_PREFETCH(obj) nps_prefetch_live<NPS_PF_NEAR_LEVEL>(obj)
+#define NPS_PREFETCH_FAR(obj) nps_prefetch_live<NPS_PF_FAR_LEVEL>(obj)
+#else
+#define NPS_PF2(a, off) ((void)0)
+#define NPS_PREFETCH(obj) ((void)0)
+#define NPS_PREFETCH_FAR(obj) ((void)0)
+#endif
+
 namespace nps {
 
 // Python builtin max(a, b): returns a unless b > a.  (max(0, nan) == 0, max(nan, 0) is nan)
@@ -42,7 +70,19 @@ NPS_HD double np_clip(double x, double lo, double hi) {
 }
 // Python/numpy scalar `x ** y` on floats is libm pow (even for y == 2: glibc pow(x, 2.0) differs from
 // x*x in ~0.08 % of cases, so the host build uses -fno-builtin-pow to keep the libm call).
-NPS_HD double py_pow(double x, double y) { return pow(x, y); }
+// On the device the exponents whose result is exactly computable go through correctly-rounded arithmetic
+// instead of libdevice's general pow (<= 2 ulp, ~230 SASS instructions per call and 35 % of the step kernel's
+// executed instructions in the round-1 profile): x*x and sqrt(x) ARE the correctly rounded pow(x, 2) and
+// pow(x, 0.5), i.e. at least as close to glibc's (<= 0.52 ulp) as libdevice pow is.  The exponent is a literal at
+// most call sites, so the test folds away; the wear exponents are batch-uniform parameters (uniform branch).
+NPS_HD double py_pow(double x, double y) {
+#if defined(__CUDA_ARCH__) && !defined(NPS_GENERIC_POW)
+    if (y == 2.0) return x * x;
+    if (y == 1.0) return x;
+    if (y == 0.5 && x > 0.0 && x < 1.7e308) return sqrt(x);
+#endif
+    return pow(x, y);
+}
 NPS_HD double py_abs(double x) { return fabs(x); }
 NPS_HD double np_sign(double x) { return (x > 0.0) ? 1.0 : ((x < 0.0) ? -1.0 : ((x == 0.0) ? 0.0 : x)); }
 NPS_HD bool   is_true(double flag) { return flag != 0.0; }

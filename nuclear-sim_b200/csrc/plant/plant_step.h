@@ -4,6 +4,7 @@
 #pragma once
 #include "hd.h"
 #include "state.h"
+#include "prefetch.h"
 #include "primary.h"
 #include "secondary.h"
 
@@ -68,6 +69,14 @@ NPS_HD void plant_secondary_to_primary(PlantState& st) {
 
 NPS_HD void plant_step(PlantState& st, const PlantParams& p, const StepInput& in) {
     const double dt = p.dt;
+    NPS_PREFETCH(st.pri);
+    NPS_PREFETCH(st.sim);
+    if (is_true(p.enable_secondary)) {   // first consumers after the primary update: feedwater control and pump 0
+        NPS_PREFETCH(st.sec);
+        NPS_PREFETCH(st.fw);
+        NPS_PREFETCH(st.wc_main);
+        NPS_PREFETCH_FAR(st.fw.pump[0]);
+    }
     primary_update(st.pri, p, in, dt);
     if (is_true(p.enable_secondary)) {
         PrimaryConditions pc;

@@ -7,6 +7,7 @@
 #pragma once
 #include "hd.h"
 #include "state.h"
+#include "prefetch.h"
 #include "feedwater.h"
 #include "sg.h"
 #include "turbine.h"
@@ -64,12 +65,12 @@ NPS_HD void secondary_update(PlantState& st, const PlantParams& p, const Primary
     // STEP 1 feedwater: :445-491
     FeedwaterResult fwr;
     feedwater_update(st.fw, st.wc_main, p, S.prev_sg_levels, S.prev_sg_steam_flows, S.prev_sg_steam_qualities,
-                     est_total_flow, 40.0, 0.5, 7.4, dt, fwr);
+                     est_total_flow, 40.0, 0.5, 7.4, dt, fwr, &st.sgs.sg[0]);
     // STEP 2 steam generators: :493-535 ('sg_i' keys are absent from sg_flow_distribution -> equal split)
     double fw_flows[3];
     for (int i = 0; i < 3; ++i) fw_flows[i] = fwr.total_flow_rate / 3;
     sg_system_update(st.sgs, p, pc.inlet_temp, pc.outlet_temp, pc.flow, load_fraction, S.load_demand / 100.0,
-                     actual_fw_temp, fw_flows, dt * 60);
+                     actual_fw_temp, fw_flows, dt * 60, &st.turb);
     for (int i = 0; i < 3; ++i) {
         S.prev_sg_levels[i] = st.sgs.sg[i].water_level;
         S.prev_sg_pressures[i] = st.sgs.sg[i].secondary_pressure;
@@ -85,7 +86,7 @@ NPS_HD void secondary_update(PlantState& st, const PlantParams& p, const Primary
 
     // STEP 5 turbine: :565-570
     TurbineResult tr;
-    turbine_update(st.turb, p, st.sgs, S.load_demand, 0.007, dt / 60.0, tr);
+    turbine_update(st.turb, p, st.sgs, S.load_demand, 0.007, dt / 60.0, tr, &st.cond);
 
     // LP-6 exhaust quality: :591-607
     double lp_quality = 0.90;
@@ -97,6 +98,8 @@ NPS_HD void secondary_update(PlantState& st, const PlantParams& p, const Primary
             lp_quality = py_max(0.0, py_min(1.0, lp_quality));
         }
     }
+    NPS_PREFETCH_FAR(st.ph);       // consumers after the condenser: shared water chemistry (2nd update) and pH control
+    NPS_PREFETCH_FAR(st.wc_main);
     CondenserResult cr;
     condenser_update(st.cond, p, tr.condenser_pressure, tr.condenser_temperature, tr.effective_steam_flow, lp_quality,
                      cooling_water_flow, S.cooling_water_temperature, 1.2, 185.0, dt / 60.0, cr);

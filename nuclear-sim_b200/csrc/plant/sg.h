@@ -6,6 +6,7 @@
 #pragma once
 #include "hd.h"
 #include "state.h"
+#include "prefetch.h"
 
 namespace nps {
 
@@ -295,7 +296,8 @@ NPS_HD void sg_update(SGState& g, const PlantParams& p, double t_in, double t_ou
 // EnhancedSteamGeneratorPhysics.update_system: steam_generator/enhanced_physics.py:433-547
 NPS_HD void sg_system_update(SGSystemState& S, const PlantParams& p, const double* inlet_temps, const double* outlet_temps,
                              const double* flow_rates, double load_demand_fraction, double system_load_demand,
-                             double feedwater_temperature, const double* actual_feedwater_flows, double dt) {
+                             double feedwater_temperature, const double* actual_feedwater_flows, double dt,
+                             const TurbineState* prefetch_next = nullptr) {
     S.load_demand = system_load_demand;
     double total_steam = p.sg_design_total_steam_flow * load_demand_fraction;
     double demands[3];
@@ -307,9 +309,15 @@ NPS_HD void sg_system_update(SGSystemState& S, const PlantParams& p, const doubl
         else { for (int i = 0; i < 3; ++i) demands[i] = total_steam / 3; }
     }
     NPS_UNIT_LOOP
-    for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < 3; ++i) {
+        if (i < 2) NPS_PREFETCH_FAR(S.sg[i + 1]);
+        else if (prefetch_next) {   // the turbine's lubrication pre-step and bearing set come next
+            NPS_PREFETCH_FAR(*prefetch_next);
+            for (int b = 0; b < 4; ++b) NPS_PREFETCH_FAR(prefetch_next->bearing[b]);
+        }
         sg_update(S.sg[i], p, inlet_temps[i], outlet_temps[i], flow_rates[i], demands[i], actual_feedwater_flows[i],
                   feedwater_temperature, dt);
+    }
     double q = 0.0, f = 0.0, pr = 0.0, te = 0.0, ql = 0.0;
     int effective = 0;
     for (int i = 0; i < 3; ++i) {

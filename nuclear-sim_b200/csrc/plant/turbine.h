@@ -7,6 +7,7 @@
 #pragma once
 #include "hd.h"
 #include "state.h"
+#include "prefetch.h"
 #include "lubrication.h"
 #include "sg.h"
 
@@ -267,7 +268,9 @@ struct TurbineResult {
 
 // Wrapped EnhancedTurbinePhysics.update_state (dt in hours; load_demand as passed = percent)
 NPS_HD void turbine_update(TurbineState& T, const PlantParams& p, const SGSystemState& S, double load_demand,
-                           double condenser_pressure, double dt, TurbineResult& out) {
+                           double condenser_pressure, double dt, TurbineResult& out,
+                           const CondenserState* prefetch_next = nullptr) {
+    NPS_PREFETCH(T.stage[0]);
     turbine_lubrication_prestep(T, p, dt);
 
     const double steam_pressure = S.average_steam_pressure, steam_temperature_in = S.average_steam_temperature;
@@ -292,6 +295,7 @@ NPS_HD void turbine_update(TurbineState& T, const PlantParams& p, const SGSystem
         const double final_pressure = 0.007;
         NPS_UNIT_LOOP
         for (int k = 0; k < 14; ++k) {
+            if (k < 13) NPS_PREFETCH(T.stage[k + 1]);
             double ratio = stage_dynamic_pressure_ratio(p, k, 14, cur_p, steam_flow);
             double outp = cur_p * ratio;
             outp = py_max(outp, final_pressure);
@@ -308,8 +312,10 @@ NPS_HD void turbine_update(TurbineState& T, const PlantParams& p, const SGSystem
             total_extraction += T.stage[k].extraction_flow;
             if (k < 8) hp_power += T.stage[k].power_output; else lp_power += T.stage[k].power_output;
             cur_p = T.stage[k].outlet_pressure; cur_t = T.stage[k].outlet_temperature; cur_f = T.stage[k].outlet_flow;
-        }
-        for (int k = 0; k < 14; ++k) {   // TurbineStage.update_degradation: stage_system.py:294-339
+            // TurbineStage.update_degradation: stage_system.py:294-339.  The reference runs it in a second pass over
+            // the 14 stages (stage_system.py:988-990); a stage's degradation touches only that stage's own
+            // factors, which no later stage reads, so doing it here is the same arithmetic on the same values while
+            // the stage record is still on chip.
             TurbineStageState& s = T.stage[k];
             s.efficiency_degradation += p.ts_fouling_rate * dt;
             s.deposit_thickness += p.ts_deposit_buildup_rate * dt;
@@ -320,6 +326,11 @@ NPS_HD void turbine_update(TurbineState& T, const PlantParams& p, const SGSystem
             s.blade_condition_factor = py_min(s.fouling_factor, s.blade_wear_factor);
             s.actual_efficiency = py_max(0.7, p.ts_design_efficiency[k] - s.efficiency_degradation);
             s.operating_hours += dt;
+        }
+        if (prefetch_next) {
+            NPS_PREFETCH_FAR(*prefetch_next);
+            NPS_PREFETCH_FAR(prefetch_next->ejector[0]);
+            NPS_PREFETCH_FAR(prefetch_next->ejector[1]);
         }
         T.ss_total_power_output = total_power * psf;
         T.ss_total_steam_flow = steam_flow;

@@ -1,0 +1,7 @@
+#!/bin/bash
+# usage: sweep_plants.sh "<variants>" "<plant counts>"
+for v in $1; do for n in $2; do
+  lib="NPS_B200_LIB=$PWD/nuclear-sim_b200/_lib/libnps_b200_$v.so"
+  echo -n "variant=$v plants=$n  "
+  env $lib python bench.py --steps 8 --warmup 3 --no-cpu-baseline --plants-per-gpu $n 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('value %.3e  e2e %.3e  ms/launch %.3f' % (d['value'], d['e2e']['value'], d['ms_per_step']))"
+done; done
