@@ -73,7 +73,10 @@ int nps_step_host(nps_handle* h, double* d_state, const int8_t* h_action, const 
 int nps_observe(nps_handle* h, const double* d_state, double* d_obs, double* d_reward, void* cuda_stream);
 
 /* --- threshold monitoring (StateManager._check_maintenance_thresholds, state_manager.py:1307-1369) ---
- * A threshold row is (field, comparator, value, cooldown_minutes); comparator: 0 '>', 1 '<', 2 '>=', 3 '<=', 4 '=='(±1e-3).
+ * A threshold row is (field, comparator, value, cooldown_minutes); comparator: 0 '>', 1 '<', 2 '>=', 3 '<=',
+ * 4 '=='(|v-x| < 1e-3), 5 '!='.  field >= 0: PlantState field; field == -1: inert row (the reference finds no logged
+ * column for it, state_manager.py:1371-1410); field <= -2: derived column, code -(2 + 4*kind + unit), kind 0 =
+ * sum_wear_level of feedwater pump `unit` (feedwater/pump_lubrication.py:1585-1596).
  * d_last_fired [n_thresholds][n_plants] holds the time (minutes) each threshold last fired (-inf = never).
  * Output: d_flags [n_words][n_plants] uint32 bit t%32 of word t/32 set when threshold t fired at time
  * now; d_any_warp [ceil(n_plants/32)] uint32 = warp ballot of "plant has any flag" (host drain index). */
@@ -89,6 +92,19 @@ int nps_check_thresholds(nps_handle* h, const double* d_state, double* d_last_fi
 int nps_set_logged_fields(nps_handle* h, const int32_t* fields, int n_logged);
 int nps_log_row(nps_handle* h, const double* d_state, double* d_ring, int64_t ring_rows, int64_t write_index,
                 void* cuda_stream);
+
+/* --- maintenance action effects (AutoMaintenanceSystem._execute_work_order -> component.perform_maintenance,
+ *     systems/maintenance/auto_maintenance.py:504-673) ---
+ * Applies n_requests (plant, target, action, arg) requests IN ORDER to the device state; requests for the same plant
+ * are serialised.  target: 0-3 FWP-1..4, 4 FEE-001, 5-7 SG-0..2, 8 SG system, 9-22 HP-1..LP-6, 23 turbine, 24 condenser.
+ * action: index into nps_maintenance_action_name(); arg: bearing selector for bearing_replacement
+ * (0 all, 1 motor_bearings, 2 pump_bearings, 3 thrust_bearing).  h_status[i]: 0 failed (MaintenanceResult.success
+ * False), 1 success, 2 target has no restated perform_maintenance.  Host arrays; synchronises on the stream. */
+int nps_n_maintenance_actions(void);
+const char* nps_maintenance_action_name(int action);
+int nps_apply_maintenance(nps_handle* h, double* d_state, const int32_t* h_plant, const int32_t* h_target,
+                          const int32_t* h_action, const int32_t* h_arg, int n_requests, int32_t* h_status,
+                          void* cuda_stream);
 
 /* gather selected fields of all plants to a host array out[n_fields][n_plants] (synchronous) */
 int nps_read_fields(nps_handle* h, const double* d_state, const int32_t* fields, int n_fields, double* out_host);

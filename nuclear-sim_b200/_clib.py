@@ -50,6 +50,10 @@ def lib() -> ctypes.CDLL:
     L.nps_set_logged_fields.argtypes = [c_void_p, c_void_p, c_int]
     L.nps_log_row.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]
     L.nps_read_fields.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p]
+    L.nps_n_maintenance_actions.restype = c_int
+    L.nps_maintenance_action_name.restype = c_char_p
+    L.nps_maintenance_action_name.argtypes = [c_int]
+    L.nps_apply_maintenance.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]
     if L.nps_abi_version() != 1:
         raise NpsError("libnps_b200.so ABI version mismatch")
     _LIB = L
@@ -65,4 +69,5 @@ EXPORTED_SYMBOLS = [
     "nps_abi_version", "nps_last_error", "nps_n_state", "nps_n_params", "nps_field_name", "nps_param_name",
     "nps_create", "nps_destroy", "nps_n_plants", "nps_set_params", "nps_step", "nps_step_host", "nps_observe",
     "nps_set_thresholds", "nps_check_thresholds", "nps_set_logged_fields", "nps_log_row", "nps_read_fields",
+    "nps_n_maintenance_actions", "nps_maintenance_action_name", "nps_apply_maintenance",
 ]

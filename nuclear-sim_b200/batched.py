@@ -182,11 +182,13 @@ class BatchedNuclearPlantSimulator:
     def set_thresholds(self, rows) -> None:
         """rows: iterable of (field_name_or_None, comparator, value, cooldown_hours)."""
         cmp_code = {">": 0, "greater_than": 0, "<": 1, "less_than": 1, ">=": 2, "greater_equal": 2,
-                    "<=": 3, "less_equal": 3, "==": 4, "equals": 4}
+                    "<=": 3, "less_equal": 3, "==": 4, "equals": 4, "!=": 5, "not_equals": 5}
         ix = field_index()
         rows = list(rows)
-        f = np.array([ix[r[0]] if r[0] is not None else -1 for r in rows], dtype=np.int32)
-        c = np.array([cmp_code[r[1]] for r in rows], dtype=np.int32)
+        # field: PlantState field name, None (inert row) or a raw int code (>= 0 field index, <= -2 derived column)
+        f = np.array([(-1 if r[0] is None else (int(r[0]) if isinstance(r[0], (int, np.integer)) else ix[r[0]])) for r in rows],
+                     dtype=np.int32)
+        c = np.array([cmp_code.get(r[1], 6) for r in rows], dtype=np.int32)   # unknown comparison never fires (state_manager.py:1441)
         v = np.array([r[2] for r in rows], dtype=np.float64)
         cd = np.array([r[3] * 60.0 for r in rows], dtype=np.float64)
         _clib.check(self.L.nps_set_thresholds(self._h, f.ctypes.data_as(ctypes.c_void_p), c.ctypes.data_as(ctypes.c_void_p),
@@ -229,6 +231,48 @@ class BatchedNuclearPlantSimulator:
                             ev.append((p, word * 32 + b))
                             bits &= bits - 1
         return ev
+
+    def reset_cooldowns(self, plant: int, rows: Sequence[int]) -> None:
+        """Forget when these thresholds of one plant last fired
+        (StateManager._reset_threshold_cooldowns_for_maintenance: state_manager.py:1783-1830)."""
+        self._thr["last"][torch.as_tensor(list(rows), dtype=torch.long, device=self.device), int(plant)] = -float("inf")
+
+    def read_threshold_values(self, plants: Sequence[int], table) -> Dict:
+        """{(plant, threshold index): value} of every bound threshold row for the given plants (the value the
+        violation record carries, state_manager.py:1343-1351)."""
+        plants = list(plants)
+        if not plants:
+            return {}
+        idx = torch.as_tensor(plants, dtype=torch.long, device=self.device)
+        sub = self.slab[:, idx].cpu().numpy()          # [n_state, len(plants)]
+        ix = field_index()
+        out = {}
+        for t, r in enumerate(table.rows):
+            if r.field:
+                vals = sub[ix[r.field]]
+            elif r.derived == "pump_sum_wear":
+                w = lambda c: sub[ix[f"{r.unit}lub.component_wear[{c}]"]]
+                vals = w(0) + np.maximum(np.maximum(w(1), w(2)), w(3)) + w(4)
+            else:
+                continue
+            for j, p in enumerate(plants):
+                out[(p, t)] = float(vals[j])
+        return out
+
+    # -- maintenance effects (auto_maintenance.py:504-673 -> csrc/plant/maintenance.h) ----------------------------
+    def apply_maintenance(self, requests) -> list:
+        """requests: iterable of (plant, target code, action code, arg); returns the per-request status codes
+        (0 failed, 1 success, 2 unsupported target), applied in order."""
+        req = np.array(list(requests), dtype=np.int32).reshape(-1, 4)
+        if len(req) == 0:
+            return []
+        cols = [np.ascontiguousarray(req[:, j]) for j in range(4)]
+        status = np.zeros(len(req), dtype=np.int32)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _clib.check(self.L.nps_apply_maintenance(self._h, _ptr(self.slab), *(c.ctypes.data_as(ctypes.c_void_p) for c in cols),
+                                                 len(req), status.ctypes.data_as(ctypes.c_void_p), ctypes.c_void_p(stream)))
+        self.n_launches += 1
+        return status.tolist()
 
     # -- trajectory ring buffer (state_manager.py:152-233) --------------------------------------
     def set_logged_fields(self, names: Sequence[str], ring_rows: int) -> None:

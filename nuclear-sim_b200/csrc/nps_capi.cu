@@ -7,14 +7,17 @@
 // cores, the bounds are the FP64 pipe and HBM.
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <string>
 #include <vector>
+#include <algorithm>
 #include <cmath>
 
 #include "../../include/nps_b200.h"
 #include "plant/plant_step.h"
+#include "plant/maintenance.h"
 #include "fields_gen.inc"
 
 using namespace nps;
@@ -131,6 +134,22 @@ __global__ void nps_observe_kernel(const double* __restrict__ slab, const __grid
 // threshold flag kernel: one thread per plant evaluates every threshold row; cooldown stamps in SoA;
 // __ballot_sync compacts "this plant fired something" into one word per warp for the host drain.
 // ------------------------------------------------------------------------------------------------
+// Logged columns that are pure functions of carried fields.  code = -(2 + 4 * kind + unit):
+//   kind 0  sum_wear_level of feedwater pump `unit` = impeller + max(motor, pump, thrust bearing) + seal wear
+//           (FeedwaterPumpLubricationSystem.get_state_dict: feedwater/pump_lubrication.py:1585-1596)
+__device__ __forceinline__ double threshold_derived(const double* __restrict__ slab, int64_t n, int64_t p, int code) {
+    const int k = -code - 2, kind = k >> 2, unit = k & 3;
+    if (kind == 0) {
+        const int f0 = (int)((offsetof(PlantState, fw) + offsetof(FeedwaterState, pump) + unit * sizeof(FWPumpState) +
+                              offsetof(FWPumpState, lub) + offsetof(LubCore, component_wear)) / sizeof(double));
+        const double* w = slab + (int64_t)f0 * n + p;
+        const double imp = w[0], mb = w[(int64_t)FWL_MOTOR_BRG * n], pb = w[(int64_t)FWL_PUMP_BRG * n];
+        const double tb = w[(int64_t)FWL_THRUST_BRG * n], sw = w[(int64_t)FWL_SEALS * n];
+        return imp + py_max3(mb, pb, tb) + sw;
+    }
+    return NAN;
+}
+
 __global__ void nps_threshold_kernel(const double* __restrict__ slab, const Threshold* __restrict__ thr, int n_thr,
                                      double now_minutes_field_unused, int time_field, double* __restrict__ last_fired,
                                      uint32_t* __restrict__ flags, uint32_t* __restrict__ any_warp, int64_t n) {
@@ -143,18 +162,20 @@ __global__ void nps_threshold_kernel(const double* __restrict__ slab, const Thre
         for (int t = 0; t < n_thr; ++t) {
             const Threshold th = thr[t];
             bool fire = false;
-            if (th.field >= 0) {
+            if (th.field != -1) {
                 const double last = last_fired[(int64_t)t * n + p];
                 // _is_threshold_in_cooldown: state_manager.py:1267-1305
                 const bool cooling = (now - last) < th.cooldown;
                 if (!cooling) {
-                    const double v = slab[(int64_t)th.field * n + p];
+                    const double v = (th.field >= 0) ? slab[(int64_t)th.field * n + p] : threshold_derived(slab, n, p, th.field);
                     switch (th.cmp) {   // _check_threshold_condition: state_manager.py:1412-1442
                         case 0: fire = v > th.value; break;
                         case 1: fire = v < th.value; break;
                         case 2: fire = v >= th.value; break;
                         case 3: fire = v <= th.value; break;
-                        default: fire = fabs(v - th.value) < 1e-3; break;
+                        case 4: fire = fabs(v - th.value) < 1e-3; break;
+                        case 5: fire = fabs(v - th.value) >= 1e-3; break;
+                        default: fire = false; break;
                     }
                     if (fire) last_fired[(int64_t)t * n + p] = now;
                 }
@@ -190,6 +211,25 @@ __global__ void nps_log_row_kernel(const double* __restrict__ slab, const int32_
         const int lf = f0 + j;
         if (lf < n_logged && p0 + tx < n) ring_row[(int64_t)lf * n + p0 + tx] = tile[j][tx];
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// maintenance effects: one thread per affected plant applies that plant's requests in order.  Sparse by nature
+// (work orders fire for a handful of plants per check), so the whole record is loaded and stored.
+// ------------------------------------------------------------------------------------------------
+struct MaintRequest { int32_t plant, target, action, arg; };
+__global__ void nps_maintenance_kernel(double* __restrict__ slab, const __grid_constant__ PlantParams prm,
+                                       const MaintRequest* __restrict__ req, const int32_t* __restrict__ group_start,
+                                       int n_groups, int32_t* __restrict__ status, int64_t n) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    const int lo = group_start[g], hi = group_start[g + 1];
+    const int64_t p = req[lo].plant;
+    PlantState st;
+    double* sv = reinterpret_cast<double*>(&st);
+    for (int f = 0; f < kNState; ++f) sv[f] = slab[(int64_t)f * n + p];
+    for (int i = lo; i < hi; ++i) status[i] = maintenance_apply(st, prm, req[i].target, req[i].action, req[i].arg);
+    for (int f = 0; f < kNState; ++f) slab[(int64_t)f * n + p] = sv[f];
 }
 
 __global__ void nps_gather_kernel(const double* __restrict__ slab, const int32_t* __restrict__ fields, int n_fields,
@@ -357,6 +397,63 @@ int nps_log_row(nps_handle* h, const double* d_state, double* d_ring, int64_t ri
     dim3 grid((unsigned)((h->n + kLogTilePlants - 1) / kLogTilePlants), (unsigned)((h->n_logged + kLogTileFields - 1) / kLogTileFields));
     nps_log_row_kernel<<<grid, kLogTilePlants, 0, (cudaStream_t)cuda_stream>>>(d_state, h->d_logged, h->n_logged, row, h->n);
     NPS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static const char* const kMaintActionNames[MA_N_ACTIONS] = {
+    "oil_change", "oil_top_off", "bearing_replacement", "seal_replacement", "component_overhaul", "system_cleaning",
+    "bearing_inspection", "impeller_inspection", "impeller_replacement", "lubrication_system_check", "motor_inspection",
+    "oil_analysis", "vibration_analysis", "tsp_chemical_cleaning", "tsp_mechanical_cleaning", "tube_bundle_inspection",
+    "moisture_separator_maintenance", "scale_removal", "eddy_current_testing", "secondary_side_cleaning",
+    "routine_maintenance", "tube_interior_scale_cleaning", "primary_scale_cleaning", "cleaning", "blade_replacement",
+    "overhaul", "condenser_tube_cleaning", "condenser_tube_plugging", "condenser_chemical_cleaning", "vacuum_system_test",
+    "vacuum_leak_detection", "other"};
+
+int nps_n_maintenance_actions(void) { return MA_N_ACTIONS; }
+const char* nps_maintenance_action_name(int action) {
+    return (action >= 0 && action < MA_N_ACTIONS) ? kMaintActionNames[action] : nullptr;
+}
+
+int nps_apply_maintenance(nps_handle* h, double* d_state, const int32_t* h_plant, const int32_t* h_target,
+                          const int32_t* h_action, const int32_t* h_arg, int n_requests, int32_t* h_status,
+                          void* cuda_stream) {
+    if (!h || !d_state || n_requests < 0) return fail("nps_apply_maintenance: bad arguments");
+    if (n_requests == 0) return 0;
+    if (!h_plant || !h_target || !h_action || !h_status) return fail("nps_apply_maintenance: null request arrays");
+    NPS_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    // group requests by plant, keeping the caller's order inside each plant (stable)
+    std::vector<int> order(n_requests);
+    for (int i = 0; i < n_requests; ++i) {
+        if (h_plant[i] < 0 || h_plant[i] >= h->n) return fail("nps_apply_maintenance: plant index out of range");
+        if (h_target[i] < 0 || h_target[i] >= MT_N_TARGETS) return fail("nps_apply_maintenance: target out of range");
+        if (h_action[i] < 0 || h_action[i] >= MA_N_ACTIONS) return fail("nps_apply_maintenance: action out of range");
+        order[i] = i;
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return h_plant[a] < h_plant[b]; });
+    std::vector<MaintRequest> req(n_requests);
+    std::vector<int32_t> start;
+    for (int j = 0; j < n_requests; ++j) {
+        const int i = order[j];
+        req[j] = MaintRequest{h_plant[i], h_target[i], h_action[i], h_arg ? h_arg[i] : 0};
+        if (j == 0 || req[j].plant != req[j - 1].plant) start.push_back(j);
+    }
+    const int n_groups = (int)start.size();
+    start.push_back(n_requests);
+    MaintRequest* d_req = nullptr; int32_t* d_start = nullptr; int32_t* d_status = nullptr;
+    NPS_CUDA(cudaMalloc(&d_req, sizeof(MaintRequest) * n_requests));
+    NPS_CUDA(cudaMalloc(&d_start, sizeof(int32_t) * start.size()));
+    NPS_CUDA(cudaMalloc(&d_status, sizeof(int32_t) * n_requests));
+    NPS_CUDA(cudaMemcpyAsync(d_req, req.data(), sizeof(MaintRequest) * n_requests, cudaMemcpyHostToDevice, s));
+    NPS_CUDA(cudaMemcpyAsync(d_start, start.data(), sizeof(int32_t) * start.size(), cudaMemcpyHostToDevice, s));
+    const int block = 32;
+    nps_maintenance_kernel<<<(n_groups + block - 1) / block, block, 0, s>>>(d_state, h->params, d_req, d_start, n_groups, d_status, h->n);
+    NPS_CUDA(cudaGetLastError());
+    std::vector<int32_t> st(n_requests);
+    NPS_CUDA(cudaMemcpyAsync(st.data(), d_status, sizeof(int32_t) * n_requests, cudaMemcpyDeviceToHost, s));
+    NPS_CUDA(cudaStreamSynchronize(s));
+    for (int j = 0; j < n_requests; ++j) h_status[order[j]] = st[j];
+    cudaFree(d_req); cudaFree(d_start); cudaFree(d_status);
     return 0;
 }
 

@@ -1,0 +1,327 @@
+// Maintenance action effects: the state mutations of component.perform_maintenance(maintenance_type=...)
+// as executed by AutoMaintenanceSystem._execute_work_order
+// (reference: nuclear_simulator/systems/maintenance/auto_maintenance.py:504-673), applied to ONE plant.
+//
+// Which Python method runs is decided by the class of the registered component:
+//   FWP-n  FeedwaterPump.perform_maintenance -> FeedwaterPumpLubricationSystem.perform_maintenance
+//          (feedwater/pump_system.py:750-766 -> feedwater/pump_lubrication.py:625-1410)
+//   SG-n   SteamGenerator.perform_maintenance                    (steam_generator/steam_generator.py:1092-1326)
+//   HP-n / LP-n  TurbineStage.perform_maintenance                (turbine/stage_system.py:341-377)
+//   SECONDARY-COMP-001-TURB  EnhancedTurbinePhysics.perform_maintenance  (turbine/enhanced_physics.py:1055-1267)
+//   SECONDARY-COMP-001-COND  EnhancedCondenserPhysics.perform_maintenance (condenser/physics.py:1188-1372)
+// The return value mirrors MaintenanceResult.success (decides whether StateManager.record_maintenance_result
+// clears violations and resets cooldowns); report strings / cost / duration fields are host-side bookkeeping.
+#pragma once
+#include "hd.h"
+#include "state.h"
+#include "feedwater.h"
+#include "sg.h"
+#include "turbine.h"
+#include "condenser.h"
+
+namespace nps {
+
+// Component targets, in the order the reference's threshold table lists them (state_manager.maintenance_thresholds).
+enum MaintTarget : int {
+    MT_PUMP0 = 0,          // FWP-1 .. FWP-4
+    MT_FW_SYSTEM = 4,      // FEE-001 (FeedwaterPumpSystem)
+    MT_SG0 = 5,            // SG-0 .. SG-2
+    MT_SG_SYSTEM = 8,      // SECONDARY-COMP-001-SG
+    MT_STAGE0 = 9,         // HP-1 .. HP-8, LP-1 .. LP-6
+    MT_TURBINE = 23,       // SECONDARY-COMP-001-TURB
+    MT_CONDENSER = 24,     // SECONDARY-COMP-001-COND
+    MT_N_TARGETS = 25
+};
+
+// Action codes (names in nuclear_sim_b200/maintenance.py ACTION_CODES, same order).
+enum MaintAction : int {
+    MA_OIL_CHANGE = 0, MA_OIL_TOP_OFF, MA_BEARING_REPLACEMENT, MA_SEAL_REPLACEMENT, MA_COMPONENT_OVERHAUL,
+    MA_SYSTEM_CLEANING, MA_BEARING_INSPECTION, MA_IMPELLER_INSPECTION, MA_IMPELLER_REPLACEMENT,
+    MA_LUBRICATION_SYSTEM_CHECK, MA_MOTOR_INSPECTION, MA_OIL_ANALYSIS, MA_VIBRATION_ANALYSIS,
+    MA_TSP_CHEMICAL_CLEANING, MA_TSP_MECHANICAL_CLEANING, MA_TUBE_BUNDLE_INSPECTION, MA_MOISTURE_SEPARATOR_MAINTENANCE,
+    MA_SCALE_REMOVAL, MA_EDDY_CURRENT_TESTING, MA_SECONDARY_SIDE_CLEANING, MA_ROUTINE_MAINTENANCE,
+    MA_TUBE_INTERIOR_SCALE_CLEANING, MA_PRIMARY_SCALE_CLEANING,
+    MA_STAGE_CLEANING, MA_BLADE_REPLACEMENT, MA_STAGE_OVERHAUL,
+    MA_CONDENSER_TUBE_CLEANING, MA_CONDENSER_TUBE_PLUGGING, MA_CONDENSER_CHEMICAL_CLEANING, MA_VACUUM_SYSTEM_TEST,
+    MA_VACUUM_LEAK_DETECTION,
+    MA_OTHER,              // any action name without a handler on the target: no state change
+    MA_N_ACTIONS
+};
+
+// result codes written back per request
+enum MaintStatus : int { MS_FAILED = 0, MS_SUCCESS = 1, MS_UNSUPPORTED_TARGET = 2 };
+
+// FeedwaterPumpLubricationSystem._calculate_lubrication_effectiveness: feedwater/pump_lubrication.py:240-269
+// (limits: contamination 15.0, acidity 1.6, moisture 0.08 - the same literals fwp_update_lubrication uses)
+NPS_HD void fwp_weighted_lubrication_effectiveness(LubCore& L) {
+    double contamination_factor = py_max(0.1, 1.0 - L.oil_contamination_level / 15.0);
+    double acidity_factor = py_max(0.1, 1.0 - L.oil_acidity_number / 1.6);
+    double moisture_factor = py_max(0.1, 1.0 - L.oil_moisture_content / 0.08);
+    double antioxidant_factor = py_max(0.1, L.antioxidant_level / 100.0);
+    double aw_factor = py_max(0.1, L.anti_wear_additive_level / 100.0);
+    double ci_factor = py_max(0.1, L.corrosion_inhibitor_level / 100.0);
+    L.lubrication_effectiveness = (contamination_factor * 0.25 + antioxidant_factor * 0.20 + aw_factor * 0.20 +
+                                   ci_factor * 0.15 + acidity_factor * 0.10 + moisture_factor * 0.10);
+    L.lubrication_effectiveness = py_max(0.1, py_min(1.0, L.lubrication_effectiveness));
+}
+
+// feedwater/pump_lubrication.py:677-1410.  bearing: 0 all, 1 motor_bearings, 2 pump_bearings, 3 thrust_bearing
+NPS_HD int maintain_pump(FWPumpState& u, int action, int bearing) {
+    LubCore& L = u.lub;
+    double* w = L.component_wear;
+    switch (action) {
+        case MA_OIL_CHANGE:   // :677-709
+            L.oil_level = 100.0; L.oil_temperature = 40.0; L.oil_contamination_level = 5.0;
+            L.oil_acidity_number = 0.5; L.oil_moisture_content = 0.02;
+            fwp_weighted_lubrication_effectiveness(L);
+            fwp_performance_factors(u, 0.0);
+            u.seal_leakage_rate = py_max(0.0, u.seal_leakage_rate * 0.5);
+            return MS_SUCCESS;
+        case MA_OIL_TOP_OFF: {   // :711-753 (target_level = 95.0)
+            double oil_added = py_max(0.0, 95.0 - L.oil_level);
+            if (oil_added > 0) {
+                L.oil_level = py_min(100.0, 95.0);
+                double dilution = oil_added / 100.0;
+                L.oil_contamination_level *= (1.0 - dilution * 0.5);
+                L.oil_acidity_number *= (1.0 - dilution * 0.3);
+                L.oil_moisture_content *= (1.0 - dilution * 0.4);
+                fwp_weighted_lubrication_effectiveness(L);
+                fwp_performance_factors(u, 0.0);
+            }
+            return MS_SUCCESS;
+        }
+        case MA_BEARING_REPLACEMENT: {   // :755-810
+            double removed;
+            if (bearing == 0) {
+                removed = w[FWL_MOTOR_BRG] + w[FWL_PUMP_BRG] + w[FWL_THRUST_BRG];
+                w[FWL_MOTOR_BRG] = 0.0; w[FWL_PUMP_BRG] = 0.0; w[FWL_THRUST_BRG] = 0.0;
+            } else if (bearing >= 1 && bearing <= 3) {
+                int c = (bearing == 1) ? FWL_MOTOR_BRG : ((bearing == 2) ? FWL_PUMP_BRG : FWL_THRUST_BRG);
+                removed = w[c];
+                w[c] = 0.0;
+            } else {
+                return MS_FAILED;
+            }
+            fwp_weighted_lubrication_effectiveness(L);
+            fwp_performance_factors(u, 0.0);
+            u.vibration_increase = py_max(0.0, u.vibration_increase - removed * 0.1);
+            return MS_SUCCESS;
+        }
+        case MA_SEAL_REPLACEMENT:   // :812-840
+            w[FWL_SEALS] = 0.0;
+            u.seal_leakage_rate = 0.0;
+            fwp_weighted_lubrication_effectiveness(L);
+            fwp_performance_factors(u, 0.0);
+            return MS_SUCCESS;
+        case MA_COMPONENT_OVERHAUL:   // :842-888
+            for (int c = 0; c < FWL_NCOMP; ++c) w[c] = 0.0;
+            L.oil_level = 100.0; L.oil_temperature = 40.0; L.oil_contamination_level = 5.0;
+            L.oil_acidity_number = 0.5; L.oil_moisture_content = 0.02;
+            u.seal_leakage_rate = 0.0;
+            u.vibration_increase = 0.0;
+            fwp_weighted_lubrication_effectiveness(L);
+            fwp_performance_factors(u, 0.0);
+            return MS_SUCCESS;
+        case MA_SYSTEM_CLEANING: {   // :890-925
+            double old_c = L.oil_contamination_level;
+            double red = py_min(old_c * 0.7, 50.0);
+            L.oil_contamination_level = py_max(5.0, old_c - red);
+            L.oil_acidity_number *= 0.8;
+            L.oil_moisture_content *= 0.9;
+            for (int c = 0; c < FWL_NCOMP; ++c) w[c] = py_max(0.0, w[c] - 0.5);
+            fwp_weighted_lubrication_effectiveness(L);
+            fwp_performance_factors(u, 0.0);
+            return MS_SUCCESS;
+        }
+        case MA_BEARING_INSPECTION: {   // :927-975
+            double mx = py_max3(w[FWL_MOTOR_BRG], w[FWL_PUMP_BRG], w[FWL_THRUST_BRG]);
+            if (mx > 5.0) {
+                w[FWL_MOTOR_BRG] *= 0.9; w[FWL_PUMP_BRG] *= 0.9; w[FWL_THRUST_BRG] *= 0.9;
+                fwp_performance_factors(u, 0.0);
+            }
+            return MS_SUCCESS;
+        }
+        case MA_IMPELLER_INSPECTION: {   // :977-1063
+            double iw = w[FWL_IMPELLER];
+            double mb = w[FWL_MOTOR_BRG], pb = w[FWL_PUMP_BRG], tb = w[FWL_THRUST_BRG];
+            double mx = py_max3(mb, pb, tb);
+            if (iw > 3.0 || mx > 5.0) {
+                w[FWL_IMPELLER] = py_max(0.0, iw * 0.9);
+                w[FWL_MOTOR_BRG] = py_max(0.0, mb - 0.5);
+                w[FWL_PUMP_BRG] = py_max(0.0, pb - 0.5);
+                w[FWL_THRUST_BRG] = py_max(0.0, tb - 0.5);
+                fwp_performance_factors(u, 0.0);
+            }
+            return MS_SUCCESS;
+        }
+        case MA_IMPELLER_REPLACEMENT: {   // :1065-1118
+            double old = w[FWL_IMPELLER];
+            w[FWL_IMPELLER] = 0.0;
+            fwp_performance_factors(u, 0.0);
+            u.vibration_increase = py_max(0.0, u.vibration_increase - old * 0.08);
+            return MS_SUCCESS;
+        }
+        case MA_LUBRICATION_SYSTEM_CHECK: {   // :1120-1270
+            if (L.oil_level < 95.0) {
+                double target = py_min(95.0, L.oil_level + 5.0);
+                double added = target - L.oil_level;
+                L.oil_level = target;
+                if (added > 0) {
+                    double dilution = added / 100.0;
+                    double cd = dilution * 0.5;
+                    L.oil_contamination_level = py_max(1.0, L.oil_contamination_level * (1.0 - cd));
+                    double boost = dilution * 15.0;
+                    L.antioxidant_level = py_min(100.0, L.antioxidant_level + boost);
+                    L.anti_wear_additive_level = py_min(100.0, L.anti_wear_additive_level + boost * 0.8);
+                }
+            }
+            double red = py_min(L.oil_contamination_level * 0.3, 5.0);
+            L.oil_contamination_level = py_max(1.0, L.oil_contamination_level - red);
+            const double restore = 15.0;
+            L.antioxidant_level = py_min(100.0, L.antioxidant_level + restore);
+            L.anti_wear_additive_level = py_min(100.0, L.anti_wear_additive_level + restore * 0.8);
+            L.corrosion_inhibitor_level = py_min(100.0, L.corrosion_inhibitor_level + restore * 0.6);
+            w[FWL_MOTOR_BRG] = py_max(0.0, w[FWL_MOTOR_BRG] - 0.5);
+            w[FWL_PUMP_BRG] = py_max(0.0, w[FWL_PUMP_BRG] - 0.5);
+            w[FWL_THRUST_BRG] = py_max(0.0, w[FWL_THRUST_BRG] - 0.5);
+            u.seal_leakage_rate = py_max(0.0, u.seal_leakage_rate * 0.9);
+            fwp_weighted_lubrication_effectiveness(L);
+            return MS_SUCCESS;
+        }
+        case MA_MOTOR_INSPECTION:   // :1272-1310
+            if (w[FWL_MOTOR_BRG] > 3.0) {
+                w[FWL_MOTOR_BRG] *= 0.95;
+                fwp_performance_factors(u, 0.0);
+            }
+            return MS_SUCCESS;
+        case MA_OIL_ANALYSIS:         // :1312-1358 (assessment only)
+        case MA_VIBRATION_ANALYSIS:   // :1360-1410 (assessment only)
+            return MS_SUCCESS;
+        default:                      // "Unknown maintenance type": :667-675
+            return MS_FAILED;
+    }
+}
+
+// TSPFoulingModel.perform_cleaning: steam_generator/tsp_fouling_model.py:447-487
+// (chemical_cleaning_effectiveness 0.75, mechanical 0.85: tsp_fouling_model.py:109-110)
+NPS_HD void tsp_perform_cleaning(SGState& g, double effectiveness) {
+    for (int level = 0; level < 7; ++level) {
+        g.tsp_thickness[level][0] *= (1.0 - effectiveness);
+        g.tsp_thickness[level][1] *= (1.0 - effectiveness * 0.8);
+        g.tsp_thickness[level][2] *= (1.0 - effectiveness * 0.9);
+        g.tsp_thickness[level][3] *= (1.0 - effectiveness);
+    }
+    g.tsp_total_cleaning_cycles += 1.0;
+    g.tsp_last_cleaning_time = 0.0;
+    tsp_recompute_restriction(g);
+}
+
+// steam_generator/steam_generator.py:1092-1326
+NPS_HD int maintain_sg(SGState& g, int action) {
+    switch (action) {
+        case MA_TSP_CHEMICAL_CLEANING: tsp_perform_cleaning(g, 0.75); return MS_SUCCESS;     // :1105-1122
+        case MA_TSP_MECHANICAL_CLEANING: tsp_perform_cleaning(g, 0.85); return MS_SUCCESS;   // :1124-1140
+        case MA_TUBE_BUNDLE_INSPECTION: return MS_SUCCESS;                                   // :1142-1166
+        case MA_MOISTURE_SEPARATOR_MAINTENANCE: {                                            // :1168-1185
+            double q = g.steam_quality;
+            double improvement = 0.999 - q;
+            g.steam_quality = py_min(0.999, q + improvement * 0.8);
+            return MS_SUCCESS;
+        }
+        case MA_SCALE_REMOVAL:                   // :1187-1201 -> TubeInteriorFouling._primary_scale_cleaning
+        case MA_TUBE_INTERIOR_SCALE_CLEANING:    // :1278-1281
+        case MA_PRIMARY_SCALE_CLEANING: {        // :1293-1296; tube_interior_fouling.py:361-420 (chemical: 0.90)
+            const double eff = 0.90;
+            double removed = g.tif_scale_thickness * eff;
+            g.tif_scale_thickness -= removed;
+            g.tif_scale_thickness = py_max(0.0, g.tif_scale_thickness);
+            for (int c = 0; c < 3; ++c) g.tif_comp[c] *= (1.0 - eff);
+            g.tif_scale_thermal_resistance = tif_thermal_resistance(g);
+            g.tif_fouling_fraction = py_min(g.tif_scale_thermal_resistance / 0.001, 1.0);
+            g.tif_last_cleaning_time = 0.0;   // FoulingModelBase._update_maintenance_history: fouling_model_base.py:210-214
+            return MS_SUCCESS;
+        }
+        // :1218-1241 reads tsp_state['operating_years'], a key TSPFoulingModel.get_state_dict does not provide: the
+        // KeyError is caught by _perform_maintenance_action (auto_maintenance.py:656-665) -> success False, no change
+        case MA_EDDY_CURRENT_TESTING: return MS_FAILED;
+        case MA_SECONDARY_SIDE_CLEANING: g.tsp_fouling_fraction *= (1.0 - 0.3); return MS_SUCCESS;   // :1243-1261
+        case MA_ROUTINE_MAINTENANCE: g.steam_quality = py_min(0.999, g.steam_quality + 0.001); return MS_SUCCESS;   // :1303-1315
+        default: return MS_FAILED;               // :1317-1324
+    }
+}
+
+// TurbineStage.perform_maintenance: turbine/stage_system.py:341-377 (always returns a dict -> success)
+NPS_HD int maintain_stage(TurbineStageState& s, const PlantParams& p, int k, int action) {
+    if (action == MA_STAGE_CLEANING) {
+        s.deposit_thickness = 0.0; s.fouling_factor = 1.0; s.efficiency_degradation *= 0.3;
+    } else if (action == MA_BLADE_REPLACEMENT) {
+        s.blade_wear_factor = 1.0; s.blade_condition_factor = s.fouling_factor;
+    } else if (action == MA_STAGE_OVERHAUL) {
+        s.deposit_thickness = 0.0; s.fouling_factor = 1.0; s.blade_wear_factor = 1.0; s.blade_condition_factor = 1.0;
+        s.efficiency_degradation = 0.0; s.actual_efficiency = p.ts_design_efficiency[k];
+    }
+    return MS_SUCCESS;
+}
+
+// AdvancedFoulingModel.perform_cleaning("chemical"): condenser/physics.py:386-450
+NPS_HD void cond_perform_chemical_cleaning(CondenserState& C) {
+    double bio_removed = C.fl_biofouling_thickness * 0.8;
+    double scale_removed = C.fl_scale_thickness * 0.6;
+    double corrosion_removed = C.fl_corrosion_product_thickness * 0.3;
+    C.fl_biofouling_thickness -= bio_removed;
+    C.fl_scale_thickness -= scale_removed;
+    C.fl_corrosion_product_thickness -= corrosion_removed;
+    C.fl_time_since_cleaning = 0.0;
+    C.fl_distribution_factor = 1.0;
+    double tr = (C.fl_biofouling_thickness / 1000.0) / 0.5 + (C.fl_scale_thickness / 1000.0) / 2.0 +
+                (C.fl_corrosion_product_thickness / 1000.0) / 1.0;
+    tr *= C.fl_distribution_factor;
+    C.fl_total_fouling_resistance = tr;
+}
+
+// EnhancedCondenserPhysics.perform_maintenance: condenser/physics.py:1188-1372
+NPS_HD int maintain_condenser(CondenserState& C, const PlantParams& p, int action) {
+    switch (action) {
+        case MA_CONDENSER_TUBE_CLEANING: {   // :1204-1232
+            double old_f = C.fl_total_fouling_resistance;
+            cond_perform_chemical_cleaning(C);
+            double reduction = old_f - C.fl_total_fouling_resistance;
+            double improvement = (reduction / py_max(0.001, old_f)) * 100;
+            C.thermal_performance_factor = py_min(1.0, C.thermal_performance_factor + improvement * 0.01);
+            return MS_SUCCESS;
+        }
+        case MA_CONDENSER_TUBE_PLUGGING: {   // :1234-1263 (tubes_to_plug = 10)
+            const double tubes = 10.0;
+            double old_active = C.td_active_tube_count;
+            C.td_plugged_tube_count += tubes;
+            C.td_active_tube_count = py_max(1000.0, old_active - tubes);
+            // :1244-1246 divides by self.config.tube_count, an attribute CondenserConfig does not have (it is
+            // heat_transfer.tube_count, condenser/config.py:43): AttributeError after the two counts were updated,
+            // caught by _perform_maintenance_action -> success False, area factor and leak rate untouched.
+            (void)p;
+            return MS_FAILED;
+        }
+        case MA_CONDENSER_CHEMICAL_CLEANING:   // :1265-1289
+            cond_perform_chemical_cleaning(C);
+            C.thermal_performance_factor = py_min(1.0, C.thermal_performance_factor + 0.1);
+            return MS_SUCCESS;
+        case MA_VACUUM_SYSTEM_TEST: return MS_SUCCESS;   // :1319-1343 (assessment only)
+        case MA_VACUUM_LEAK_DETECTION:                   // :1345-1362
+            C.vs_current_air_leakage *= 0.5;
+            return MS_SUCCESS;
+        default: return MS_FAILED;                       // :1364-1371
+    }
+}
+
+// One request: (target, action, arg).  Targets without a perform_maintenance restatement report
+// MS_UNSUPPORTED_TARGET so the host can refuse instead of silently diverging.
+NPS_HD int maintenance_apply(PlantState& st, const PlantParams& p, int target, int action, int arg) {
+    if (target >= MT_PUMP0 && target < MT_PUMP0 + 4) return maintain_pump(st.fw.pump[target - MT_PUMP0], action, arg);
+    if (target >= MT_SG0 && target < MT_SG0 + 3) return maintain_sg(st.sgs.sg[target - MT_SG0], action);
+    if (target >= MT_STAGE0 && target < MT_STAGE0 + 14) return maintain_stage(st.turb.stage[target - MT_STAGE0], p, target - MT_STAGE0, action);
+    if (target == MT_CONDENSER) return maintain_condenser(st.cond, p, action);
+    if (target == MT_TURBINE && action == MA_OTHER) return MS_FAILED;   // enhanced_physics.py:1259-1266 (unknown type)
+    return MS_UNSUPPORTED_TARGET;
+}
+
+}  // namespace nps

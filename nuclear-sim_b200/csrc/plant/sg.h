@@ -49,6 +49,43 @@ NPS_HD double tsp_average_thickness(const SGState& g) {
     return t / 7;
 }
 
+// calculate_flow_restriction / calculate_heat_transfer_degradation / calculate_flow_maldistribution /
+// determine_fouling_stage: tsp_fouling_model.py:302-411.  Shared by the per-step update and by perform_cleaning.
+NPS_HD void tsp_recompute_restriction(SGState& g) {
+    double restr[7];
+    double total_restriction = 0.0;
+    const double hole_mm = 0.023 * 1000.0;
+    for (int level = 0; level < 7; ++level) {
+        double tt = tsp_total_thickness(g, level);
+        double eff_d = hole_mm - 2.0 * tt;
+        eff_d = py_max(eff_d, hole_mm * 0.1);
+        double orig_area = NPS_PI * py_pow(hole_mm / 2.0, 2.0);
+        double eff_area = NPS_PI * py_pow(eff_d / 2.0, 2.0);
+        double r = 1.0 - eff_area / orig_area;
+        restr[level] = r;
+        total_restriction += r;
+    }
+    g.tsp_fouling_fraction = total_restriction / 7;
+    double avg_area_ratio = py_max(1.0 - g.tsp_fouling_fraction, 0.1);
+    g.tsp_pressure_drop_ratio = py_pow(1.0 / avg_area_ratio, 2.0);
+    {   // calculate_heat_transfer_degradation
+        double mixing = py_pow(g.tsp_fouling_fraction, 1.5);
+        double mald = g.tsp_fouling_fraction * 0.3;
+        g.tsp_heat_transfer_degradation = py_min((mixing + mald) * 0.6, 0.9);
+    }
+    {   // calculate_flow_maldistribution: np.mean / np.std over 7 values (sequential sums)
+        double s = 0.0;
+        for (int i = 0; i < 7; ++i) s += restr[i];
+        double mean = s / 7.0;
+        double v = 0.0;
+        for (int i = 0; i < 7; ++i) { double x = restr[i] - mean; v += x * x; }
+        double sd = sqrt(v / 7.0);
+        g.tsp_flow_maldistribution = py_min(sd / (mean + 0.01), 1.0);
+    }
+    double ff = g.tsp_fouling_fraction;
+    g.tsp_fouling_stage = (ff < 0.4) ? 0.0 : ((ff < 0.7) ? 1.0 : ((ff < 0.85) ? 2.0 : 3.0));
+}
+
 // TSPFoulingModel.update_fouling_state: tsp_fouling_model.py:654-724 (+ :195-445); the chemistry
 // comes from the SG system's own WaterChemistry (WAT-001), which the step path never updates.
 NPS_HD void tsp_update(SGState& g, const PlantParams& p, double temperature, double flow_velocity, double dt_hours) {
@@ -86,39 +123,8 @@ NPS_HD void tsp_update(SGState& g, const PlantParams& p, double temperature, dou
         g.tsp_thickness[level][2] = py_min(g.tsp_thickness[level][2], max_thickness * 0.3);
         g.tsp_thickness[level][3] = py_min(g.tsp_thickness[level][3], max_thickness * 0.1);
     }
-    // calculate_flow_restriction
-    double restr[7];
-    double total_restriction = 0.0;
-    const double hole_mm = 0.023 * 1000.0;
-    for (int level = 0; level < 7; ++level) {
-        double tt = tsp_total_thickness(g, level);
-        double eff_d = hole_mm - 2.0 * tt;
-        eff_d = py_max(eff_d, hole_mm * 0.1);
-        double orig_area = NPS_PI * py_pow(hole_mm / 2.0, 2.0);
-        double eff_area = NPS_PI * py_pow(eff_d / 2.0, 2.0);
-        double r = 1.0 - eff_area / orig_area;
-        restr[level] = r;
-        total_restriction += r;
-    }
-    g.tsp_fouling_fraction = total_restriction / 7;
-    double avg_area_ratio = py_max(1.0 - g.tsp_fouling_fraction, 0.1);
-    g.tsp_pressure_drop_ratio = py_pow(1.0 / avg_area_ratio, 2.0);
-    {   // calculate_heat_transfer_degradation
-        double mixing = py_pow(g.tsp_fouling_fraction, 1.5);
-        double mald = g.tsp_fouling_fraction * 0.3;
-        g.tsp_heat_transfer_degradation = py_min((mixing + mald) * 0.6, 0.9);
-    }
-    {   // calculate_flow_maldistribution: np.mean / np.std over 7 values (sequential sums)
-        double s = 0.0;
-        for (int i = 0; i < 7; ++i) s += restr[i];
-        double mean = s / 7.0;
-        double v = 0.0;
-        for (int i = 0; i < 7; ++i) { double x = restr[i] - mean; v += x * x; }
-        double sd = sqrt(v / 7.0);
-        g.tsp_flow_maldistribution = py_min(sd / (mean + 0.01), 1.0);
-    }
+    tsp_recompute_restriction(g);
     double ff = g.tsp_fouling_fraction;
-    g.tsp_fouling_stage = (ff < 0.4) ? 0.0 : ((ff < 0.7) ? 1.0 : ((ff < 0.85) ? 2.0 : 3.0));
     int reasons = 0;
     if (ff >= 0.85) reasons |= 1;
     if (g.tsp_heat_transfer_degradation >= (1.0 - 0.60)) reasons |= 2;

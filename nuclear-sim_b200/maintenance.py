@@ -1,0 +1,485 @@
+"""Host side of threshold monitoring, work-order issuance and maintenance execution for the batched engine.
+
+The reference does this per plant in Python objects:
+  * StateManager._check_maintenance_thresholds / _find_parameter_in_row_data / _emit_batched_threshold_violation
+    (simulator/state/state_manager.py:1307-1410, 1574-1625)            -> flag kernel + ``ThresholdTable`` (binding)
+  * MaintenanceOrchestrator._make_maintenance_decision
+    (systems/maintenance/maintenance_orchestrator.py:192-380, 469-624)  -> ``orchestrate``
+  * AutoMaintenanceSystem.update / _handle_state_manager_threshold / _create_automatic_work_order /
+    _execute_scheduled_work_orders / _execute_work_order
+    (systems/maintenance/auto_maintenance.py:200-580)                   -> ``BatchedAutoMaintenance``
+  * StateManager.record_maintenance_result / _reset_threshold_cooldowns_for_maintenance
+    (simulator/state/state_manager.py:1639-1830)                        -> cooldown stamps reset on the device
+  * component.perform_maintenance(...)                                  -> nps_apply_maintenance (csrc/plant/maintenance.h)
+
+Events are sparse (a few plants per check), so the bookkeeping is plain Python dicts keyed by plant; everything that
+touches all plants every step (threshold compare, cooldown stamps, effects) stays on the device.
+"""
+from __future__ import annotations
+
+import json
+import os
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from ._layout import field_index
+
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+
+# ---------------------------------------------------------------------------------------------------------------
+# component table of the PWR3000 plant: ids, classes and equipment types as registered by the reference
+# (data/pwr3000_components.json is written by oracle/make_column_map.py from a live plant; order = the order
+# StateManager.maintenance_thresholds lists them, which is the order events are emitted in)
+# ---------------------------------------------------------------------------------------------------------------
+ACTION_NAMES = (
+    "oil_change", "oil_top_off", "bearing_replacement", "seal_replacement", "component_overhaul", "system_cleaning",
+    "bearing_inspection", "impeller_inspection", "impeller_replacement", "lubrication_system_check", "motor_inspection",
+    "oil_analysis", "vibration_analysis", "tsp_chemical_cleaning", "tsp_mechanical_cleaning", "tube_bundle_inspection",
+    "moisture_separator_maintenance", "scale_removal", "eddy_current_testing", "secondary_side_cleaning",
+    "routine_maintenance", "tube_interior_scale_cleaning", "primary_scale_cleaning", "cleaning", "blade_replacement",
+    "overhaul", "condenser_tube_cleaning", "condenser_tube_plugging", "condenser_chemical_cleaning", "vacuum_system_test",
+    "vacuum_leak_detection", "other")
+ACTION_CODE = {n: i for i, n in enumerate(ACTION_NAMES)}
+BEARING_ARG = {None: 0, "": 0, "all": 0, "motor_bearings": 1, "pump_bearings": 2, "thrust_bearing": 3}
+
+
+def target_code(component_id: str) -> int:
+    """MaintTarget of csrc/plant/maintenance.h for a reference component id."""
+    if component_id.startswith("FWP-"):
+        return int(component_id[4:]) - 1
+    if component_id == "FEE-001":
+        return 4
+    if component_id.startswith("SG-"):
+        return 5 + int(component_id[3:])
+    if component_id == "SECONDARY-COMP-001-SG":
+        return 8
+    if component_id.startswith("HP-"):
+        return 9 + int(component_id[3:]) - 1
+    if component_id.startswith("LP-"):
+        return 9 + 8 + int(component_id[3:]) - 1
+    if component_id == "SECONDARY-COMP-001-TURB":
+        return 23
+    if component_id == "SECONDARY-COMP-001-COND":
+        return 24
+    raise KeyError(component_id)
+
+
+def action_code(action: str) -> int:
+    return ACTION_CODE.get(action, ACTION_CODE["other"])
+
+
+def load_components() -> List[dict]:
+    with open(os.path.join(_DATA, "pwr3000_components.json")) as fh:
+        return json.load(fh)["components"]
+
+
+def load_reference_columns() -> Dict[str, dict]:
+    with open(os.path.join(_DATA, "reference_columns.json")) as fh:
+        return json.load(fh)["columns"]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# threshold table
+# ---------------------------------------------------------------------------------------------------------------
+DERIVED_CODES = {"pump_sum_wear": 0}   # csrc: field = -(2 + 4 * code + unit) ... see ThresholdTable.device_rows
+
+
+@dataclass
+class ThresholdRow:
+    component_id: str
+    parameter: str
+    comparison: str
+    threshold: float
+    cooldown_hours: float
+    action: str
+    priority: str
+    sub_component: Optional[str]      # threshold_config['component_id'] (bearing selector)
+    column: Optional[str] = None      # reference column the checker resolves, None = inert (no column matches)
+    field: Optional[str] = None       # PlantState field carrying that column
+    derived: Optional[str] = None     # or a derived quantity
+    unit: Optional[str] = None        # PlantState prefix of the unit a derived quantity is evaluated on
+    note: str = ""
+
+
+def _subsystem_to_equipment(name: str) -> str:
+    # StateManager._create_maintenance_config_from_comprehensive: state_manager.py:1107-1112
+    return {"feedwater": "pump", "turbine": "turbine_stage", "steam_generator": "steam_generator",
+            "condenser": "condenser"}.get(name, name)
+
+
+def candidate_columns(component_id: str, parameter: str) -> List[str]:
+    """The seven names StateManager._find_parameter_in_row_data tries, in order (state_manager.py:1385-1402)."""
+    p = {"impeller_inspection_wear": "impeller_wear"}.get(parameter, parameter)
+    c = component_id
+    return [f"{c}.{p}", f"secondary.feedwater_{c}.{p}", f"secondary.feedwater.{p}", f"secondary.{c}.{p}",
+            f"secondary.steam_generator_{c}.{p}", f"secondary.turbine_{c}.{p}", f"secondary.condenser_{c}.{p}"]
+
+
+class ThresholdTable:
+    """Threshold rows of one plant design, bound to PlantState fields the way the reference binds them to columns."""
+
+    def __init__(self, maintenance_system_config: dict, components: Optional[List[dict]] = None,
+                 columns: Optional[Dict[str, dict]] = None):
+        components = components if components is not None else load_components()
+        columns = columns if columns is not None else load_reference_columns()
+        cfgs = {}
+        for subsystem, data in (maintenance_system_config.get("component_configs") or {}).items():
+            cfgs[_subsystem_to_equipment(subsystem)] = data.get("thresholds", {}) or {}
+        self.mode = maintenance_system_config.get("maintenance_mode", "realistic")
+        self.rows: List[ThresholdRow] = []
+        fields = field_index()
+        for comp in components:
+            cid = comp["id"]
+            # AutoMaintenanceSystem.setup_monitoring_from_state_manager filters: auto_maintenance.py:135-144
+            if cid.endswith("-LUB") or "lubrication" in cid.lower() or any(s in cid for s in ("-CTRL", "-PROT", "-DIAG", "-MON")):
+                continue
+            for pname, tc in cfgs.get(comp["equipment_type"], {}).items():
+                row = ThresholdRow(cid, pname, tc.get("comparison", "greater_than"), tc.get("threshold"),
+                                   float(tc.get("cooldown_hours", 24.0)), tc.get("action"), tc.get("priority", "MEDIUM"),
+                                   tc.get("component_id"))
+                # "turbine_TB-LUB" / lowercase-"t" skip: state_manager.py:1330 (sic)
+                if "turbine_TB-LUB" in cid or "t" in cid:
+                    row.note = "skipped by the checker (component id contains 't')"
+                elif row.threshold is None:
+                    row.note = "no threshold value"
+                else:
+                    for name in candidate_columns(cid, pname):
+                        if name in columns:
+                            col = columns[name]
+                            if not col.get("numeric", False):
+                                # isinstance(value, (int, float)) fails -> the loop moves on to the next pattern
+                                continue
+                            row.column = name
+                            if col.get("field") in fields:
+                                row.field = col["field"]
+                            elif col.get("derived"):
+                                row.derived, row.unit = col["derived"], col.get("unit")
+                            else:
+                                row.note = "column exists in the reference but is not carried in PlantState"
+                            break
+                    else:
+                        row.note = "inert: no logged column matches (same in the reference)"
+                self.rows.append(row)
+
+    def __len__(self):
+        return len(self.rows)
+
+    def bound(self) -> List[int]:
+        return [i for i, r in enumerate(self.rows) if r.field or r.derived]
+
+    def unsupported(self) -> List[ThresholdRow]:
+        return [r for r in self.rows if r.column and not (r.field or r.derived)]
+
+    def device_rows(self):
+        """(field index or derived code, comparator, value, cooldown_hours) per row; inert rows get field -1."""
+        fields = field_index()
+        out = []
+        for r in self.rows:
+            if r.field:
+                f = fields[r.field]
+            elif r.derived:
+                unit = int(r.unit.split("[")[1].split("]")[0])
+                f = -(2 + 4 * DERIVED_CODES[r.derived] + unit)
+            else:
+                f = -1
+            out.append((f, r.comparison, float(r.threshold) if r.threshold is not None else 0.0, r.cooldown_hours))
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# orchestrator decision (decision_only mode): maintenance_orchestrator.py:81-380
+# ---------------------------------------------------------------------------------------------------------------
+_HIERARCHY = {   # maintenance_orchestrator.py:469-624 (only the parts _make_maintenance_decision reads)
+    "feedwater_pump": {
+        "comprehensive": [
+            ("component_overhaul", ["bearing_replacement", "seal_replacement", "oil_change", "motor_inspection",
+                                    "impeller_replacement", "bearing_inspection", "oil_analysis", "vibration_analysis"],
+             {"multiple_major_actions": 2, "total_violations": 4, "bearing_wear_threshold": 15.0,
+              "system_health_factor_threshold": 0.75}),
+            ("comprehensive_system_inspection", ["bearing_inspection", "motor_inspection", "impeller_inspection",
+                                                 "vibration_analysis", "oil_analysis", "lubrication_inspection"],
+             {"multiple_major_actions": 3, "total_violations": 5})],
+        "coordinated": {"bearing_replacement": ["oil_change", "oil_analysis", "vibration_analysis"],
+                        "impeller_replacement": ["cavitation_analysis", "npsh_analysis", "bearing_inspection"],
+                        "seal_replacement": ["oil_analysis", "lubrication_inspection"],
+                        "motor_inspection": ["bearing_inspection", "vibration_analysis"]},
+        "promotion": {"oil_change": ("bearing_replacement", ["bearing_wear > 5.0", "motor_temperature > 80.0", "vibration_increase > 2.0"]),
+                      "bearing_inspection": ("bearing_replacement", ["bearing_wear > 10.0", "vibration_increase > 5.0"]),
+                      "oil_top_off": ("oil_change", ["oil_contamination_level > 12.0", "oil_acidity_number > 1.4"]),
+                      "lubrication_system_check": ("oil_change", ["oil_contamination_level > 12.0"]),
+                      "oil_analysis": ("oil_change", ["oil_contamination_level > 15.0", "oil_acidity_number > 1.4"])}},
+    "turbine_stage": {
+        "comprehensive": [("turbine_overhaul", ["blade_replacement", "bearing_replacement", "rotor_balancing",
+                                                "vibration_analysis", "turbine_oil_change"],
+                           {"multiple_major_actions": 2, "vibration_threshold": 10.0, "efficiency_degradation_threshold": 0.15})],
+        "coordinated": {"blade_replacement": ["rotor_balancing", "vibration_analysis", "performance_test"],
+                        "bearing_replacement": ["turbine_oil_change", "vibration_analysis"],
+                        "rotor_balancing": ["vibration_analysis", "critical_speed_test"]},
+        "promotion": {"turbine_oil_change": ("bearing_replacement", ["bearing_wear > 8.0", "vibration_increase > 3.0"])}},
+    "steam_generator": {
+        "comprehensive": [
+            ("tube_bundle_overhaul", ["tube_cleaning", "tube_inspection", "tsp_chemical_cleaning", "tsp_mechanical_cleaning",
+                                      "eddy_current_testing", "scale_removal", "tube_interior_inspection",
+                                      "tube_interior_scale_cleaning", "tube_interior_eddy_current_testing", "tsp_inspection"],
+             {"multiple_major_actions": 3, "fouling_threshold": 20.0, "tube_plugging_percentage_threshold": 5.0,
+              "heat_transfer_degradation_threshold": 0.25}),
+            ("comprehensive_steam_generator_inspection", ["tube_bundle_inspection", "tsp_inspection", "tube_interior_inspection",
+                                                          "tube_sheet_inspection", "moisture_separator_maintenance",
+                                                          "tsp_flow_test", "eddy_current_testing"],
+             {"multiple_major_actions": 4, "total_violations": 6})],
+        "coordinated": {"tsp_chemical_cleaning": ["tsp_inspection", "tsp_flow_test", "water_chemistry_adjustment"],
+                        "tsp_mechanical_cleaning": ["tsp_inspection", "tube_bundle_inspection"],
+                        "tube_interior_scale_cleaning": ["tube_interior_inspection", "primary_chemistry_optimization",
+                                                         "tube_interior_eddy_current_testing"],
+                        "tube_cleaning": ["tube_inspection", "water_chemistry_adjustment"],
+                        "scale_removal": ["water_chemistry_adjustment", "tube_inspection"],
+                        "eddy_current_testing": ["tube_bundle_inspection", "tube_interior_inspection"],
+                        "primary_chemistry_optimization": ["tube_interior_inspection", "water_chemistry_adjustment"]},
+        "promotion": {"tsp_inspection": ("tsp_chemical_cleaning", ["fouling_fraction > 0.15", "heat_transfer_degradation > 0.10"]),
+                      "tube_interior_inspection": ("tube_interior_scale_cleaning", ["scale_thickness > 1.0", "thermal_resistance > 0.0005"]),
+                      "tsp_flow_test": ("tsp_mechanical_cleaning", ["pressure_drop_ratio > 3.0", "flow_maldistribution > 0.25"]),
+                      "tube_cleaning": ("tube_bundle_overhaul", ["fouling_factor > 0.3", "heat_transfer_degradation > 0.2"]),
+                      "water_chemistry_adjustment": ("primary_chemistry_optimization", ["scale_formation_rate > 0.01", "chemistry_imbalance > 0.1"])}},
+    "condenser": {
+        "comprehensive": [("condenser_overhaul", ["condenser_tube_cleaning", "condenser_tube_inspection",
+                                                  "vacuum_system_check", "condenser_performance_test"],
+                           {"multiple_major_actions": 2, "vacuum_degradation_threshold": 5.0,
+                            "heat_transfer_degradation_threshold": 0.15})],
+        "coordinated": {"condenser_tube_cleaning": ["condenser_tube_inspection", "vacuum_system_check"],
+                        "vacuum_ejector_cleaning": ["vacuum_system_test", "condenser_performance_test"]},
+        "promotion": {}},
+}
+
+
+def infer_component_type(component_id: str) -> str:
+    """MaintenanceOrchestrator._infer_component_type_from_id: maintenance_orchestrator.py:173-186."""
+    c = component_id.lower()
+    if "fwp" in c or "feedwater" in c:
+        return "feedwater_pump"
+    if "tb" in c or "turbine" in c:
+        return "turbine_stage"
+    if "sg" in c or "steam_generator" in c:
+        return "steam_generator"
+    if "cd" in c or "condenser" in c:
+        return "condenser"
+    return "unknown"
+
+
+def orchestrate(component_id: str, violations: Sequence[dict], requested_action: Optional[str]) -> str:
+    """selected_action of _make_maintenance_decision (maintenance_orchestrator.py:188-255)."""
+    h = _HIERARCHY.get(infer_component_type(component_id), {})
+    v_actions = [v.get("action") for v in violations if v.get("action")]
+    if not requested_action:
+        if not v_actions:
+            return "routine_maintenance"
+        prio = {"component_overhaul": 10, "bearing_replacement": 9, "impeller_replacement": 8, "seal_replacement": 7,
+                "motor_inspection": 6, "oil_change": 5, "bearing_inspection": 4, "oil_analysis": 3,
+                "lubrication_system_check": 2, "oil_top_off": 2, "routine_maintenance": 1}
+        requested_action = max(v_actions, key=lambda a: prio.get(a, 0))
+    # _check_comprehensive_promotion / _meets_comprehensive_criteria: :257-279, 332-361
+    for name, encompasses, trig in h.get("comprehensive", []):
+        n_enc = sum(1 for a in v_actions if a in encompasses)
+        if "multiple_major_actions" in trig and n_enc >= trig["multiple_major_actions"]:
+            return name
+        if "total_violations" in trig and len(violations) >= trig["total_violations"]:
+            return name
+        for key, thr in trig.items():
+            if key.endswith("_threshold"):
+                pn = key.replace("_threshold", "")
+                for v in violations:
+                    if v.get("parameter") == pn and v.get("value", 0) > thr:
+                        return name
+    # _check_action_coordination: :281-303 (the base action itself is selected)
+    for base, coordinated in h.get("coordinated", {}).items():
+        if requested_action == base and any(a in v_actions for a in coordinated):
+            return base
+    # _check_action_promotion / _check_promotion_conditions: :305-330, 363-381
+    rule = h.get("promotion", {}).get(requested_action)
+    if rule:
+        promote_to, conditions = rule
+        for cond in conditions:
+            if ">" in cond:
+                pn, thr = cond.split(">")
+                pn, thr = pn.strip(), float(thr.strip())
+                for v in violations:
+                    if v.get("parameter") == pn and v.get("value", 0) > thr:
+                        return promote_to
+    return requested_action
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# work orders
+# ---------------------------------------------------------------------------------------------------------------
+_KNOWN_ACTIONS_CACHE: Optional[set] = None
+_PRIORITY_RANK = {"LOW": 1, "MEDIUM": 2, "HIGH": 3, "CRITICAL": 4, "EMERGENCY": 5}
+
+# which threshold parameters a performed action re-arms: state_manager.py:1797-1808
+_COOLDOWN_RESET = {
+    "scale_removal": ["tube_wall_temperature", "fouling_factor", "efficiency", "thermal_resistance"],
+    "oil_change": ["oil_level", "oil_contamination", "oil_temperature", "oil_acidity"],
+    "oil_top_off": ["oil_level"],
+    "bearing_replacement": ["bearing_wear", "bearing_temperature", "vibration_level"],
+    "bearing_inspection": ["bearing_wear", "bearing_temperature"],
+    "vibration_analysis": ["vibration_level"],
+    "chemical_cleaning": ["fouling_factor", "efficiency", "tube_wall_temperature"],
+    "tube_cleaning": ["fouling_factor", "tube_wall_temperature"],
+    "performance_optimization": ["efficiency"],
+}
+
+
+def known_action_names() -> set:
+    """Values of the reference's MaintenanceActionType enum (systems/maintenance/maintenance_actions.py:19-198); a work
+    order is only created for a known action (auto_maintenance.py:338-346).  data/maintenance_action_types.json is
+    written by oracle/make_column_map.py from the live enum."""
+    global _KNOWN_ACTIONS_CACHE
+    if _KNOWN_ACTIONS_CACHE is None:
+        with open(os.path.join(_DATA, "maintenance_action_types.json")) as fh:
+            _KNOWN_ACTIONS_CACHE = set(json.load(fh)["actions"])
+    return _KNOWN_ACTIONS_CACHE
+
+
+@dataclass
+class WorkOrder:
+    work_order_id: str
+    plant: int
+    component_id: str
+    action: str
+    priority: str
+    created: float            # minutes
+    planned_start: float      # minutes
+    sub_component: Optional[str] = None
+    status: str = "SCHEDULED"
+    executed_at: Optional[float] = None
+    success: Optional[bool] = None
+
+
+@dataclass
+class _PlantBook:
+    orders: List[WorkOrder] = field(default_factory=list)
+    recent_triggers: Dict[str, float] = field(default_factory=dict)
+    n_created: int = 0
+
+
+class BatchedAutoMaintenance:
+    """AutoMaintenanceSystem for N plants that share one clock (they are stepped in lockstep).
+
+    ``aggressive`` mirrors setup_monitoring_from_state_manager(aggressive_mode=True) as used by
+    MaintenanceScenarioRunner (maintenance_scenario_runner.py:296-299): every priority executes with zero delay.
+    """
+
+    def __init__(self, sim, table: ThresholdTable, aggressive: bool = True, head_quirks: bool = True):
+        """head_quirks=True reproduces the reference at HEAD: StateManager.record_maintenance_result raises
+        AttributeError (state_manager.py:1657 reads a non-existent ``self.current_time``) right after the component
+        was maintained; the exception aborts the rest of AutoMaintenanceSystem.update and is swallowed by
+        NuclearPlantSimulator.step (sim.py:210-216).  Net effect: at most ONE work order per plant executes per
+        15-minute update, no maintenance history is recorded, violations are not cleared and threshold cooldowns
+        are never reset.  head_quirks=False runs the code path the reference intends (all due orders execute,
+        cooldowns of the addressed parameters are reset)."""
+        self.sim = sim
+        self.table = table
+        self.head_quirks = head_quirks
+        self.check_interval_hours = 0.25
+        self.last_check_time = 0.0
+        self.work_order_cooldown_hours = 24.0
+        if aggressive:
+            self.delays = {"EMERGENCY": 0.0, "CRITICAL": 0.0, "HIGH": 0.0, "MEDIUM": 0.0, "LOW": 0.0}
+        else:   # auto_maintenance.py:452-466 (hours): CRITICAL = half the HIGH delay
+            self.delays = {"EMERGENCY": 0.0, "CRITICAL": 0.5, "HIGH": 1.0, "MEDIUM": 4.0, "LOW": 24.0}
+        self.books: Dict[int, _PlantBook] = {}
+        self.created_log: List[WorkOrder] = []
+        self.executed_log: List[WorkOrder] = []
+        self.event_log: List[dict] = []
+        self._rows_by_component: Dict[str, List[int]] = {}
+        for i, r in enumerate(table.rows):
+            self._rows_by_component.setdefault(r.component_id, []).append(i)
+        sim.set_thresholds(table.device_rows())
+
+    # -- AutoMaintenanceSystem.update: auto_maintenance.py:200-236 ------------------------------------------------
+    def update(self, t_minutes: float) -> List[WorkOrder]:
+        """Call after the physics step and BEFORE check(): executes the work orders that are due (sim.py:209-213)."""
+        if self.last_check_time > 0.0 and t_minutes - self.last_check_time < self.check_interval_hours * 60:
+            return []
+        self.last_check_time = t_minutes
+        due: List[WorkOrder] = []
+        for plant in sorted(self.books):
+            for wo in self.books[plant].orders:   # creation order (WorkOrderManager.work_orders dict order)
+                if wo.status == "SCHEDULED" and t_minutes >= wo.planned_start:
+                    due.append(wo)
+                    if self.head_quirks:
+                        break
+        if not due:
+            return []
+        status = self.sim.apply_maintenance([(wo.plant, target_code(wo.component_id), action_code(wo.action),
+                                              BEARING_ARG.get(wo.sub_component, 0) if wo.action == "bearing_replacement" else 0)
+                                             for wo in due])
+        for wo, st in zip(due, status):
+            if st == 2:
+                raise NotImplementedError(f"perform_maintenance on {wo.component_id} is not restated on the device")
+            wo.status, wo.executed_at, wo.success = "COMPLETED", t_minutes, bool(st == 1)
+            self.executed_log.append(wo)
+            if wo.success and not self.head_quirks:   # record_maintenance_result -> _reset_threshold_cooldowns_for_maintenance
+                addressed = _COOLDOWN_RESET.get(wo.action, [])
+                rows = [i for i in self._rows_by_component.get(wo.component_id, []) if self.table.rows[i].parameter in addressed]
+                if rows:
+                    self.sim.reset_cooldowns(wo.plant, rows)
+        return due
+
+    # -- StateManager._check_maintenance_thresholds + AutoMaintenanceSystem._handle_state_manager_threshold --------
+    def check(self, t_minutes: float) -> List[WorkOrder]:
+        """Flag kernel + host drain: emits the reference's batched events and creates work orders."""
+        self.sim.check_thresholds()
+        fired = self.sim.drain_events()
+        if not fired:
+            return []
+        by_plant: Dict[int, Dict[str, List[int]]] = {}
+        for plant, t in fired:
+            by_plant.setdefault(plant, {}).setdefault(self.table.rows[t].component_id, []).append(t)
+        values = self.sim.read_threshold_values(sorted(by_plant), self.table)
+        created = []
+        for plant in sorted(by_plant):
+            # component order = table order (dict order of maintenance_thresholds), parameters in config order
+            comps = sorted(by_plant[plant], key=lambda c: self._rows_by_component[c][0])
+            for cid in comps:
+                violations = []
+                for t in sorted(by_plant[plant][cid]):
+                    r = self.table.rows[t]
+                    violations.append({"parameter": r.parameter, "value": values[(plant, t)], "threshold": r.threshold,
+                                       "comparison": r.comparison, "action": r.action, "priority": r.priority,
+                                       "component_id": r.sub_component})
+                action = orchestrate(cid, violations, violations[0]["action"])
+                priority = max((v["priority"] for v in violations), key=lambda p: _PRIORITY_RANK.get(p, 2))
+                self.event_log.append({"t": t_minutes, "plant": plant, "component": cid, "action": action,
+                                       "violations": violations})
+                sub = None
+                for v in violations:   # auto_maintenance.py:259-267
+                    if v.get("action") == action and v.get("component_id"):
+                        sub = v["component_id"]
+                        break
+                wo = self._create_work_order(plant, cid, action, priority, t_minutes, sub)
+                if wo:
+                    created.append(wo)
+        return created
+
+    # -- _create_automatic_work_order: auto_maintenance.py:332-450 --------------------------------------------------
+    def _create_work_order(self, plant, cid, action, priority, t_minutes, sub) -> Optional[WorkOrder]:
+        if not action or action not in known_action_names():
+            return None
+        book = self.books.setdefault(plant, _PlantBook())
+        key = f"{cid}:{action}"
+        if key in book.recent_triggers:
+            # minutes compared against an hours constant (sic): auto_maintenance.py:351-358
+            if t_minutes - book.recent_triggers[key] < self.work_order_cooldown_hours:
+                return None
+        for wo in book.orders:
+            if wo.component_id == cid and wo.status in ("PLANNED", "SCHEDULED", "IN_PROGRESS") and wo.action == action:
+                return None
+        book.n_created += 1
+        prio = priority.upper() if priority.upper() in self.delays else "MEDIUM"
+        wo = WorkOrder(f"WO-{book.n_created:06d}", plant, cid, action, prio, t_minutes,
+                       t_minutes + self.delays[prio] * 60.0, sub)
+        book.orders.append(wo)
+        book.recent_triggers[key] = t_minutes
+        self.created_log.append(wo)
+        return wo

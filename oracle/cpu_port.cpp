@@ -65,6 +65,16 @@ int nps_oracle_observe(const double* state, const double* params, int64_t n_plan
 
 }  // extern "C"
 
+// maintenance effect on ONE plant (array-of-structs state): returns the MaintStatus code
+#include "maintenance.h"
+extern "C" int nps_oracle_apply_maintenance(double* state, const double* params, int target, int action, int arg) {
+    PlantParams p; std::memcpy(&p, params, sizeof(p));
+    PlantState st; std::memcpy(&st, state, sizeof(st));
+    int rc = maintenance_apply(st, p, target, action, arg);
+    std::memcpy(state, &st, sizeof(st));
+    return rc;
+}
+
 // ---- per-subsystem entry points used by tests/ to localise a mismatch --------------------------
 #include "feedwater.h"
 extern "C" int nps_oracle_feedwater(double* state, const double* params, const double* sg_levels,

@@ -1,0 +1,179 @@
+"""TEST INFRASTRUCTURE — maintenance fixtures from the LIVE reference (/root/reference).
+
+  python oracle/make_golden_maint.py effects     -> tests/golden/maint_effects.npz
+  python oracle/make_golden_maint.py scenarios   -> tests/golden/maint_<scenario>.npz
+
+effects:   before/after PlantState vectors around AutoMaintenanceSystem._perform_maintenance_action
+           (systems/maintenance/auto_maintenance.py:582-673) for every (component, action) pair the engine restates,
+           called exactly as _execute_work_order calls it, on plants with degraded initial conditions.
+scenarios: full NuclearPlantSimulator.step with state management and the automatic maintenance system, set up the
+           way MaintenanceScenarioRunner does (data_gen/runners/maintenance_scenario_runner.py:205-330): per step the
+           state after the step, the threshold events StateManager emitted, the work orders created and executed.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import types
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_REPO = os.path.dirname(_HERE)
+sys.path.insert(0, _REPO)
+from oracle import refplant as R  # noqa: E402
+
+GOLDEN = os.path.join(_REPO, "tests", "golden")
+
+# (component id, action, extracted_component_id or None)
+EFFECT_CASES = [
+    ("FWP-1", "oil_top_off", None), ("FWP-1", "oil_change", None), ("FWP-2", "bearing_replacement", None),
+    ("FWP-1", "bearing_replacement", "pump_bearings"), ("FWP-3", "bearing_replacement", "thrust_bearing"),
+    ("FWP-4", "bearing_replacement", "motor_bearings"), ("FWP-1", "seal_replacement", None),
+    ("FWP-2", "system_cleaning", None), ("FWP-1", "bearing_inspection", None), ("FWP-1", "impeller_inspection", None),
+    ("FWP-1", "impeller_replacement", None), ("FWP-1", "lubrication_system_check", None),
+    ("FWP-1", "motor_inspection", None), ("FWP-1", "oil_analysis", None), ("FWP-1", "vibration_analysis", None),
+    ("FWP-1", "cavitation_analysis", None), ("FWP-1", "npsh_analysis", None), ("FWP-1", "lubrication_inspection", None),
+    ("FWP-3", "component_overhaul", None),
+    ("SG-0", "tsp_chemical_cleaning", None), ("SG-1", "tsp_mechanical_cleaning", None), ("SG-0", "scale_removal", None),
+    ("SG-2", "moisture_separator_maintenance", None), ("SG-1", "secondary_side_cleaning", None),
+    ("SG-2", "routine_maintenance", None), ("SG-0", "tube_bundle_inspection", None), ("SG-0", "eddy_current_testing", None),
+    ("SG-1", "tube_interior_scale_cleaning", None), ("SG-2", "tube_bundle_overhaul", None),
+    ("HP-3", "efficiency_analysis", None), ("LP-2", "cleaning", None), ("HP-1", "blade_replacement", None),
+    ("LP-6", "overhaul", None), ("SECONDARY-COMP-001-TURB", "efficiency_analysis", None),
+    ("SECONDARY-COMP-001-COND", "condenser_tube_cleaning", None), ("SECONDARY-COMP-001-COND", "condenser_tube_plugging", None),
+    ("SECONDARY-COMP-001-COND", "condenser_chemical_cleaning", None), ("SECONDARY-COMP-001-COND", "vacuum_system_test", None),
+    ("SECONDARY-COMP-001-COND", "vacuum_leak_detection", None), ("SECONDARY-COMP-001-COND", "condenser_performance_test", None),
+]
+
+
+def runner_style_plant(action, dt=5.0, noise=False):
+    """Plant + maintenance monitoring configured as MaintenanceScenarioRunner does."""
+    cfg = R.compose_config(action, duration_hours=24.0)
+    rp = R.make_reference_plant(cfg, dt=dt, heat_source="constant", noise_enabled=noise, noise_std_percent=0.1,
+                                enable_state_management=True)
+    sim = rp.sim
+    with R.quiet():
+        sim.state_manager.config = cfg
+        sim.maintenance_system.setup_monitoring_from_state_manager(sim.state_manager, aggressive_mode=True)
+    return rp, cfg
+
+
+def effects():
+    L = R._layout()
+    names = np.array(L.field_names())
+    before, after, comp, act, arg, ok, params = [], [], [], [], [], [], None
+    plants = {}
+    for ic in ("oil_change", "tsp_chemical_cleaning"):
+        plants[ic] = runner_style_plant(ic)[0]
+    rng = np.random.RandomState(11)
+    for i, (cid, action, sub) in enumerate(EFFECT_CASES):
+        rp = plants["oil_change"] if (cid.startswith("FWP") or "COND" in cid or cid[:2] in ("HP", "LP") or "TURB" in cid) \
+            else plants["tsp_chemical_cleaning"]
+        sim = rp.sim
+        for _ in range(2):
+            z = np.array([0.0, rng.standard_normal(), rng.random_sample(), rng.random_sample(), rng.random_sample()])
+            rp.step(8, 1.0, z)
+        ms = sim.maintenance_system
+        inst = sim.state_manager.get_registered_instance_info()[cid]["instance"]
+        wo = types.SimpleNamespace(metadata={"extracted_component_id": sub} if sub else {})
+        b = R.extract_state(sim)
+        with R.quiet():
+            res = ms._perform_maintenance_action(inst, action, wo)
+        a = R.extract_state(sim)
+        if params is None:
+            params = R.extract_params(sim)
+        before.append(b); after.append(a); comp.append(cid); act.append(action); arg.append(sub or ""); ok.append(bool(res.success))
+        ch = np.nonzero(~((a == b) | (np.isnan(a) & np.isnan(b))))[0]
+        print(f"[effects] {cid:24s} {action:32s} {sub or '':16s} success={res.success!s:5s} changed={len(ch):3d} "
+              + ", ".join(names[j].split('.', 2)[-1] for j in ch[:6]))
+    sn, pn = np.array(L.field_names("PlantState")), np.array(L.field_names("PlantParams"))
+    os.makedirs(GOLDEN, exist_ok=True)
+    np.savez_compressed(os.path.join(GOLDEN, "maint_effects.npz"), before=np.array(before), after=np.array(after),
+                        component=np.array(comp), action=np.array(act), arg=np.array(arg), success=np.array(ok),
+                        params=params, state_names=sn, param_names=pn)
+
+
+def scenario(name, action, T, dt=5.0, tweak=None):
+    """Full step with maintenance; records states, events, work orders."""
+    rp, cfg = runner_style_plant(action, dt=dt)
+    sim = rp.sim
+    sm, ms = sim.state_manager, sim.maintenance_system
+    if tweak:
+        tweak(sim)
+    L = R._layout()
+    events = []      # dict(step, t, component, violations[(param, value, action, priority, component_id)], action)
+    created = []     # dict(step, t, wo, component, action, priority, planned_start, extracted)
+    executed = []    # dict(step, t, wo, component, action, success)
+    cur = {"step": -1}
+    orig_emit = sm._emit_batched_threshold_violation
+
+    def emit(cid, violations, optimal, ts):
+        events.append({"step": cur["step"], "t": float(ts), "component": cid, "action": optimal,
+                       "violations": [[v["parameter"], float(v["value"]), v["action"], v["priority"], v.get("component_id")]
+                                      for v in violations]})
+        return orig_emit(cid, violations, optimal, ts)
+    sm._emit_batched_threshold_violation = emit
+    orig_create = ms._create_automatic_work_order
+
+    def create(*a, **k):
+        wo = orig_create(*a, **k)
+        if wo is not None:
+            created.append({"step": cur["step"], "t": float(wo.created_date), "wo": wo.work_order_id, "component": wo.component_id,
+                            "action": wo.maintenance_actions[0].action_type, "priority": wo.priority.name,
+                            "planned_start": float(wo.planned_start_date),
+                            "extracted": getattr(wo, "metadata", {}).get("extracted_component_id") if hasattr(wo, "metadata") else None})
+        return wo
+    ms._create_automatic_work_order = create
+    # _execute_work_order raises inside StateManager.record_maintenance_result at HEAD (state_manager.py:1657 reads a
+    # non-existent self.current_time), AFTER the component was maintained; the exception aborts the rest of
+    # AutoMaintenanceSystem.update and is swallowed by sim.step (sim.py:210-216).  So the execution is recorded at
+    # the point the component is actually touched.
+    orig_perf = ms._perform_maintenance_action
+
+    def perform(component, action_type, work_order=None):
+        res = orig_perf(component, action_type, work_order)
+        executed.append({"step": cur["step"], "t": float(ms.last_check_time), "wo": getattr(work_order, "work_order_id", None),
+                         "component": getattr(work_order, "component_id", None), "action": action_type,
+                         "success": bool(res.success)})
+        return res
+    ms._perform_maintenance_action = perform
+
+    state0 = R.extract_state(sim)
+    params = R.extract_params(sim)
+    NS = L.N_STATE
+    states = np.zeros((T, NS))
+    noise = np.zeros((T, 5))
+    rng = np.random.RandomState(2024)
+    for t in range(T):
+        cur["step"] = t
+        z = np.array([0.0, rng.standard_normal(), rng.random_sample(), rng.random_sample(), rng.random_sample()])
+        noise[t] = z
+        rp.step(8, 1.0, z)
+        states[t] = R.extract_state(sim)
+    mcfg = cfg.get("maintenance_system", {})
+    sn, pn = np.array(L.field_names("PlantState")), np.array(L.field_names("PlantParams"))
+    np.savez_compressed(os.path.join(GOLDEN, f"maint_{name}.npz"), state0=state0, params=params, states=states, noise=noise,
+                        log=np.array(json.dumps({"events": events, "created": created, "executed": executed,
+                                                 "maintenance_system": mcfg})),
+                        state_names=sn, param_names=pn)
+    print(f"[scenario] {name}: T={T} events={len(events)} created={[(c['step'], c['component'], c['action']) for c in created]} "
+          f"executed={[(e['step'], e['component'], e['action'], e['success']) for e in executed]}")
+
+
+def scenarios():
+    scenario("oil_top_off", "oil_top_off", 60)
+    scenario("tsp_chemical_cleaning", "tsp_chemical_cleaning", 60)
+    scenario("oil_change", "oil_change", 60)
+    scenario("scale_removal", "scale_removal", 60)
+
+
+if __name__ == "__main__":
+    if not R.reference_available():
+        sys.exit("reference not found")
+    what = sys.argv[1:] or ["effects", "scenarios"]
+    if "effects" in what:
+        effects()
+    if "scenarios" in what:
+        scenarios()

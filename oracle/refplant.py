@@ -127,7 +127,10 @@ class ReferencePlant:
 
 def _clear_registries() -> None:
     from simulator.state.state_manager import StateManager
-    for attr in ("_pending_registrations",):
+    for attr in ("_pending_registrations", "_global_instance_counters"):
+        # _global_instance_counters numbers auto-generated ids (REA-001, WAT-00n, FEE-001 ...) per PROCESS
+        # (state_manager.py:620-629); clearing it makes every plant built here look like the first plant of a fresh
+        # interpreter, which is how the reference is actually run (one plant per process)
         if hasattr(StateManager, attr):
             getattr(StateManager, attr).clear()
     try:

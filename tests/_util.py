@@ -131,3 +131,108 @@ def oracle_run(L, state0, params, actions, mags, noise, setpoint, inject, t0, t1
         rc = L.nps_oracle_step_sp(ptr(st), ptr(params), ptr(a), ptr(m), ptr(z), ptr(sp), ctypes.c_int64(P), 1)
         assert rc == 0
     return st
+
+
+class OracleSim:
+    """CPU stand-in for BatchedNuclearPlantSimulator built on the host oracle (TEST INFRASTRUCTURE): same surface as
+    the device simulator for the maintenance host logic — step, threshold check with cooldown stamps
+    (a numpy restatement of nps_threshold_kernel / state_manager.py:1307-1369), effects, value read-back."""
+
+    def __init__(self, states, params):
+        from nuclear_sim_b200 import field_index
+        self.L = oracle_lib()
+        self.L.nps_oracle_apply_maintenance.restype = ctypes.c_int
+        self.st = np.ascontiguousarray(np.atleast_2d(states), dtype=np.float64).copy()
+        self.params = np.ascontiguousarray(params, dtype=np.float64)
+        self.n_plants = self.st.shape[0]
+        self.ix = field_index()
+        self._thr = None
+
+    def step(self, actions=None, magnitudes=None, noise=None, power_setpoint=None):
+        P = self.n_plants
+        a = np.full(P, 8, dtype=np.int8) if actions is None else np.ascontiguousarray(actions, dtype=np.int8)
+        m = np.ones(P) if magnitudes is None else np.ascontiguousarray(magnitudes, dtype=np.float64)
+        z = np.tile(np.array([0.0, 0.0, 1.0, 1.0, 1.0]), (P, 1)) if noise is None else np.ascontiguousarray(noise, dtype=np.float64)
+        sp = np.full(P, np.nan) if power_setpoint is None else np.ascontiguousarray(power_setpoint, dtype=np.float64)
+        assert self.L.nps_oracle_step_sp(ptr(self.st), ptr(self.params), ptr(a), ptr(m), ptr(z), ptr(sp), ctypes.c_int64(P), 1) == 0
+
+    def state_numpy(self):
+        return self.st.copy()
+
+    # thresholds
+    def set_thresholds(self, rows):
+        code = {"greater_than": 0, "less_than": 1, "greater_equal": 2, "less_equal": 3, "equals": 4, "not_equals": 5}
+        self._rows = [(-1 if r[0] is None else (int(r[0]) if isinstance(r[0], (int, np.integer)) else self.ix[r[0]]),
+                       code.get(r[1], 6), float(r[2]), float(r[3]) * 60.0) for r in rows]
+        self._last = np.full((len(self._rows), self.n_plants), -np.inf)
+        self._fired = []
+
+    def _value(self, f):
+        if f >= 0:
+            return self.st[:, f]
+        k = -f - 2
+        kind, unit = k >> 2, k & 3
+        assert kind == 0
+        w = lambda c: self.st[:, self.ix[f"fw.pump[{unit}].lub.component_wear[{c}]"]]
+        return w(0) + np.maximum(np.maximum(w(1), w(2)), w(3)) + w(4)
+
+    def check_thresholds(self):
+        now = self.st[:, self.ix["sim.time_minutes"]]
+        self._fired = []
+        for t, (f, c, val, cd) in enumerate(self._rows):
+            if f == -1:
+                continue
+            v = self._value(f)
+            ready = ~((now - self._last[t]) < cd)
+            with np.errstate(invalid="ignore"):
+                fire = [v > val, v < val, v >= val, v <= val, np.abs(v - val) < 1e-3, np.abs(v - val) >= 1e-3,
+                        np.zeros_like(v, dtype=bool)][c] & ready
+            self._last[t, fire] = now[fire]
+            self._fired += [(int(p), t) for p in np.nonzero(fire)[0]]
+
+    def drain_events(self):
+        return sorted(self._fired)
+
+    def reset_cooldowns(self, plant, rows):
+        self._last[list(rows), int(plant)] = -np.inf
+
+    def read_threshold_values(self, plants, table):
+        out = {}
+        for t, (f, *_rest) in enumerate(self._rows):
+            if f == -1:
+                continue
+            v = self._value(f)
+            for p in plants:
+                out[(p, t)] = float(v[p])
+        return out
+
+    def apply_maintenance(self, requests):
+        status = []
+        for plant, target, action, arg in requests:
+            row = np.ascontiguousarray(self.st[plant]).copy()
+            status.append(self.L.nps_oracle_apply_maintenance(ptr(row), ptr(self.params), int(target), int(action), int(arg)))
+            self.st[plant] = row
+        return status
+
+
+def replay_maintenance_scenario(sim, golden, make_maintenance, check_state):
+    """Drive `sim` through a maint_<scenario>.npz fixture with K=1 steps in the reference's order
+    (physics -> maintenance update -> threshold check, sim.py:155-223); returns the BatchedAutoMaintenance."""
+    import json
+    log = json.loads(str(golden["log"]))
+    from nuclear_sim_b200 import field_index
+    dt = float(golden["params"][field_index("PlantParams")["dt"]])
+    maint = make_maintenance(sim, log["maintenance_system"])
+    T = golden["states"].shape[0]
+    for t in range(T):
+        z = golden["noise"][t][None, :] if golden["noise"].ndim == 2 else golden["noise"][t]     # [P, 5]
+        if hasattr(sim, "slab"):      # device simulator: [K=1, 5, N] tensor
+            import torch
+            sim.step(noise=torch.from_numpy(np.ascontiguousarray(z.T[None])), K=1)
+        else:
+            sim.step(noise=z)
+        t_min = (t + 1) * dt
+        maint.update(t_min)
+        maint.check(t_min)
+        check_state(t, sim.state_numpy())
+    return maint, log

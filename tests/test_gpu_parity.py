@@ -163,3 +163,72 @@ def test_threshold_flags_and_ring_buffer():
     assert log.shape == (4, 3, n)
     np.testing.assert_array_equal(log[-1, 1], lvl)
     np.testing.assert_array_equal(log[-1, 0], sim.state.power_level.cpu().numpy())
+
+
+# ---- maintenance: flag kernel -> work orders -> effects on the device state --------------------------------------
+MAINT_SCENARIOS = ["oil_top_off", "tsp_chemical_cleaning", "oil_change", "scale_removal"]
+
+
+@pytest.mark.parametrize("name", MAINT_SCENARIOS)
+def test_cuda_maintenance_scenario_matches_reference(name):
+    """Full loop through the C ABI (nps_step, nps_check_thresholds, nps_apply_maintenance) against the live-reference
+    fixture: identical threshold events / work orders / execution steps, state within tolerance at every step."""
+    import os
+    from nuclear_sim_b200 import maintenance as M
+    from tests.test_maintenance_host import compare_logs
+    g = np.load(os.path.join(U.GOLDEN, f"maint_{name}.npz"), allow_pickle=False)
+    sim = _sim(g["state0"][None, :], g["params"])
+
+    def check_state(t, got):
+        U.assert_states_close(got, g["states"][t][None, :], U.TOL_STEP * (t + 1), f"{name} step {t}")
+    maint, log = U.replay_maintenance_scenario(
+        sim, g, lambda s, cfg: M.BatchedAutoMaintenance(s, M.ThresholdTable(cfg), aggressive=True), check_state)
+    compare_logs(maint, log)
+
+
+def test_cuda_maintenance_effects_match_reference():
+    """nps_apply_maintenance for every (component, action) fixture pair, batched: one plant per case."""
+    import os
+    from nuclear_sim_b200 import maintenance as M
+    z = np.load(os.path.join(U.GOLDEN, "maint_effects.npz"), allow_pickle=False)
+    n = len(z["component"])
+    sim = _sim(np.ascontiguousarray(z["before"]), z["params"])
+    req = []
+    for i in range(n):
+        action, sub = str(z["action"][i]), str(z["arg"][i])
+        req.append((i, M.target_code(str(z["component"][i])), M.action_code(action),
+                    M.BEARING_ARG.get(sub, 0) if action == "bearing_replacement" else 0))
+    status = sim.apply_maintenance(req)
+    assert [bool(s == 1) for s in status] == [bool(b) for b in z["success"]]
+    U.assert_states_close(sim.state_numpy(), z["after"], 1e-13, "maintenance effects")
+
+
+def test_cuda_maintenance_batched_equals_oracle_host_logic():
+    """256 plants with staggered oil levels / fouling: the device loop and the oracle stand-in must issue the same
+    work orders for the same plants at the same steps, and end in the same state."""
+    import os
+    import json
+    from nuclear_sim_b200 import maintenance as M, field_index
+    g = np.load(os.path.join(U.GOLDEN, "maint_oil_top_off.npz"), allow_pickle=False)
+    cfg = json.loads(str(g["log"]))["maintenance_system"]
+    ix = field_index()
+    n = 256
+    st = np.tile(g["state0"], (n, 1))
+    rng = np.random.RandomState(5)
+    st[:, ix["fw.pump[0].lub.oil_level"]] = 58.0 + rng.uniform(0.0, 1.5, n)
+    st[:, ix["fw.pump[2].lub.oil_level"]] = 58.0 + rng.uniform(0.0, 3.0, n)
+    st[:, ix["fw.pump[1].lub.oil_contamination_level"]] = 15.2 - rng.uniform(0.0, 0.02, n)
+    dt = float(g["params"][field_index("PlantParams")["dt"]])
+    sims = [_sim(st, g["params"]), U.OracleSim(st, g["params"])]
+    maints = [M.BatchedAutoMaintenance(s, M.ThresholdTable(cfg), aggressive=True) for s in sims]
+    import torch
+    for t in range(30):
+        sims[0].step(K=1)
+        sims[1].step()
+        for m in maints:
+            m.update((t + 1) * dt)
+            m.check((t + 1) * dt)
+    key = lambda w: (w.plant, w.created, w.component_id, w.action, w.priority, w.executed_at, w.success)
+    assert [key(w) for w in maints[0].created_log] == [key(w) for w in maints[1].created_log]
+    assert len(maints[0].created_log) > 50 and len(maints[0].executed_log) > 50
+    U.assert_states_close(sims[0].state_numpy(), sims[1].state_numpy(), U.TOL_STEP * 30, "batched maintenance")

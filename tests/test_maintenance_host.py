@@ -1,0 +1,134 @@
+"""Maintenance: action effects (host oracle vs live-reference fixtures), threshold binding, orchestrator decisions.
+
+tests/golden/maint_effects.npz and maint_<scenario>.npz come from the unmodified reference (oracle/make_golden_maint.py).
+"""
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests import _util as U
+
+
+def _maint():
+    from nuclear_sim_b200 import maintenance
+    return maintenance
+
+
+def test_action_names_match_library():
+    from nuclear_sim_b200 import _clib
+    M = _maint()
+    L = _clib.lib()
+    n = L.nps_n_maintenance_actions()
+    assert n == len(M.ACTION_NAMES)
+    assert tuple(L.nps_maintenance_action_name(i).decode() for i in range(n)) == M.ACTION_NAMES
+
+
+def _load_effects():
+    z = np.load(os.path.join(U.GOLDEN, "maint_effects.npz"), allow_pickle=False)
+    from nuclear_sim_b200 import field_names
+    assert tuple(str(s) for s in z["state_names"]) == field_names("PlantState")
+    return z
+
+
+def test_effects_match_reference(oracle_lib):
+    """component.perform_maintenance state mutations, one (component, action) pair at a time."""
+    M = _maint()
+    z = _load_effects()
+    params = np.ascontiguousarray(z["params"])
+    oracle_lib.nps_oracle_apply_maintenance.restype = ctypes.c_int
+    for i in range(len(z["component"])):
+        cid, action, sub = str(z["component"][i]), str(z["action"][i]), str(z["arg"][i])
+        st = np.ascontiguousarray(z["before"][i]).copy()
+        arg = M.BEARING_ARG.get(sub, 0) if action == "bearing_replacement" else 0
+        rc = oracle_lib.nps_oracle_apply_maintenance(U.ptr(st), U.ptr(params), M.target_code(cid), M.action_code(action), arg)
+        assert rc in (0, 1), f"{cid} {action}: unsupported target"
+        assert bool(rc) == bool(z["success"][i]), f"{cid} {action}: success flag {rc} vs reference {z['success'][i]}"
+        U.assert_states_close(st[None, :], z["after"][i][None, :], 1e-13, f"{cid} {action} {sub}")
+
+
+def _template_maintenance_config():
+    z = np.load(os.path.join(U.GOLDEN, "maint_oil_top_off.npz"), allow_pickle=False)
+    return json.loads(str(z["log"]))["maintenance_system"]
+
+
+def test_threshold_binding_matches_reference_probe():
+    """331 threshold rows, 90 of them bound to a logged column; the rest are inert exactly
+    as in the reference, where _find_parameter_in_row_data finds no column."""
+    M = _maint()
+    tab = M.ThresholdTable(_template_maintenance_config())
+    assert len(tab) == 331
+    assert len(tab.bound()) == 90
+    assert not tab.unsupported()
+    by = {(r.component_id, r.parameter): r for r in tab.rows}
+    assert by[("FWP-1", "oil_level")].field == "fw.pump[0].lub.oil_level"
+    assert by[("FWP-3", "thrust_bearing_wear")].field == "fw.pump[2].lub.component_wear[3]"
+    assert by[("FWP-3", "thrust_bearing_wear")].sub_component == "thrust_bearing"
+    assert by[("FWP-2", "sum_wear_level")].derived == "pump_sum_wear"
+    assert by[("SG-1", "tube_wall_temperature")].field == "sgs.sg[1].tube_wall_temp"
+    assert by[("LP-6", "efficiency")].field == "turb.stage[13].actual_efficiency"
+    assert by[("SECONDARY-COMP-001-TURB", "efficiency")].field == "turb.stage[13].actual_efficiency"   # last stage wins
+    assert by[("FEE-001", "oil_level")].field is None and by[("FEE-001", "oil_level")].column is None
+    assert by[("SECONDARY-COMP-001-COND", "fouling_resistance")].field == "cond.fl_total_fouling_resistance"
+    # order of components = order the reference emits events in
+    assert [r.component_id for r in tab.rows][0] == "FWP-1" and tab.rows[-1].component_id == "SECONDARY-COMP-001-COND"
+
+
+def test_orchestrator_decisions():
+    M = _maint()
+    v = lambda p, val, a: {"parameter": p, "value": val, "action": a}
+    assert M.orchestrate("FWP-1", [v("oil_level", 57.9, "oil_top_off")], "oil_top_off") == "oil_top_off"
+    # promotion: oil_top_off -> oil_change when the contamination violation is in the batch
+    assert M.orchestrate("FWP-1", [v("oil_level", 57.9, "oil_top_off"), v("oil_contamination_level", 15.5, "oil_change")],
+                         "oil_top_off") == "oil_change"
+    # two encompassed major actions -> component_overhaul
+    assert M.orchestrate("FWP-2", [v("motor_bearing_wear", 9.0, "bearing_replacement"), v("seal_wear", 17.0, "seal_replacement")],
+                         "bearing_replacement") == "component_overhaul"
+    # coordination keeps the base action
+    assert M.orchestrate("FWP-2", [v("motor_bearing_wear", 9.0, "bearing_replacement"), v("npsh_available", 17.0, "npsh_analysis")],
+                         "bearing_replacement") == "bearing_replacement"
+    assert M.orchestrate("SG-0", [v("tsp_fouling_fraction", 0.31, "tsp_chemical_cleaning")], "tsp_chemical_cleaning") == "tsp_chemical_cleaning"
+    # 'HP-1' contains neither 'tb' nor 'turbine': unknown type, no hierarchy
+    assert M.infer_component_type("HP-1") == "unknown"
+    assert M.infer_component_type("SECONDARY-COMP-001-COND") == "unknown"     # neither 'cd' nor 'condenser' occurs in the id
+    assert M.infer_component_type("SECONDARY-COMP-001-SG") == "steam_generator"
+
+
+SCENARIOS = ["oil_top_off", "tsp_chemical_cleaning", "oil_change", "scale_removal"]
+
+
+def compare_logs(maint, log, plant=0):
+    """Discrete events must match bit-exactly: which step, which component, which violations, which action."""
+    ev_ref = log["events"]
+    ev = [e for e in maint.event_log if e["plant"] == plant]
+    assert [(e["t"], e["component"], e["action"]) for e in ev] == [(e["t"], e["component"], e["action"]) for e in ev_ref]
+    for a, b in zip(ev, ev_ref):
+        assert [(v["parameter"], v["action"], v["priority"], v["component_id"]) for v in a["violations"]] == \
+               [(v[0], v[2], v[3], v[4]) for v in b["violations"]]
+        for va, vb in zip(a["violations"], b["violations"]):
+            assert abs(va["value"] - vb[1]) <= 1e-9 * max(1.0, abs(vb[1]))
+    cr = [w for w in maint.created_log if w.plant == plant]
+    assert [(w.created, w.work_order_id, w.component_id, w.action, w.priority, w.planned_start, w.sub_component) for w in cr] == \
+           [(c["t"], c["wo"], c["component"], c["action"], c["priority"], c["planned_start"], c["extracted"]) for c in log["created"]]
+    ex = [w for w in maint.executed_log if w.plant == plant]
+    assert [(w.executed_at, w.work_order_id, w.component_id, w.action, w.success) for w in ex] == \
+           [(e["t"], e["wo"], e["component"], e["action"], e["success"]) for e in log["executed"]]
+
+
+@pytest.mark.parametrize("name", SCENARIOS)
+def test_scenario_host_logic_on_oracle(name):
+    """Threshold events, work-order issuance and execution times equal the live reference's, and the state after every
+    step (including the steps where perform_maintenance mutated it) stays within the per-step tolerance."""
+    M = _maint()
+    g = np.load(os.path.join(U.GOLDEN, f"maint_{name}.npz"), allow_pickle=False)
+    sim = U.OracleSim(g["state0"], g["params"])
+    worst = [0.0]
+
+    def check_state(t, got):
+        worst[0] = max(worst[0], U.assert_states_close(got, g["states"][t][None, :], U.TOL_STEP * (t + 1), f"{name} step {t}"))
+    maint, log = U.replay_maintenance_scenario(
+        sim, g, lambda s, cfg: M.BatchedAutoMaintenance(s, M.ThresholdTable(cfg), aggressive=True), check_state)
+    compare_logs(maint, log)
+    assert len(log["created"]) >= 1 and len(log["executed"]) >= 1
