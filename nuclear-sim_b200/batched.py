@@ -165,6 +165,26 @@ class BatchedNuclearPlantSimulator:
             self.slab[:, m] = self._initial[:, m]
         return self.get_observation()
 
+    # -- single-plant conveniences used by the scalar NuclearPlantSimulator facade (plant_simulator.py) ----------
+    def step_plant(self, plant: int, action: int, magnitude: float, z: np.ndarray):
+        """One reference-style step of a ONE-plant engine: returns (observation[22], reward, done)."""
+        if self.n_plants != 1 or plant != 0:
+            raise _clib.NpsError("step_plant drives a 1-plant engine; batches step in lockstep through step()")
+        out = self.step(actions=torch.tensor([[int(action)]], dtype=torch.int8),
+                        magnitudes=torch.tensor([[float(magnitude)]], dtype=torch.float64),
+                        noise=torch.as_tensor(np.asarray(z, dtype=np.float64).reshape(1, NOISE_PER_STEP, 1)), K=1)
+        return (out["observation"][0].cpu().numpy().copy(), float(out["reward"][0].item()), bool(out["done"][0].item()))
+
+    def observe_plant(self, plant: int) -> np.ndarray:
+        return self.get_observation()[plant].cpu().numpy().copy()
+
+    def reset_plant(self, plant: int) -> None:
+        self.slab[:, plant] = self._initial[:, plant]
+
+    def write_fields(self, plant: int, values: Dict[int, float]) -> None:
+        for f, v in values.items():
+            self.slab[int(f), int(plant)] = float(v)
+
     # -- state access -------------------------------------------------------------------------
     def state_numpy(self) -> np.ndarray:
         """[n_plants, n_state] host copy in PlantState field order."""

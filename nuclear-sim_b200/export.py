@@ -1,0 +1,152 @@
+"""Trajectory export in the reference's schemas.
+
+* wide CSV  — StateManager.export_to_csv / export_by_category / export_by_subcategory
+              (nuclear_simulator/simulator/state/state_manager.py:296-386): one row per logged step, first column
+              ``time`` (ISO datetime), then ``category.subcategory[_<id>].variable`` columns in the reference's order;
+* long CSV  — data/plant_data_logger.py:82-157: ``timestamp,parameter_name,value,unit,quality``.
+
+The reference builds each row from Python ``get_state_dict()`` calls (789 columns).  The batched engine carries the
+same quantities as PlantState fields; data/reference_columns.json (written by oracle/make_column_map.py from a live
+plant) names the field behind every column.  Columns that are constants in the reference are written as that constant;
+columns that are derived report values which the engine does not carry are listed in ``unavailable_columns`` and left
+out (the reference's own consumers of these files — the runners' fwp.csv / secondary.csv — read them by name).
+"""
+from __future__ import annotations
+
+import csv
+import datetime as _dt
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from ._layout import field_index
+from .maintenance import load_reference_columns
+
+
+class ColumnSchema:
+    """Reference column order + how to obtain each column from a PlantState vector."""
+
+    def __init__(self, columns: Optional[Dict[str, dict]] = None):
+        cols = columns if columns is not None else load_reference_columns()
+        ix = field_index()
+        self.names: List[str] = []
+        self.kind: List[Tuple[str, object, str]] = []     # (how, payload, python type name)
+        self.unavailable: List[str] = []
+        for name, e in cols.items():
+            if name == "time":
+                continue
+            if e.get("field") in ix:
+                self.names.append(name); self.kind.append(("field", ix[e["field"]], e["type"]))
+            elif e.get("derived") == "pump_sum_wear":
+                u = e["unit"]
+                w = [ix[f"{u}lub.component_wear[{c}]"] for c in range(5)]
+                self.names.append(name); self.kind.append(("sum_wear", w, e["type"]))
+            elif "const" in e:
+                self.names.append(name); self.kind.append(("const", e["const"], e["type"]))
+            else:
+                self.unavailable.append(name)
+
+    def select(self, prefix: Optional[str] = None) -> List[int]:
+        return [i for i, n in enumerate(self.names) if prefix is None or n.startswith(prefix)]
+
+    def logged_fields(self, which: Sequence[int]) -> List[int]:
+        """PlantState field indices needed to produce the selected columns (for the device ring buffer)."""
+        need = []
+        for i in which:
+            how, payload, _ = self.kind[i]
+            if how == "field":
+                need.append(payload)
+            elif how == "sum_wear":
+                need += list(payload)
+        return sorted(set(need))
+
+    def row(self, state: np.ndarray, which: Sequence[int]) -> list:
+        out = []
+        for i in which:
+            how, payload, typ = self.kind[i]
+            if how == "field":
+                v = float(state[payload])
+            elif how == "sum_wear":
+                w = state[payload]
+                v = float(w[0] + max(w[1], w[2], w[3]) + w[4])
+            else:
+                v = payload
+            if typ in ("bool", "bool_"):
+                out.append(bool(v))
+            elif typ == "int":
+                out.append(int(v))
+            else:
+                out.append(v)
+        return out
+
+
+class TrajectoryStore:
+    """Host-side row store with StateManager's export surface for ONE plant's rows (full PlantState per step)."""
+
+    def __init__(self, start_datetime: Optional[_dt.datetime] = None, max_rows: int = 100000):
+        self.start_datetime = start_datetime or _dt.datetime(2024, 1, 1)
+        self.times: List[_dt.datetime] = []
+        self.rows: List[np.ndarray] = []
+        self.max_rows = int(max_rows)
+        self.schema = ColumnSchema()
+
+    def add_row(self, when: _dt.datetime, state: np.ndarray) -> None:
+        self.times.append(when)
+        self.rows.append(np.array(state, dtype=np.float64, copy=True))
+        if len(self.rows) > self.max_rows:       # StateManager trims the oldest rows when over capacity
+            del self.rows[0]; del self.times[0]
+
+    def clear(self) -> None:
+        self.times.clear(); self.rows.clear()
+
+    def _write(self, filename: str, which: Sequence[int], time_range=None) -> int:
+        n = 0
+        with open(filename, "w", newline="") as fh:
+            w = csv.writer(fh)
+            w.writerow(["time"] + [self.schema.names[i] for i in which])
+            for t, s in zip(self.times, self.rows):
+                if time_range is not None and not (time_range[0] <= t <= time_range[1]):
+                    continue
+                w.writerow([t.isoformat()] + self.schema.row(s, which))
+                n += 1
+        return n
+
+    def export_to_csv(self, filename: str, time_range=None, variables: Optional[Iterable[str]] = None) -> int:
+        which = self.schema.select() if variables is None else [self.schema.names.index(v) for v in variables]
+        return self._write(filename, which, time_range)
+
+    def export_by_category(self, category: str, filename: str, time_range=None) -> int:
+        return self._write(filename, self.schema.select(f"{category}."), time_range)
+
+    def export_by_subcategory(self, category: str, subcategory: str, filename: str, time_range=None) -> int:
+        return self._write(filename, self.schema.select(f"{category}.{subcategory}."), time_range)
+
+
+# PlantDataLogger.extract_all_parameters (data/plant_data_logger.py:91-136): 22 parameters per step, in this order
+def plant_data_logger_parameters(state: np.ndarray, simulation_time: float) -> List[Tuple[str, object, str]]:
+    ix = field_index()
+    g = lambda f: float(state[ix[f]])
+    out = [("neutron_flux", g("pri.neutron_flux"), "neutrons/cm\u00b2/s"), ("reactivity", g("pri.reactivity"), "\u0394k/k")]
+    out += [(f"delayed_neutron_precursors_group_{i + 1}", g(f"pri.precursors[{i}]"), "relative") for i in range(6)]
+    out += [("fuel_temperature", g("pri.fuel_temperature"), "\u00b0C"), ("coolant_temperature", g("pri.coolant_temperature"), "\u00b0C"),
+            ("coolant_pressure", g("pri.coolant_pressure"), "MPa"), ("coolant_flow_rate", g("pri.coolant_flow_rate"), "kg/s"),
+            ("steam_temperature", g("pri.steam_temperature"), "\u00b0C"), ("steam_pressure", g("pri.steam_pressure"), "MPa"),
+            ("steam_flow_rate", g("pri.steam_flow_rate"), "kg/s"), ("feedwater_flow_rate", g("pri.feedwater_flow_rate"), "kg/s"),
+            ("control_rod_position", g("pri.control_rod_position"), "%"), ("steam_valve_position", g("pri.steam_valve_position"), "%"),
+            ("power_level", g("pri.power_level"), "%"), ("scram_status", int(g("pri.scram_status")), "boolean"),
+            ("thermal_power", g("pri.neutron_flux") / 1e12 * 3000, "MW"), ("simulation_time", float(simulation_time), "s")]
+    return out
+
+
+def export_long_format(filename: str, timestamps: Sequence[str], states: Sequence[np.ndarray], sim_times: Sequence[float],
+                       quality: str = "GOOD") -> int:
+    """PlantDataLogger long format: timestamp,parameter_name,value,unit,quality (data/plant_data_logger.py:82-157)."""
+    n = 0
+    with open(filename, "w", newline="") as fh:
+        w = csv.writer(fh)
+        w.writerow(["timestamp", "parameter_name", "value", "unit", "quality"])
+        for ts, s, t in zip(timestamps, states, sim_times):
+            for name, value, unit in plant_data_logger_parameters(s, t):
+                w.writerow([ts, name, value, unit, quality])
+                n += 1
+    return n

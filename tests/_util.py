@@ -144,6 +144,7 @@ class OracleSim:
         self.L.nps_oracle_apply_maintenance.restype = ctypes.c_int
         self.st = np.ascontiguousarray(np.atleast_2d(states), dtype=np.float64).copy()
         self.params = np.ascontiguousarray(params, dtype=np.float64)
+        self._initial = self.st.copy()
         self.n_plants = self.st.shape[0]
         self.ix = field_index()
         self._thr = None
@@ -158,6 +159,28 @@ class OracleSim:
 
     def state_numpy(self):
         return self.st.copy()
+
+    # single-plant conveniences (same surface as BatchedNuclearPlantSimulator)
+    def step_plant(self, plant, action, magnitude, z):
+        assert self.n_plants == 1 and plant == 0
+        self.step(actions=[action], magnitudes=[magnitude], noise=np.asarray(z, dtype=np.float64)[None, :])
+        obs, rew = self._observe()
+        return obs[0], float(rew[0]), bool(self.st[0, self.ix["pri.scram_activated"]] != 0.0)
+
+    def _observe(self):
+        obs = np.zeros((self.n_plants, 22)); rew = np.zeros(self.n_plants)
+        self.L.nps_oracle_observe(ptr(np.ascontiguousarray(self.st)), ptr(self.params), ctypes.c_int64(self.n_plants), ptr(obs), ptr(rew))
+        return obs, rew
+
+    def observe_plant(self, plant):
+        return self._observe()[0][plant]
+
+    def reset_plant(self, plant):
+        self.st[plant] = self._initial[plant]
+
+    def write_fields(self, plant, values):
+        for f, v in values.items():
+            self.st[int(plant), int(f)] = float(v)
 
     # thresholds
     def set_thresholds(self, rows):

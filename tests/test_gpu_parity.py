@@ -232,3 +232,35 @@ def test_cuda_maintenance_batched_equals_oracle_host_logic():
     assert [key(w) for w in maints[0].created_log] == [key(w) for w in maints[1].created_log]
     assert len(maints[0].created_log) > 50 and len(maints[0].executed_log) > 50
     U.assert_states_close(sims[0].state_numpy(), sims[1].state_numpy(), U.TOL_STEP * 30, "batched maintenance")
+
+
+def test_cuda_scalar_facade_runs_maintenance_scenario(tmp_path):
+    """The reference-API facade (plant_simulator.NuclearPlantSimulator) on a 1-plant CUDA engine: step() dicts, work
+    orders through the runner-facing members, CSV export in the reference schema."""
+    import csv
+    import json
+    import os
+    import types
+    from nuclear_sim_b200.plant_simulator import NuclearPlantSimulator
+    g = np.load(os.path.join(U.GOLDEN, "maint_oil_top_off.npz"), allow_pickle=False)
+    log = json.loads(str(g["log"]))
+    sim = NuclearPlantSimulator(dt=5.0, initial_state=g["state0"], params=g["params"], device="cuda:0")
+    sim.state_manager.config = {"maintenance_system": log["maintenance_system"]}
+    sim.maintenance_system.setup_monitoring_from_state_manager(sim.state_manager, aggressive_mode=True)
+    created = []
+    for t in range(g["states"].shape[0]):
+        z = g["noise"][t]
+        sim._ph_rng = types.SimpleNamespace(standard_normal=lambda z=z: float(z[1]),
+                                            random_sample=lambda z=z, it=iter([2, 3, 4]): float(z[next(it)]))
+        out = sim.step(action=None)
+        assert out["observation"].shape == (22,) and isinstance(out["reward"], float) and out["done"] is False
+        if sim.maintenance_system.current_update_work_orders:
+            created.append(t)
+        U.assert_states_close(sim._engine.state_numpy(), g["states"][t][None, :], U.TOL_STEP * (t + 1), f"facade step {t}")
+    assert created == [c["step"] for c in log["created"]]
+    fwp = tmp_path / "fwp.csv"
+    sim.state_manager.export_by_subcategory("secondary", "feedwater_FWP-1", str(fwp))
+    rows = list(csv.reader(open(fwp)))
+    j = rows[0].index("secondary.feedwater_FWP-1.oil_level")
+    ref_j = int(np.nonzero(g["state_names"] == "fw.pump[0].lub.oil_level")[0][0])
+    assert np.allclose([float(r[j]) for r in rows[1:]], g["states"][:, ref_j], rtol=1e-9)
