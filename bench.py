@@ -7,7 +7,7 @@
 Workload (config.workload): BASELINE config #3 — 65,536 plants PER GPU with randomised initial
 conditions, ReactorHeatSource at equilibrium, load-following / power-ramp rod actions plus the
 (inert) feedwater actions, dt = 1.0.  One bench "step" = ONE launch of the fused step kernel
-advancing every plant by SUBSTEPS (=8) timesteps, i.e. plants x 8 plant-steps.  Plants shard over
+advancing every plant by SUBSTEPS (=32) timesteps, i.e. plants x 32 plant-steps.  Plants shard over
 ranks with no data-path collective (weak scaling); an NCCL all-gather of trajectory summaries runs
 after the timed region.
 
@@ -33,12 +33,30 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 PLANTS_PER_GPU = 65536
-SUBSTEPS = 8
+SUBSTEPS = 32
 FLOP_PER_PLANT_STEP = 2.0e4          # SURVEY.md §8d canonical figure (FP64 flop-equivalents)
 METRIC = "plant-steps/sec"
 UNIT = "plant-steps/s"
 WORKLOAD = ("cfg3: 65,536 plants per GPU, randomized ICs, reactor heat source, load-following/power-ramp "
-            "rod + feedwater actions, dt=1.0, 8 fused substeps per launch")
+            "rod + feedwater actions, dt=1.0, 32 fused substeps per launch")
+
+
+def _n_live_fields():
+    """Fields that are read before written within a step (csrc/plant/live_fields.txt): the per-substep working set."""
+    path = os.path.join(ROOT, "nuclear-sim_b200", "csrc", "plant", "live_fields.txt")
+    return sum(1 for ln in open(path) if ln.strip() and not ln.startswith("#"))
+
+
+def _measured_traffic(n, ksub):
+    """DRAM bytes per launch of nps_step_kernel from the committed ncu capture (profiles/r01_step_kernel_traffic.json),
+    scaled per plant-substep; None when the capture is for a different build."""
+    path = os.path.join(ROOT, "profiles", "r01_step_kernel_traffic.json")
+    try:
+        t = json.load(open(path))
+        per = (t["dram_bytes_read"] + t["dram_bytes_write"]) / (t["plants"] * t["substeps"])
+        return per * n * ksub
+    except Exception:
+        return None
 
 
 def _peaks():
@@ -174,6 +192,9 @@ def main():
     ap.add_argument("--plants-per-gpu", type=int, default=PLANTS_PER_GPU)
     ap.add_argument("--substeps", type=int, default=SUBSTEPS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2"],
+                    help="cfg3 (headline): reactor heat source + load-following actions; cfg2: constant heat source, "
+                         "steady 100 %%, NO_ACTION (same plant count; diagnostic for branch-mix sensitivity)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -198,7 +219,7 @@ def main():
     n = args.plants_per_gpu
     ksub = args.substeps
 
-    s0, params = load_snapshot("pwr3000_reactor_dt1")
+    s0, params = load_snapshot("pwr3000_reactor_dt1" if args.workload == "cfg3" else "pwr3000_steady_dt1")
     pid = np.arange(rank * n, (rank + 1) * n)
     sim = BatchedNuclearPlantSimulator(n, sc.randomized_states(s0, pid), params, device=str(dev))
     state_bytes = sim.slab.numel() * 8
@@ -210,6 +231,8 @@ def main():
     noise_h = torch.empty((total, ksub, 5, n), dtype=torch.float64).pin_memory()
     for i in range(total):
         a, m = sc.load_following_inputs(pid, i * ksub, ksub)
+        if args.workload == "cfg2":
+            a[:] = 8
         acts_h[i] = torch.from_numpy(a); mags_h[i] = torch.from_numpy(m)
         noise_h[i] = torch.from_numpy(sc.noise_inputs(pid, i * ksub, ksub))
     acts_d, mags_d, noise_d = acts_h.to(dev), mags_h.to(dev), noise_h.to(dev)
@@ -277,16 +300,24 @@ def main():
 
     if rank == 0:
         peak, peak_src = _peaks()
-        # algorithmic bytes of one launch: state slab read + written once, per-substep inputs read, outputs written
-        bytes_per_launch = 2 * state_bytes + ksub * n * (1 + 8 + 40) + n * (22 * 8 + 8 + 1)
+        # Algorithmic bytes of one launch: a plant's state is 10.4 KB and 448 plants are resident per
+        # SM (4.7 MB against 0.5 MB of registers + shared memory), so EVERY substep must stream the fields that are
+        # live on entry in from HBM and the same number back out; fields that are only outputs leave once per launch.
+        n_live = _n_live_fields()
+        per_substep = 2 * n_live * 8 + (1 + 8 + 40)                        # live state in + out, per-substep inputs
+        per_launch = (N_STATE - n_live) * 8 + (22 * 8 + 8 + 1)              # output-only fields, obs/reward/done
+        bytes_per_launch = n * (ksub * per_substep + per_launch)
+        resident_bytes_per_launch = 2 * state_bytes + ksub * n * (1 + 8 + 40) + n * (22 * 8 + 8 + 1)
         avg_launch_s = float(per_launch_ms.mean()) * 1e-3
         achieved = bytes_per_launch / avg_launch_s / 1e9
+        traffic = _measured_traffic(n, ksub)
         fp64_tflops = n * ksub * FLOP_PER_PLANT_STEP / avg_launch_s / 1e12
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": t_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "plants_per_gpu": n, "substeps_per_step": ksub, "n_state_fields": N_STATE,
+            "config": {"workload": WORKLOAD if args.workload == "cfg3" else WORKLOAD.replace("cfg3", "cfg2 (steady 100 %, constant heat source, NO_ACTION)"),
+                       "plants_per_gpu": n, "substeps_per_step": ksub, "n_state_fields": N_STATE,
                        "state_bytes_per_gpu": state_bytes,
                        "l2": "inputs larger than L2 (state slab %.0f MB per GPU is streamed every launch)" % (state_bytes / 1e6),
                        "mean_power_percent_after_run": mean_power},
@@ -296,9 +327,15 @@ def main():
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
                        "samples": clocks["samples"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "nps_step_kernel",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "nps_step_kernel",
                          "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_launch_s * 1e3,
-                         "fp64_tflops_at_2e4_flop_per_plant_step": fp64_tflops},
+                         "algorithmic_bytes_per_plant_step": bytes_per_launch / (n * ksub), "n_live_fields": n_live,
+                         "note": "per-substep streaming of the live state (it cannot be resident: 4.7 MB per SM); "
+                                 "frac_if_state_resident is the K-amortised figure of SURVEY 8d",
+                         "frac_if_state_resident": resident_bytes_per_launch / avg_launch_s / 1e9 / peak,
+                         "dram_gbs_actual": (traffic / avg_launch_s / 1e9) if traffic else None,
+                         "fp64_tflops_at_2e4_flop_per_plant_step": fp64_tflops,
+                         "fp64_frac_of_37_tflops": fp64_tflops / 37.0},
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline()

@@ -53,21 +53,20 @@ struct nps_handle {
 // ------------------------------------------------------------------------------------------------
 // step kernel: thread-per-plant, state register/local resident across k substeps
 // ------------------------------------------------------------------------------------------------
-#ifndef NPS_STEP_BLOCK
-#define NPS_STEP_BLOCK 64
-#endif
-#ifndef NPS_STEP_MINBLOCKS
-#define NPS_STEP_MINBLOCKS 7   /* <=128 registers: 448 threads/SM, so 65,536 plants are ONE wave on 148 SMs */
-#endif
+// Launch shapes (both 128 registers, 448 resident threads per SM, so 65,536 plants are ONE wave on 148 SMs):
+//   large batches  448 threads x 1 block/SM  - measured 2 % faster than 64 x 7 at 65,536 plants (profiles/r01_sweep_block_substeps.txt)
+//   small batches   64 threads x 7 blocks/SM - spreads a few thousand plants over all SMs instead of a handful
+// NPS_STEP_BLOCK / NPS_STEP_MINBLOCKS pin one shape for tuning builds.
 #ifndef NPS_COPY_UNROLL
 #define NPS_COPY_UNROLL 8   /* loads in flight per thread while the slab is copied in / out; 2, 4, 24 and 48 all
                                measured slower on B200 (profiles/r01_tuning_variants.txt) */
 #endif
 #define NPS_STR_(x) #x
 #define NPS_PRAGMA_UNROLL(n) _Pragma(NPS_STR_(unroll n))
-constexpr int kStepBlock = NPS_STEP_BLOCK;
+constexpr int kLargeBatch = 148 * 448 / 2;
 
-__global__ void __launch_bounds__(kStepBlock, NPS_STEP_MINBLOCKS)
+template <int BLOCK, int MINBLOCKS>
+__global__ void __launch_bounds__(BLOCK, MINBLOCKS)
 nps_step_kernel(double* __restrict__ slab, const __grid_constant__ PlantParams prm, const int8_t* __restrict__ action,
                 const double* __restrict__ magnitude, const double* __restrict__ noise,
                 const double* __restrict__ setpoint, int k_substeps, int64_t n,
@@ -262,7 +261,12 @@ int nps_create(int64_t n_plants, int device, nps_handle** out) {
     h->n = n_plants; h->device = device;
     std::memset(&h->params, 0, sizeof(PlantParams));
     // the step kernel keeps one PlantState per thread in local memory
-    NPS_CUDA(cudaFuncSetCacheConfig(nps_step_kernel, cudaFuncCachePreferL1));
+#if defined(NPS_STEP_BLOCK)
+    NPS_CUDA(cudaFuncSetCacheConfig(nps_step_kernel<NPS_STEP_BLOCK, NPS_STEP_MINBLOCKS>, cudaFuncCachePreferL1));
+#else
+    NPS_CUDA(cudaFuncSetCacheConfig(nps_step_kernel<448, 1>, cudaFuncCachePreferL1));
+    NPS_CUDA(cudaFuncSetCacheConfig(nps_step_kernel<64, 7>, cudaFuncCachePreferL1));
+#endif
     *out = h;
     return 0;
 }
@@ -291,9 +295,17 @@ int nps_step(nps_handle* h, double* d_state, const int8_t* d_action, const doubl
     if (!h || !d_state) return fail("nps_step: null argument");
     if (k_substeps <= 0) return fail("nps_step: k_substeps must be positive");
     cudaStream_t s = (cudaStream_t)cuda_stream;
-    const int grid = (int)((h->n + kStepBlock - 1) / kStepBlock);
-    nps_step_kernel<<<grid, kStepBlock, 0, s>>>(d_state, h->params, d_action, d_magnitude, d_noise, d_setpoint,
-                                                k_substeps, h->n, d_obs, d_reward, d_done);
+#if defined(NPS_STEP_BLOCK)
+    nps_step_kernel<NPS_STEP_BLOCK, NPS_STEP_MINBLOCKS><<<(int)((h->n + NPS_STEP_BLOCK - 1) / NPS_STEP_BLOCK), NPS_STEP_BLOCK, 0, s>>>(
+        d_state, h->params, d_action, d_magnitude, d_noise, d_setpoint, k_substeps, h->n, d_obs, d_reward, d_done);
+#else
+    if (h->n >= kLargeBatch)
+        nps_step_kernel<448, 1><<<(int)((h->n + 447) / 448), 448, 0, s>>>(d_state, h->params, d_action, d_magnitude, d_noise,
+                                                                         d_setpoint, k_substeps, h->n, d_obs, d_reward, d_done);
+    else
+        nps_step_kernel<64, 7><<<(int)((h->n + 63) / 64), 64, 0, s>>>(d_state, h->params, d_action, d_magnitude, d_noise,
+                                                                      d_setpoint, k_substeps, h->n, d_obs, d_reward, d_done);
+#endif
     NPS_CUDA(cudaGetLastError());
     return 0;
 }

@@ -11,7 +11,7 @@
 namespace nps {
 
 // condenser/physics.py:1824-1853
-NPS_HD double cond_sat_temp(double p_mpa) {
+NPS_HD_SHARED double cond_sat_temp(double p_mpa) {
     if (p_mpa <= 0.001) return 10.0;
     double p_bar = np_clip(p_mpa * 10.0, 0.01, 100.0);
     double t = 1730.63 / (8.07131 - log10(p_bar)) - 233.426;

@@ -431,6 +431,7 @@ NPS_HD void feedwater_update(FeedwaterState& fw, WaterChemState& wc, const Plant
     NPS_UNIT_LOOP
     for (int k = 0; k < 4; ++k) {
         FWPumpState& u = fw.pump[k];
+        NPS_PREFETCH_SELF(u);
         if (k < 3) NPS_PREFETCH_FAR(fw.pump[k + 1]);
         else if (prefetch_next) NPS_PREFETCH_FAR(*prefetch_next);   // what runs after the feedwater system
         if ((int)u.status == PUMP_RUNNING && n_prev > 0) {

@@ -14,9 +14,19 @@
 #if defined(__CUDACC__)
 #define NPS_HD __host__ __device__ __forceinline__
 #define NPS_HD_NOINLINE __host__ __device__ __noinline__
+// Helpers called from many sites (saturation temperatures: 24 call sites; water chemistry: 3; oil quality: 2) are
+// compiled ONCE on the device instead of inlined everywhere: the step kernel is ~0.5 MB of straight-line SASS and
+// 15 % of its stall samples were instruction-fetch misses; sharing these bodies measured +3.5 % (profiles/
+// r01_tuning_variants.txt).  NPS_INLINE_HELPERS restores full inlining.
+#if !defined(NPS_INLINE_HELPERS)
+#define NPS_HD_SHARED __host__ __device__ __noinline__
+#else
+#define NPS_HD_SHARED __host__ __device__ __forceinline__
+#endif
 #else
 #define NPS_HD inline
 #define NPS_HD_NOINLINE
+#define NPS_HD_SHARED inline
 #endif
 
 // Loops over repeated plant units (4 pumps, 3 SGs, 14 stages, 4 bearings) stay rolled on the device unless
@@ -49,7 +59,18 @@
 #define NPS_PF2(a, off) do { if (LEVEL == 1) NPS_PF2_L1(a, off); else if (LEVEL == 2) NPS_PF2_L2(a, off); } while (0)
 #define NPS_PREFETCH(obj) nps_prefetch_live<NPS_PF_NEAR_LEVEL>(obj)
 #define NPS_PREFETCH_FAR(obj) nps_prefetch_live<NPS_PF_FAR_LEVEL>(obj)
+// NPS_PREFETCH_SELF: at the start of a unit's own processing.  Level 1/2 = prefetch.L1/.L2; level 3 = "burst touch":
+// real loads of every live-in field issued back to back (one exposed DRAM latency instead of one per field).
+#ifndef NPS_PF_SELF_LEVEL
+#define NPS_PF_SELF_LEVEL 0
+#endif
+#if NPS_PF_SELF_LEVEL == 3
+#define NPS_PREFETCH_SELF(obj) do { double t__ = nps_touch_live(obj), s__; asm volatile("mov.f64 %0, %1;" : "=d"(s__) : "d"(t__)); } while (0)
 #else
+#define NPS_PREFETCH_SELF(obj) nps_prefetch_live<NPS_PF_SELF_LEVEL>(obj)
+#endif
+#else
+#define NPS_PREFETCH_SELF(obj) ((void)0)
 #define NPS_PF2(a, off) ((void)0)
 #define NPS_PREFETCH(obj) ((void)0)
 #define NPS_PREFETCH_FAR(obj) ((void)0)
@@ -72,14 +93,21 @@ NPS_HD double np_clip(double x, double lo, double hi) {
 // x*x in ~0.08 % of cases, so the host build uses -fno-builtin-pow to keep the libm call).
 // On the device the exponents whose result is exactly computable go through correctly-rounded arithmetic
 // instead of libdevice's general pow (<= 2 ulp, ~230 SASS instructions per call and 35 % of the step kernel's
-// executed instructions in the round-1 profile): x*x and sqrt(x) ARE the correctly rounded pow(x, 2) and
-// pow(x, 0.5), i.e. at least as close to glibc's (<= 0.52 ulp) as libdevice pow is.  The exponent is a literal at
+// executed instructions in the round-1 profile; 280 calls per plant-step, 125 of them with y == 2): x*x and sqrt(x)
+// ARE the correctly rounded pow(x, 2) and pow(x, 0.5), i.e. at least as close to glibc's (<= 0.52 ulp) as libdevice
+// pow is.  The exponent is a literal at
 // most call sites, so the test folds away; the wear exponents are batch-uniform parameters (uniform branch).
 NPS_HD double py_pow(double x, double y) {
 #if defined(__CUDA_ARCH__) && !defined(NPS_GENERIC_POW)
     if (y == 2.0) return x * x;
     if (y == 1.0) return x;
-    if (y == 0.5 && x > 0.0 && x < 1.7e308) return sqrt(x);
+    if (x > 0.0 && x < 1.7e308) {
+        if (y == 0.5) return sqrt(x);
+        // two correctly-rounded operations: <= 1 ulp from the exact power, inside libdevice pow's own 2-ulp bound
+        if (y == 3.0) return x * x * x;
+        if (y == 1.5) return x * sqrt(x);
+        if (y == 0.25) return sqrt(sqrt(x));
+    }
 #endif
     return pow(x, y);
 }

@@ -19,7 +19,7 @@ struct LubComponent {
 struct LubLimits { double contamination_limit, acidity_limit, moisture_limit, viscosity_change_limit; };
 
 // update_oil_quality: lubrication_base.py:186-352
-NPS_HD void lub_update_oil_quality(LubCore& L, int n_comp, const LubLimits& lim, double operating_temperature,
+NPS_HD_SHARED void lub_update_oil_quality(LubCore& L, int n_comp, const LubLimits& lim, double operating_temperature,
                                    double contamination_input, double moisture_input, double dt) {
     double temp_change = (operating_temperature - L.oil_temperature) / 0.5 * dt;
     double max_temp_change = 10.0 * dt;

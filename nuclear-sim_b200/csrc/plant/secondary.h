@@ -19,7 +19,7 @@ namespace nps {
 struct PrimaryConditions { double inlet_temp[3], outlet_temp[3], flow[3], thermal_power[3]; };
 
 // _saturation_temperature (Clausius-Clapeyron variant): systems/secondary/__init__.py:1455-1492
-NPS_HD double secondary_sat_temp(double p_mpa) {
+NPS_HD_SHARED double secondary_sat_temp(double p_mpa) {
     if (p_mpa <= 0.001) return 10.0;
     const double p_ref = 0.101325, t_ref = 100.0, h_fg = 2257.0, r_v = 0.4615;
     double t_ref_k = t_ref + 273.15;
@@ -98,6 +98,9 @@ NPS_HD void secondary_update(PlantState& st, const PlantParams& p, const Primary
             lp_quality = py_max(0.0, py_min(1.0, lp_quality));
         }
     }
+    NPS_PREFETCH_SELF(st.cond);
+    NPS_PREFETCH_SELF(st.cond.ejector[0]);
+    NPS_PREFETCH_SELF(st.cond.ejector[1]);
     NPS_PREFETCH_FAR(st.ph);       // consumers after the condenser: shared water chemistry (2nd update) and pH control
     NPS_PREFETCH_FAR(st.wc_main);
     CondenserResult cr;
@@ -109,6 +112,7 @@ NPS_HD void secondary_update(PlantState& st, const PlantParams& p, const Primary
 
     // chemistry: :634-665
     const MakeupWater mk = {7.2, 100.0, 300.0, 30.0, 8.0};
+    NPS_PREFETCH_SELF(st.ph);
     wc_update(st.wc_main, true, mk, 0.02, dt);
     ph_control_update(st.ph, st.wc_main.ph, dt, in.z_ph, in.u_ph);
     wc_queue_effects(st.wc_main, st.ph.ph_setpoint, st.ph.ammonia_dose_rate, st.ph.morpholine_dose_rate);

@@ -13,7 +13,7 @@ namespace nps {
 #define NPS_PI 3.141592653589793
 
 // Thermodynamic correlations: steam_generator.py:854-941
-NPS_HD double sg_sat_temp(double p_mpa) {
+NPS_HD_SHARED double sg_sat_temp(double p_mpa) {
     if (p_mpa <= 0.001) return 10.0;
     double p_bar = p_mpa * 10.0;
     double t;
@@ -316,6 +316,7 @@ NPS_HD void sg_system_update(SGSystemState& S, const PlantParams& p, const doubl
     }
     NPS_UNIT_LOOP
     for (int i = 0; i < 3; ++i) {
+        NPS_PREFETCH_SELF(S.sg[i]);
         if (i < 2) NPS_PREFETCH_FAR(S.sg[i + 1]);
         else if (prefetch_next) {   // the turbine's lubrication pre-step and bearing set come next
             NPS_PREFETCH_FAR(*prefetch_next);

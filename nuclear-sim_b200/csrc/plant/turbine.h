@@ -14,32 +14,64 @@
 namespace nps {
 
 // Antoine saturation temperature shared by stage_system.py:458-466 and enhanced_physics.py:1295-1303
-NPS_HD double turb_sat_temp(double p_mpa) {
+NPS_HD_SHARED double turb_sat_temp(double p_mpa) {
     if (p_mpa <= 0.001) return 10.0;
     double p_bar = np_clip(p_mpa * 10.0, 0.01, 100.0);
     double t = 1730.63 / (8.07131 - log10(p_bar)) - 233.426;
     return np_clip(t, 10.0, 374.0);
 }
-NPS_HD double turb_h_g(double p_mpa) {   // stage_system.py:468-473
+NPS_HD_SHARED double turb_h_g(double p_mpa) {   // stage_system.py:468-473
     double temp = turb_sat_temp(p_mpa);
     double h_f = 4.18 * temp;
     double h_fg = 2257.0 * py_pow(1.0 - temp / 374.0, 0.38);
     return h_f + h_fg;
 }
+// Saturation properties are pure functions of pressure, and the 14-stage chain asks for them at the same pressures
+// again and again (a stage's outlet pressure is the next stage's inlet pressure; enthalpy, entropy and
+// enthalpy->temperature all start from T_sat(p)): 117 log10 and 55 pow(., 0.38) per plant-step in the reference.  A
+// two-entry memo keyed on the EXACT pressure bits returns the value the function would recompute, so results are
+// unchanged bit for bit; it only removes the repeats.
+struct TurbSatMemo {
+    double p[2], sat[2], hg[2];
+    int has_hg[2];
+    int next;
+};
+NPS_HD void turb_memo_init(TurbSatMemo& m) { m.p[0] = m.p[1] = -1.0; m.has_hg[0] = m.has_hg[1] = 0; m.next = 0; }
+NPS_HD int turb_memo_slot(TurbSatMemo& m, double p_mpa) {
+    if (m.p[0] == p_mpa) return 0;
+    if (m.p[1] == p_mpa) return 1;
+    const int s = m.next;
+    m.next = 1 - s;
+    m.p[s] = p_mpa; m.sat[s] = turb_sat_temp(p_mpa); m.has_hg[s] = 0;
+    return s;
+}
+NPS_HD double turb_sat_temp_m(TurbSatMemo& m, double p_mpa) { return m.sat[turb_memo_slot(m, p_mpa)]; }
+NPS_HD double turb_h_g_m(TurbSatMemo& m, double p_mpa) {   // == turb_h_g(p_mpa)
+    const int s = turb_memo_slot(m, p_mpa);
+    if (!m.has_hg[s]) {
+        double temp = m.sat[s];
+        double h_f = 4.18 * temp;
+        double h_fg = 2257.0 * py_pow(1.0 - temp / 374.0, 0.38);
+        m.hg[s] = h_f + h_fg;
+        m.has_hg[s] = 1;
+    }
+    return m.hg[s];
+}
 // TurbineStage._steam_enthalpy: stage_system.py:418-443
-NPS_HD double stage_steam_enthalpy(double t, double p_mpa) {
+NPS_HD double stage_steam_enthalpy(double t, double p_mpa, TurbSatMemo& m) {
     p_mpa = py_max(0.001, py_min(p_mpa, 22.0));
     t = py_max(0.0, py_min(t, 800.0));
-    double sat = turb_sat_temp(p_mpa);
-    if (t <= sat) return turb_h_g(p_mpa);
-    double h_g = turb_h_g(p_mpa);
+    double sat = turb_sat_temp_m(m, p_mpa);
+    if (t <= sat) return turb_h_g_m(m, p_mpa);
+    double h_g = turb_h_g_m(m, p_mpa);
     double superheat = t - sat;
     double cp = (p_mpa > 10.0) ? 2.5 : ((p_mpa > 1.0) ? 2.2 : 2.0);
     return h_g + cp * superheat;
 }
+NPS_HD double stage_steam_enthalpy(double t, double p_mpa) { TurbSatMemo m; turb_memo_init(m); return stage_steam_enthalpy(t, p_mpa, m); }
 // TurbineStage._steam_entropy: stage_system.py:445-456
-NPS_HD double stage_steam_entropy(double t, double p_mpa) {
-    double sat = turb_sat_temp(p_mpa);
+NPS_HD double stage_steam_entropy(double t, double p_mpa, TurbSatMemo& m) {
+    double sat = turb_sat_temp_m(m, p_mpa);
     double s_f = 4.18 * log((sat + 273.15) / 273.15);
     double s_fg = 2257.0 / (sat + 273.15);
     double s_g = s_f + s_fg;
@@ -164,7 +196,7 @@ NPS_HD void turbine_lubrication_prestep(TurbineState& T, const PlantParams& p, d
 
 // TurbineStage.calculate_stage_expansion: stage_system.py:98-292
 NPS_HD void stage_expand(TurbineStageState& s, const PlantParams& p, int k, double inlet_pressure, double inlet_temperature,
-                         double inlet_flow, double outlet_pressure, double extraction_demand) {
+                         double inlet_flow, double outlet_pressure, double extraction_demand, TurbSatMemo& memo) {
     s.inlet_pressure = inlet_pressure;
     s.inlet_temperature = inlet_temperature;
     s.inlet_flow = inlet_flow;
@@ -189,21 +221,22 @@ NPS_HD void stage_expand(TurbineStageState& s, const PlantParams& p, int k, doub
         else if (outlet_pressure > max_allowed) s.outlet_pressure = max_allowed;
         else s.outlet_pressure = outlet_pressure;
     }
-    s.inlet_enthalpy = stage_steam_enthalpy(inlet_temperature, inlet_pressure);
-    s.inlet_entropy = stage_steam_entropy(inlet_temperature, inlet_pressure);
+    s.inlet_enthalpy = stage_steam_enthalpy(inlet_temperature, inlet_pressure, memo);
+    s.inlet_entropy = stage_steam_entropy(inlet_temperature, inlet_pressure, memo);
     if (is_true(p.ts_has_extraction[k]) && extraction_demand > 0) {
         s.extraction_flow = np_clip(extraction_demand, p.ts_min_extraction_flow[k],
                                     py_min(p.ts_max_extraction_flow[k], inlet_flow * 0.3));
         s.extraction_pressure = inlet_pressure * 0.7 + outlet_pressure * (1 - 0.7);
-        double et = turb_sat_temp(s.extraction_pressure);
-        s.extraction_enthalpy = stage_steam_enthalpy(et, s.extraction_pressure);
+        TurbSatMemo em; turb_memo_init(em);   // extraction pressure: its own lookups, leaves the chain's entries alone
+        double et = turb_sat_temp_m(em, s.extraction_pressure);
+        s.extraction_enthalpy = stage_steam_enthalpy(et, s.extraction_pressure, em);
     } else {
         s.extraction_flow = 0.0;
     }
     s.outlet_flow = s.inlet_flow - s.extraction_flow;
     double pr = s.outlet_pressure / inlet_pressure;
     double t_isen = (inlet_temperature + 273.15) * py_pow(pr, 0.25) - 273.15;
-    double h_isen = stage_steam_enthalpy(t_isen, s.outlet_pressure);
+    double h_isen = stage_steam_enthalpy(t_isen, s.outlet_pressure, memo);
     const double quality_factor = 1.0;   // steam_quality hard-coded 0.99 at stage_system.py:217
     double total_eff = (s.actual_efficiency * s.blade_condition_factor * s.fouling_factor * s.blade_wear_factor * quality_factor);
     double isen_drop = s.inlet_enthalpy - h_isen;
@@ -217,8 +250,8 @@ NPS_HD void stage_expand(TurbineStageState& s, const PlantParams& p, int k, doub
     s.enthalpy_drop = actual_drop;
     s.outlet_enthalpy = s.inlet_enthalpy - actual_drop;
     {   // _enthalpy_to_temperature with the REQUESTED outlet pressure (stage_system.py:256)
-        double sat = turb_sat_temp(outlet_pressure);
-        double h_g = turb_h_g(outlet_pressure);
+        double sat = turb_sat_temp_m(memo, outlet_pressure);
+        double h_g = turb_h_g_m(memo, outlet_pressure);
         s.outlet_temperature = (s.outlet_enthalpy <= h_g) ? sat : sat + (s.outlet_enthalpy - h_g) / 2.1;
     }
     double main_power = s.outlet_flow * actual_drop / 1000.0;
@@ -271,6 +304,8 @@ NPS_HD void turbine_update(TurbineState& T, const PlantParams& p, const SGSystem
                            double condenser_pressure, double dt, TurbineResult& out,
                            const CondenserState* prefetch_next = nullptr) {
     NPS_PREFETCH(T.stage[0]);
+    NPS_PREFETCH_SELF(T);
+    for (int b = 0; b < 4; ++b) NPS_PREFETCH_SELF(T.bearing[b]);
     turbine_lubrication_prestep(T, p, dt);
 
     const double steam_pressure = S.average_steam_pressure, steam_temperature_in = S.average_steam_temperature;
@@ -293,6 +328,7 @@ NPS_HD void turbine_update(TurbineState& T, const PlantParams& p, const SGSystem
     {
         double cur_p = steam_pressure, cur_t = steam_temperature_in, cur_f = steam_flow;
         const double final_pressure = 0.007;
+        TurbSatMemo memo; turb_memo_init(memo);
         NPS_UNIT_LOOP
         for (int k = 0; k < 14; ++k) {
             if (k < 13) NPS_PREFETCH(T.stage[k + 1]);
@@ -307,7 +343,7 @@ NPS_HD void turbine_update(TurbineState& T, const PlantParams& p, const SGSystem
             if (k == 2) ed = 25.0 * load_demand; else if (k == 3) ed = 30.0 * load_demand;
             else if (k == 4) ed = 20.0 * load_demand; else if (k == 8) ed = 15.0 * load_demand;
             else if (k == 9) ed = 10.0 * load_demand;
-            stage_expand(T.stage[k], p, k, cur_p, cur_t, cur_f, outp, ed);
+            stage_expand(T.stage[k], p, k, cur_p, cur_t, cur_f, outp, ed, memo);
             total_power += T.stage[k].power_output;
             total_extraction += T.stage[k].extraction_flow;
             if (k < 8) hp_power += T.stage[k].power_output; else lp_power += T.stage[k].power_output;
@@ -337,8 +373,8 @@ NPS_HD void turbine_update(TurbineState& T, const PlantParams& p, const SGSystem
         T.ss_total_extraction_flow = total_extraction;
         T.ss_system_efficiency = py_min(1.0, T.ss_system_efficiency * psf);
         if (steam_flow > 0) {
-            double h_in = stage_steam_enthalpy(steam_temperature_in, steam_pressure);
-            double h_out = stage_steam_enthalpy(cur_t, cur_p);
+            double h_out = stage_steam_enthalpy(cur_t, cur_p, memo);     // last outlet pressure: still in the memo
+            double h_in = stage_steam_enthalpy(steam_temperature_in, steam_pressure, memo);
             T.ss_overall_efficiency = (h_in - h_out) / h_in;
         } else {
             T.ss_overall_efficiency = 0.0;

@@ -11,7 +11,7 @@ namespace nps {
 struct MakeupWater { double ph, hardness, tds, chloride, dissolved_oxygen; };
 
 // _calculate_composite_parameters: water_chemistry.py:277-320
-NPS_HD void wc_composite(WaterChemState& w) {
+NPS_HD_SHARED void wc_composite(WaterChemState& w) {
     double iron_effect = w.iron_concentration * 0.5;
     double chloride_effect = w.chloride / 100.0;
     double ph_effect = fabs(w.ph - 7.0) * 0.2;
@@ -37,7 +37,7 @@ NPS_HD void wc_composite(WaterChemState& w) {
 }
 
 // update_chemistry: water_chemistry.py:322-389.  `has_makeup` mirrors `if makeup_water_quality:`.
-NPS_HD void wc_update(WaterChemState& w, bool has_makeup, const MakeupWater& mk, double blowdown, double dt) {
+NPS_HD_SHARED void wc_update(WaterChemState& w, bool has_makeup, const MakeupWater& mk, double blowdown, double dt) {
     double dt_hours;
     if (dt > 100) dt_hours = dt / 3600.0;
     else if (dt > 1) dt_hours = dt / 60.0;

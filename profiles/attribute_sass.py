@@ -3,7 +3,7 @@
 
     cuobjdump -xelf all libnps_b200.so ; nvdisasm -gi -c nps_capi.sm_100a.cubin > dis.txt
     ncu -i prof.ncu-rep --page source --csv > sass.csv
-    python profiles/attribute_sass.py dis.txt sass.csv [n_warp_steps]
+    python profiles/attribute_sass.py dis.txt sass.csv [n_warp_steps] [kernel symbol substring]
 
 The ncu source page only carries metrics for the kernel's own .cu file; everything on the step path is
 inlined from csrc/plant/*.h, so the join goes through nvdisasm's line table (same cubin, same order).
@@ -80,7 +80,7 @@ def enclosing(tbl, line):
 def main():
     dis, sass = sys.argv[1], sys.argv[2]
     nws = float(sys.argv[3]) if len(sys.argv) > 3 else 16384.0
-    ins = parse_dis(dis)
+    ins = parse_dis(dis, sys.argv[4] if len(sys.argv) > 4 else "nps_step_kernel")
     rows = list(csv.reader(open(sass)))
     hdr = rows[1]
     i_exec, i_samp = hdr.index("Instructions Executed"), hdr.index("# Samples")
