@@ -35,7 +35,7 @@ constexpr int kNParams = (int)(sizeof(PlantParams) / sizeof(double));
 static_assert(kNState == NPS_GEN_N_STATE, "state.h and fields_gen.inc disagree; rerun the build");
 static_assert(kNParams == NPS_GEN_N_PARAMS, "state.h and fields_gen.inc disagree; rerun the build");
 
-struct Threshold { int field; int cmp; double value; double cooldown; };
+struct Threshold { int field; int cmp; double value; double cooldown; int row; int pad; };
 
 struct nps_handle {
     int64_t n = 0;
@@ -45,7 +45,7 @@ struct nps_handle {
     int8_t* d_action = nullptr; double* d_mag = nullptr; double* d_noise = nullptr; double* d_setpoint = nullptr;
     double* d_obs = nullptr; double* d_reward = nullptr; uint8_t* d_done = nullptr;
     int staged_k = 0;
-    Threshold* d_thresholds = nullptr; int n_thresholds = 0;
+    Threshold* d_thresholds = nullptr; int n_thresholds = 0; int n_live_thresholds = 0;
     int32_t* d_logged = nullptr; int n_logged = 0;
     int32_t* d_gather_fields = nullptr; double* d_gather_out = nullptr; int gather_cap = 0;
 };
@@ -149,45 +149,55 @@ __device__ __forceinline__ double threshold_derived(const double* __restrict__ s
     return NAN;
 }
 
-__global__ void nps_threshold_kernel(const double* __restrict__ slab, const Threshold* __restrict__ thr, int n_thr,
-                                     double now_minutes_field_unused, int time_field, double* __restrict__ last_fired,
-                                     uint32_t* __restrict__ flags, uint32_t* __restrict__ any_warp, int64_t n) {
+constexpr int kThrRowsPerThread = 8;
+__global__ void __launch_bounds__(128)
+nps_threshold_kernel(const double* __restrict__ slab, const Threshold* __restrict__ live, int n_live, int time_field,
+                     double* __restrict__ last_fired, uint32_t* __restrict__ flags, uint32_t* __restrict__ any_warp, int64_t n) {
+    // thread = (plant, group of 8 LIVE rows).  Inert rows never reach the device loop; the 8 cooldown stamps and the 8
+    // values of a group are independent loads issued back to back, so the kernel streams instead of chasing 2 x 90
+    // dependent loads per plant (that version ran at 11 % of the HBM roofline, this one is measured in profiles/).
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = p < n;
+    const int r0 = blockIdx.y * kThrRowsPerThread;
     bool any = false;
-    if (live) {
+    if (p < n) {
         const double now = slab[(int64_t)time_field * n + p];
-        uint32_t word = 0;
-        for (int t = 0; t < n_thr; ++t) {
-            const Threshold th = thr[t];
-            bool fire = false;
-            if (th.field != -1) {
-                const double last = last_fired[(int64_t)t * n + p];
-                // _is_threshold_in_cooldown: state_manager.py:1267-1305
-                const bool cooling = (now - last) < th.cooldown;
-                if (!cooling) {
-                    const double v = (th.field >= 0) ? slab[(int64_t)th.field * n + p] : threshold_derived(slab, n, p, th.field);
-                    switch (th.cmp) {   // _check_threshold_condition: state_manager.py:1412-1442
-                        case 0: fire = v > th.value; break;
-                        case 1: fire = v < th.value; break;
-                        case 2: fire = v >= th.value; break;
-                        case 3: fire = v <= th.value; break;
-                        case 4: fire = fabs(v - th.value) < 1e-3; break;
-                        case 5: fire = fabs(v - th.value) >= 1e-3; break;
-                        default: fire = false; break;
-                    }
-                    if (fire) last_fired[(int64_t)t * n + p] = now;
-                }
+        double last[kThrRowsPerThread], val[kThrRowsPerThread];
+#pragma unroll
+        for (int j = 0; j < kThrRowsPerThread; ++j) {
+            const int r = r0 + j;
+            if (r < n_live) {
+                const Threshold th = live[r];
+                last[j] = last_fired[(int64_t)th.row * n + p];
+                val[j] = (th.field >= 0) ? slab[(int64_t)th.field * n + p] : threshold_derived(slab, n, p, th.field);
             }
-            if (fire) { word |= (1u << (t & 31)); any = true; }
-            if ((t & 31) == 31 || t == n_thr - 1) { flags[(int64_t)(t >> 5) * n + p] = word; word = 0; }
+        }
+#pragma unroll
+        for (int j = 0; j < kThrRowsPerThread; ++j) {
+            const int r = r0 + j;
+            if (r >= n_live) break;
+            const Threshold th = live[r];
+            // _is_threshold_in_cooldown: state_manager.py:1267-1305 (checked before the value is looked at)
+            if ((now - last[j]) < th.cooldown) continue;
+            const double v = val[j];
+            bool fire;
+            switch (th.cmp) {   // _check_threshold_condition: state_manager.py:1412-1442
+                case 0: fire = v > th.value; break;
+                case 1: fire = v < th.value; break;
+                case 2: fire = v >= th.value; break;
+                case 3: fire = v <= th.value; break;
+                case 4: fire = fabs(v - th.value) < 1e-3; break;
+                case 5: fire = fabs(v - th.value) >= 1e-3; break;
+                default: fire = false; break;
+            }
+            if (fire) {
+                last_fired[(int64_t)th.row * n + p] = now;   // _record_threshold_violation_time
+                atomicOr(&flags[(int64_t)(th.row >> 5) * n + p], 1u << (th.row & 31));
+                any = true;
+            }
         }
     }
     const unsigned ballot = __ballot_sync(0xffffffffu, any);
-    if ((threadIdx.x & 31) == 0 && any_warp) {
-        const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-        any_warp[w] = ballot;
-    }
+    if ((threadIdx.x & 31) == 0 && ballot && any_warp) atomicOr(&any_warp[p >> 5], ballot);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -365,14 +375,17 @@ int nps_set_thresholds(nps_handle* h, const int32_t* field, const int32_t* compa
     NPS_CUDA(cudaSetDevice(h->device));
     cudaFree(h->d_thresholds); h->d_thresholds = nullptr; h->n_thresholds = 0;
     if (n_thresholds == 0) return 0;
-    std::vector<Threshold> t(n_thresholds);
+    std::vector<Threshold> t;      // live rows only (field != -1), each remembering its row index in the caller's table
     for (int i = 0; i < n_thresholds; ++i) {
         if (field[i] >= kNState) return fail("nps_set_thresholds: field index out of range");
-        t[i] = Threshold{field[i], comparator[i], value[i], cooldown_minutes[i]};
+        if (field[i] != -1) t.push_back(Threshold{field[i], comparator[i], value[i], cooldown_minutes[i], i, 0});
     }
-    NPS_CUDA(cudaMalloc(&h->d_thresholds, sizeof(Threshold) * n_thresholds));
-    NPS_CUDA(cudaMemcpy(h->d_thresholds, t.data(), sizeof(Threshold) * n_thresholds, cudaMemcpyHostToDevice));
+    if (!t.empty()) {
+        NPS_CUDA(cudaMalloc(&h->d_thresholds, sizeof(Threshold) * t.size()));
+        NPS_CUDA(cudaMemcpy(h->d_thresholds, t.data(), sizeof(Threshold) * t.size(), cudaMemcpyHostToDevice));
+    }
     h->n_thresholds = n_thresholds;
+    h->n_live_thresholds = (int)t.size();
     return 0;
 }
 
@@ -380,11 +393,15 @@ int nps_check_thresholds(nps_handle* h, const double* d_state, double* d_last_fi
                          uint32_t* d_any_warp, void* cuda_stream) {
     if (!h || !d_state || !d_last_fired || !d_flags) return fail("nps_check_thresholds: null argument");
     if (h->n_thresholds == 0) return fail("nps_check_thresholds: no thresholds set");
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    const int n_words = (h->n_thresholds + 31) / 32;
+    NPS_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(uint32_t) * (size_t)n_words * h->n, s));
+    if (d_any_warp) NPS_CUDA(cudaMemsetAsync(d_any_warp, 0, sizeof(uint32_t) * (size_t)((h->n + 31) / 32), s));
+    if (h->n_live_thresholds == 0) return 0;
     const int block = 128;
-    const int grid = (int)((h->n + block - 1) / block);
-    const int time_field = kTimeMinutesField;
-    nps_threshold_kernel<<<grid, block, 0, (cudaStream_t)cuda_stream>>>(d_state, h->d_thresholds, h->n_thresholds, 0.0,
-                                                                       time_field, d_last_fired, d_flags, d_any_warp, h->n);
+    dim3 grid((unsigned)((h->n + block - 1) / block), (unsigned)((h->n_live_thresholds + kThrRowsPerThread - 1) / kThrRowsPerThread));
+    nps_threshold_kernel<<<grid, block, 0, s>>>(d_state, h->d_thresholds, h->n_live_thresholds, kTimeMinutesField, d_last_fired,
+                                               d_flags, d_any_warp, h->n);
     NPS_CUDA(cudaGetLastError());
     return 0;
 }
