@@ -89,6 +89,7 @@ NPS_PRAGMA_UNROLL(NPS_COPY_UNROLL)
             in.z_heat = 0.0; in.z_ph = 0.0; in.u_ph[0] = 1.0; in.u_ph[1] = 1.0; in.u_ph[2] = 1.0;
         }
         in.power_setpoint = setpoint ? setpoint[(int64_t)k * n + p] : NAN;
+        in.emit_outputs = (k == k_substeps - 1);
         plant_step(st, prm, in);
         scrammed |= is_true(st.pri.scram_activated);
     }

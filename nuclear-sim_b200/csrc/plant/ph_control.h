@@ -29,7 +29,8 @@ NPS_HD double np_sum_small(int n, Get get) {
     return 0.0 + res;
 }
 
-NPS_HD void ph_control_update(PHControlState& s, double current_ph, double dt, double z, const double* u) {
+NPS_HD void ph_control_update(PHControlState& s, double current_ph, double dt, double z, const double* u,
+                              bool emit_outputs = true) {
     const double dt_minutes = dt * 60.0;
     s.operating_hours += dt;
     // _apply_sensor_dynamics: :274-291
@@ -104,9 +105,11 @@ NPS_HD void ph_control_update(PHControlState& s, double current_ph, double dt, d
         if (n < 100) { s.dev_hist[(head + n) % 100] = deviation; n += 1; }
         else { s.dev_hist[head] = deviation; head = (head + 1) % 100; }
         s.dev_count = (double)n; s.dev_head = (double)head;
-        const double* h = s.dev_hist;
-        double sum = np_sum_small(n, [&](int i) { double v = h[(head + i) % 100]; return v * v; });
-        s.control_deviation_rms = sqrt(sum / n);
+        if (emit_outputs) {   // logged only (ph_control_system.py:455); reads the whole 100-sample window
+            const double* h = s.dev_hist;
+            double sum = np_sum_small(n, [&](int i) { double v = h[(head + i) % 100]; return v * v; });
+            s.control_deviation_rms = sqrt(sum / n);
+        }
         bool in_control = deviation <= 0.05;
         if (is_true(s.tic_initialized)) {
             s.tic_sum += in_control ? dt : 0.0;

@@ -24,6 +24,10 @@ struct StepInput {
     double z_ph;       // standard-normal draw for the pH sensor noise (ph_control_system.py:288)
     double u_ph[3];    // uniform draws for pH equipment failures (ph_control_system.py:409,414,420)
     double power_setpoint;  // heat_source.set_power_setpoint(%) applied before the step; NaN = unchanged
+    // false on the non-final substeps of a fused launch: report-only quantities that nothing reads back (the pH
+    // controller's 100-sample deviation RMS, the stage inlet entropy) are pure functions of the state at the moment
+    // they are observed, and nobody observes the state between fused substeps, so they are evaluated once, at the end.
+    bool emit_outputs = true;
 };
 
 // _apply_control_actions: systems/primary/__init__.py:289-359 with the action routing of

@@ -86,7 +86,7 @@ NPS_HD void secondary_update(PlantState& st, const PlantParams& p, const Primary
 
     // STEP 5 turbine: :565-570
     TurbineResult tr;
-    turbine_update(st.turb, p, st.sgs, S.load_demand, 0.007, dt / 60.0, tr, &st.cond);
+    turbine_update(st.turb, p, st.sgs, S.load_demand, 0.007, dt / 60.0, tr, &st.cond, in.emit_outputs);
 
     // LP-6 exhaust quality: :591-607
     double lp_quality = 0.90;
@@ -114,7 +114,7 @@ NPS_HD void secondary_update(PlantState& st, const PlantParams& p, const Primary
     const MakeupWater mk = {7.2, 100.0, 300.0, 30.0, 8.0};
     NPS_PREFETCH_SELF(st.ph);
     wc_update(st.wc_main, true, mk, 0.02, dt);
-    ph_control_update(st.ph, st.wc_main.ph, dt, in.z_ph, in.u_ph);
+    ph_control_update(st.ph, st.wc_main.ph, dt, in.z_ph, in.u_ph, in.emit_outputs);
     wc_queue_effects(st.wc_main, st.ph.ph_setpoint, st.ph.ammonia_dose_rate, st.ph.morpholine_dose_rate);
 
     S.total_steam_flow = total_steam_flow;

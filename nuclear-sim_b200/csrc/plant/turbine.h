@@ -196,7 +196,8 @@ NPS_HD void turbine_lubrication_prestep(TurbineState& T, const PlantParams& p, d
 
 // TurbineStage.calculate_stage_expansion: stage_system.py:98-292
 NPS_HD void stage_expand(TurbineStageState& s, const PlantParams& p, int k, double inlet_pressure, double inlet_temperature,
-                         double inlet_flow, double outlet_pressure, double extraction_demand, TurbSatMemo& memo) {
+                         double inlet_flow, double outlet_pressure, double extraction_demand, TurbSatMemo& memo,
+                         bool emit_outputs = true) {
     s.inlet_pressure = inlet_pressure;
     s.inlet_temperature = inlet_temperature;
     s.inlet_flow = inlet_flow;
@@ -222,7 +223,7 @@ NPS_HD void stage_expand(TurbineStageState& s, const PlantParams& p, int k, doub
         else s.outlet_pressure = outlet_pressure;
     }
     s.inlet_enthalpy = stage_steam_enthalpy(inlet_temperature, inlet_pressure, memo);
-    s.inlet_entropy = stage_steam_entropy(inlet_temperature, inlet_pressure, memo);
+    if (emit_outputs) s.inlet_entropy = stage_steam_entropy(inlet_temperature, inlet_pressure, memo);   // logged only
     if (is_true(p.ts_has_extraction[k]) && extraction_demand > 0) {
         s.extraction_flow = np_clip(extraction_demand, p.ts_min_extraction_flow[k],
                                     py_min(p.ts_max_extraction_flow[k], inlet_flow * 0.3));
@@ -302,7 +303,7 @@ struct TurbineResult {
 // Wrapped EnhancedTurbinePhysics.update_state (dt in hours; load_demand as passed = percent)
 NPS_HD void turbine_update(TurbineState& T, const PlantParams& p, const SGSystemState& S, double load_demand,
                            double condenser_pressure, double dt, TurbineResult& out,
-                           const CondenserState* prefetch_next = nullptr) {
+                           const CondenserState* prefetch_next = nullptr, bool emit_outputs = true) {
     NPS_PREFETCH(T.stage[0]);
     NPS_PREFETCH_SELF(T);
     for (int b = 0; b < 4; ++b) NPS_PREFETCH_SELF(T.bearing[b]);
@@ -343,7 +344,7 @@ NPS_HD void turbine_update(TurbineState& T, const PlantParams& p, const SGSystem
             if (k == 2) ed = 25.0 * load_demand; else if (k == 3) ed = 30.0 * load_demand;
             else if (k == 4) ed = 20.0 * load_demand; else if (k == 8) ed = 15.0 * load_demand;
             else if (k == 9) ed = 10.0 * load_demand;
-            stage_expand(T.stage[k], p, k, cur_p, cur_t, cur_f, outp, ed, memo);
+            stage_expand(T.stage[k], p, k, cur_p, cur_t, cur_f, outp, ed, memo, emit_outputs);
             total_power += T.stage[k].power_output;
             total_extraction += T.stage[k].extraction_flow;
             if (k < 8) hp_power += T.stage[k].power_output; else lp_power += T.stage[k].power_output;
