@@ -12,8 +12,9 @@ ranks with no data-path collective (weak scaling); an NCCL all-gather of traject
 after the timed region.
 
 value  : plant-steps/s with the per-step inputs already resident in HBM (CUDA events, max over ranks)
-e2e    : the same metric through the host-buffer C-ABI call (nps_step_host): pinned host inputs are
-         copied in and observation/reward/done copied out inside the timed region, every step
+e2e    : the same metric through the host-buffer C-ABI call (nps_step_host_async, two launches in flight): pinned
+         host inputs are copied in and observation/reward/done copied out and read on the host inside the timed
+         region, every step
 roofline / cpu_baseline: see DESIGN.md §Measurement.
 """
 from __future__ import annotations
@@ -236,9 +237,9 @@ def main():
         acts_h[i] = torch.from_numpy(a); mags_h[i] = torch.from_numpy(m)
         noise_h[i] = torch.from_numpy(sc.noise_inputs(pid, i * ksub, ksub))
     acts_d, mags_d, noise_d = acts_h.to(dev), mags_h.to(dev), noise_h.to(dev)
-    obs_h = torch.empty((22, n), dtype=torch.float64).pin_memory()
-    rew_h = torch.empty(n, dtype=torch.float64).pin_memory()
-    done_h = torch.empty(n, dtype=torch.uint8).pin_memory()
+    obs_h = [torch.empty((22, n), dtype=torch.float64).pin_memory() for _ in range(2)]
+    rew_h = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(2)]
+    done_h = [torch.empty(n, dtype=torch.uint8).pin_memory() for _ in range(2)]
 
     def barrier():
         if world > 1:
@@ -271,14 +272,25 @@ def main():
     value = world * n * ksub * K / (t_ms * 1e-3)
 
     # ------------------------------------------------------------------ end-to-end arm (host buffers through the C ABI)
+    # Every step: pinned host inputs -> device, 32 substeps, observation/reward/done -> pinned host, and the host reads
+    # the step's reward.  nps_step_host_async keeps two launches in flight so the copies of step i+1 overlap the kernel
+    # of step i; the host consumes step i's result while step i+1 runs.
     sim.reset()
     for i in range(W):
-        sim.step_host(acts_h[i], mags_h[i], noise_h[i], None, ksub, obs_h, rew_h, done_h)
+        sim.step_host(acts_h[i], mags_h[i], noise_h[i], None, ksub, obs_h[0], rew_h[0], done_h[0])
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reward_sum, tickets = 0.0, []
     e0.record()
     for i in range(K):
-        sim.step_host(acts_h[W + i], mags_h[W + i], noise_h[W + i], None, ksub, obs_h, rew_h, done_h)
+        b = i & 1
+        if i >= 2:
+            sim.wait(tickets[i - 2])
+            reward_sum += float(rew_h[b].mean())
+        tickets.append(sim.step_host_async(acts_h[W + i], mags_h[W + i], noise_h[W + i], None, ksub, obs_h[b], rew_h[b], done_h[b]))
+    for i in range(max(0, K - 2), K):
+        sim.wait(tickets[i])
+        reward_sum += float(rew_h[i & 1].mean())
     e1.record()
     barrier()
     te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -287,7 +299,7 @@ def main():
     e2e_value = world * n * ksub * K / (float(te.item()) * 1e-3)
     h2d = ksub * n * (1 + 8 + 5 * 8)
     d2h = n * (22 * 8 + 8 + 1)
-    loss_check = float(rew_h.mean())
+    loss_check = reward_sum / K
 
     # ------------------------------------------------------------------ trajectory summaries: the only collective
     summary = torch.stack([sim.state.power_level, sim.state.electrical_power_output, sim.state.fuel_temperature,

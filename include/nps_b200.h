@@ -69,6 +69,16 @@ int nps_step_host(nps_handle* h, double* d_state, const int8_t* h_action, const 
                   const double* h_noise, const double* h_setpoint, int k_substeps, double* h_obs, double* h_reward,
                   uint8_t* h_done, void* cuda_stream);
 
+/* Pipelined form of nps_step_host for a driver that steps in a loop: returns at once with a ticket (0 or 1); the
+ * host->device copies run on an internal copy stream into one of two staging sets, so the inputs of launch i+1 travel
+ * while launch i computes, and the results of launch i travel while launch i+1 computes.  Host buffers must be pinned
+ * and must stay untouched until nps_wait(ticket) returns (inputs) / are valid after it returns (outputs).  At most two
+ * launches may be outstanding: wait for ticket t before issuing the call that will reuse it. */
+int nps_step_host_async(nps_handle* h, double* d_state, const int8_t* h_action, const double* h_magnitude,
+                        const double* h_noise, const double* h_setpoint, int k_substeps, double* h_obs, double* h_reward,
+                        uint8_t* h_done, void* cuda_stream);
+int nps_wait(nps_handle* h, int ticket);
+
 /* get_observation()/calculate_reward() of the current state without stepping */
 int nps_observe(nps_handle* h, const double* d_state, double* d_obs, double* d_reward, void* cuda_stream);
 

@@ -151,6 +151,21 @@ class BatchedNuclearPlantSimulator:
                                          ctypes.c_void_p(stream)))
         self.n_launches += 1
 
+    def step_host_async(self, h_actions, h_magnitudes, h_noise, h_setpoint, K, h_obs, h_reward, h_done) -> int:
+        """Pipelined step_host (nps_step_host_async): returns a ticket; wait(ticket) makes the outputs valid."""
+        def hp(t):
+            return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        t = self.L.nps_step_host_async(self._h, _ptr(self.slab), hp(h_actions), hp(h_magnitudes), hp(h_noise), hp(h_setpoint),
+                                       int(K), hp(h_obs), hp(h_reward), hp(h_done), ctypes.c_void_p(stream))
+        if t < 0:
+            _clib.check(t)
+        self.n_launches += 1
+        return int(t)
+
+    def wait(self, ticket: int) -> None:
+        _clib.check(self.L.nps_wait(self._h, int(ticket)))
+
     def get_observation(self) -> torch.Tensor:
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _clib.check(self.L.nps_observe(self._h, _ptr(self.slab), _ptr(self._obs), _ptr(self._reward), ctypes.c_void_p(stream)))

@@ -48,6 +48,14 @@ struct nps_handle {
     Threshold* d_thresholds = nullptr; int n_thresholds = 0; int n_live_thresholds = 0;
     int32_t* d_logged = nullptr; int n_logged = 0;
     int32_t* d_gather_fields = nullptr; double* d_gather_out = nullptr; int gather_cap = 0;
+    // nps_step_host_async: two staging sets so the host->device copy of launch i+1 overlaps the kernel of launch i
+    struct Pipe {
+        int8_t* d_action = nullptr; double* d_mag = nullptr; double* d_noise = nullptr; double* d_setpoint = nullptr;
+        double* d_obs = nullptr; double* d_reward = nullptr; uint8_t* d_done = nullptr;
+        cudaEvent_t in_done = nullptr, kernel_done = nullptr, out_done = nullptr;
+    } pipe[2];
+    cudaStream_t copy_stream = nullptr, out_stream = nullptr;   // host->device and device->host on separate streams
+    int pipe_k = 0; int64_t pipe_count = 0;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -288,6 +296,15 @@ void nps_destroy(nps_handle* h) {
     cudaFree(h->d_setpoint); cudaFree(h->d_action); cudaFree(h->d_mag); cudaFree(h->d_noise);
     cudaFree(h->d_obs); cudaFree(h->d_reward); cudaFree(h->d_done); cudaFree(h->d_thresholds);
     cudaFree(h->d_logged); cudaFree(h->d_gather_fields); cudaFree(h->d_gather_out);
+    for (auto& q : h->pipe) {
+        cudaFree(q.d_action); cudaFree(q.d_mag); cudaFree(q.d_noise); cudaFree(q.d_setpoint);
+        cudaFree(q.d_obs); cudaFree(q.d_reward); cudaFree(q.d_done);
+        if (q.in_done) cudaEventDestroy(q.in_done);
+        if (q.kernel_done) cudaEventDestroy(q.kernel_done);
+        if (q.out_done) cudaEventDestroy(q.out_done);
+    }
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->out_stream) cudaStreamDestroy(h->out_stream);
     delete h;
 }
 
@@ -358,6 +375,67 @@ int nps_step_host(nps_handle* h, double* d_state, const int8_t* h_action, const 
     if (h_reward) NPS_CUDA(cudaMemcpyAsync(h_reward, h->d_reward, (size_t)h->n * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (h_done) NPS_CUDA(cudaMemcpyAsync(h_done, h->d_done, (size_t)h->n, cudaMemcpyDeviceToHost, s));
     NPS_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+static int ensure_pipe(nps_handle* h, int k) {
+    if (h->pipe_k >= k && h->copy_stream) return 0;
+    if (!h->copy_stream) NPS_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    if (!h->out_stream) NPS_CUDA(cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking));
+    for (auto& q : h->pipe) {
+        cudaFree(q.d_action); cudaFree(q.d_mag); cudaFree(q.d_noise); cudaFree(q.d_setpoint);
+        NPS_CUDA(cudaMalloc(&q.d_action, (size_t)k * h->n));
+        NPS_CUDA(cudaMalloc(&q.d_mag, (size_t)k * h->n * sizeof(double)));
+        NPS_CUDA(cudaMalloc(&q.d_noise, (size_t)k * NPS_NOISE_PER_STEP * h->n * sizeof(double)));
+        NPS_CUDA(cudaMalloc(&q.d_setpoint, (size_t)k * h->n * sizeof(double)));
+        if (!q.d_obs) {
+            NPS_CUDA(cudaMalloc(&q.d_obs, (size_t)NPS_OBS_DIM * h->n * sizeof(double)));
+            NPS_CUDA(cudaMalloc(&q.d_reward, (size_t)h->n * sizeof(double)));
+            NPS_CUDA(cudaMalloc(&q.d_done, (size_t)h->n));
+            NPS_CUDA(cudaEventCreateWithFlags(&q.in_done, cudaEventDisableTiming));
+            NPS_CUDA(cudaEventCreateWithFlags(&q.kernel_done, cudaEventDisableTiming));
+            NPS_CUDA(cudaEventCreateWithFlags(&q.out_done, cudaEventDisableTiming));
+        }
+    }
+    h->pipe_k = k;
+    return 0;
+}
+
+int nps_step_host_async(nps_handle* h, double* d_state, const int8_t* h_action, const double* h_magnitude,
+                        const double* h_noise, const double* h_setpoint, int k_substeps, double* h_obs, double* h_reward,
+                        uint8_t* h_done, void* cuda_stream) {
+    if (!h || !d_state) return fail("nps_step_host_async: null argument");
+    if (k_substeps <= 0) return fail("nps_step_host_async: k_substeps must be positive");
+    NPS_CUDA(cudaSetDevice(h->device));
+    if (ensure_pipe(h, k_substeps)) return -1;
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    const int slot = (int)(h->pipe_count++ & 1);
+    nps_handle::Pipe& q = h->pipe[slot];
+    const size_t kn = (size_t)k_substeps * h->n;
+    // the staging set may still be read by the launch issued two calls ago
+    NPS_CUDA(cudaStreamWaitEvent(h->copy_stream, q.kernel_done, 0));
+    if (h_action) NPS_CUDA(cudaMemcpyAsync(q.d_action, h_action, kn, cudaMemcpyHostToDevice, h->copy_stream));
+    if (h_magnitude) NPS_CUDA(cudaMemcpyAsync(q.d_mag, h_magnitude, kn * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
+    if (h_noise) NPS_CUDA(cudaMemcpyAsync(q.d_noise, h_noise, kn * NPS_NOISE_PER_STEP * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
+    if (h_setpoint) NPS_CUDA(cudaMemcpyAsync(q.d_setpoint, h_setpoint, kn * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
+    NPS_CUDA(cudaEventRecord(q.in_done, h->copy_stream));
+    NPS_CUDA(cudaStreamWaitEvent(s, q.in_done, 0));
+    if (nps_step(h, d_state, h_action ? q.d_action : nullptr, h_magnitude ? q.d_mag : nullptr, h_noise ? q.d_noise : nullptr,
+                 h_setpoint ? q.d_setpoint : nullptr, k_substeps, h_obs ? q.d_obs : nullptr, h_reward ? q.d_reward : nullptr,
+                 h_done ? q.d_done : nullptr, cuda_stream)) return -1;
+    NPS_CUDA(cudaEventRecord(q.kernel_done, s));
+    // results go home on their own stream: neither the next launch nor the next input copy queues behind them
+    NPS_CUDA(cudaStreamWaitEvent(h->out_stream, q.kernel_done, 0));
+    if (h_obs) NPS_CUDA(cudaMemcpyAsync(h_obs, q.d_obs, (size_t)NPS_OBS_DIM * h->n * sizeof(double), cudaMemcpyDeviceToHost, h->out_stream));
+    if (h_reward) NPS_CUDA(cudaMemcpyAsync(h_reward, q.d_reward, (size_t)h->n * sizeof(double), cudaMemcpyDeviceToHost, h->out_stream));
+    if (h_done) NPS_CUDA(cudaMemcpyAsync(h_done, q.d_done, (size_t)h->n, cudaMemcpyDeviceToHost, h->out_stream));
+    NPS_CUDA(cudaEventRecord(q.out_done, h->out_stream));
+    return slot;
+}
+
+int nps_wait(nps_handle* h, int ticket) {
+    if (!h || ticket < 0 || ticket > 1 || !h->pipe[ticket].out_done) return fail("nps_wait: bad ticket");
+    NPS_CUDA(cudaEventSynchronize(h->pipe[ticket].out_done));
     return 0;
 }
 

@@ -32,6 +32,11 @@ def parse_dis(path, kernel="nps_step_kernel"):
             continue
         if not on:
             continue
+        lab = re.match(r'\s*(\$\S+):', ln)
+        if lab:      # libdevice subroutine ($kernel$__internal_accurate_pow ...): it carries no line info of its own
+            frames = [("<libdevice>/" + lab.group(1).split('$')[-1], 0)]
+            fresh = True
+            continue
         m = rx_file.search(ln)
         if m:
             if fresh:
