@@ -248,23 +248,20 @@ class BatchedNuclearPlantSimulator:
         return t["flags"], t["any"]
 
     def drain_events(self):
-        """Host drain: list of (plant, threshold_index) that fired in the last check_thresholds()."""
+        """Host drain: sorted list of (plant, threshold_index) that fired in the last check_thresholds().  The warp
+        ballot words say which 32-plant groups have anything at all; only those columns of the flag matrix travel."""
         t = self._thr
         anyw = t["any"].cpu().numpy().view(np.uint32)
-        if not anyw.any():
+        groups = np.nonzero(anyw)[0]
+        if groups.size == 0:
             return []
-        flags = t["flags"].cpu().numpy().view(np.uint32)
-        ev = []
-        for w in np.nonzero(anyw)[0]:
-            for lane in range(32):
-                if anyw[w] >> lane & 1:
-                    p = int(w) * 32 + lane
-                    for word in range(flags.shape[0]):
-                        bits = int(flags[word, p])
-                        while bits:
-                            b = (bits & -bits).bit_length() - 1
-                            ev.append((p, word * 32 + b))
-                            bits &= bits - 1
+        lanes = (anyw[groups, None] >> np.arange(32, dtype=np.uint32)[None, :]) & 1
+        plants = (groups[:, None] * 32 + np.arange(32)[None, :])[lanes.astype(bool)]
+        idx = torch.as_tensor(plants, dtype=torch.long, device=self.device)
+        words = t["flags"][:, idx].cpu().numpy().view(np.uint32)            # [n_words, n_flagged_plants]
+        bits = (words[:, :, None] >> np.arange(32, dtype=np.uint32)[None, None, :]) & 1
+        w, j, b = np.nonzero(bits)
+        ev = sorted(zip(plants[j].tolist(), (w * 32 + b).tolist()))
         return ev
 
     def reset_cooldowns(self, plant: int, rows: Sequence[int]) -> None:
@@ -272,26 +269,29 @@ class BatchedNuclearPlantSimulator:
         (StateManager._reset_threshold_cooldowns_for_maintenance: state_manager.py:1783-1830)."""
         self._thr["last"][torch.as_tensor(list(rows), dtype=torch.long, device=self.device), int(plant)] = -float("inf")
 
-    def read_threshold_values(self, plants: Sequence[int], table) -> Dict:
-        """{(plant, threshold index): value} of every bound threshold row for the given plants (the value the
-        violation record carries, state_manager.py:1343-1351)."""
+    def read_threshold_values(self, plants: Sequence[int], table, events=None) -> Dict:
+        """{(plant, threshold index): value} — the value the violation record carries (state_manager.py:1343-1351).
+        With `events` (the drained (plant, row) pairs) only those values are gathered on the device."""
         plants = list(plants)
         if not plants:
             return {}
-        idx = torch.as_tensor(plants, dtype=torch.long, device=self.device)
-        sub = self.slab[:, idx].cpu().numpy()          # [n_state, len(plants)]
         ix = field_index()
+        if events is None:
+            events = [(p, t) for p in plants for t, r in enumerate(table.rows) if r.field or r.derived]
+        ev_p = torch.as_tensor([e[0] for e in events], dtype=torch.long, device=self.device)
         out = {}
-        for t, r in enumerate(table.rows):
-            if r.field:
-                vals = sub[ix[r.field]]
-            elif r.derived == "pump_sum_wear":
-                w = lambda c: sub[ix[f"{r.unit}lub.component_wear[{c}]"]]
-                vals = w(0) + np.maximum(np.maximum(w(1), w(2)), w(3)) + w(4)
-            else:
-                continue
-            for j, p in enumerate(plants):
-                out[(p, t)] = float(vals[j])
+        direct = [i for i, (p, t) in enumerate(events) if table.rows[t].field]
+        if direct:
+            f = torch.as_tensor([ix[table.rows[events[i][1]].field] for i in direct], dtype=torch.long, device=self.device)
+            vals = self.slab[f, ev_p[direct]].cpu().numpy()
+            for i, v in zip(direct, vals):
+                out[events[i]] = float(v)
+        for i, (p, t) in enumerate(events):
+            r = table.rows[t]
+            if r.derived == "pump_sum_wear":
+                f = torch.as_tensor([ix[f"{r.unit}lub.component_wear[{c}]"] for c in range(5)], dtype=torch.long, device=self.device)
+                w = self.slab[f, p].cpu().numpy()
+                out[(p, t)] = float(w[0] + max(w[1], w[2], w[3]) + w[4])
         return out
 
     # -- maintenance effects (auto_maintenance.py:504-673 -> csrc/plant/maintenance.h) ----------------------------

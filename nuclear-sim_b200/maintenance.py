@@ -309,6 +309,35 @@ def orchestrate(component_id: str, violations: Sequence[dict], requested_action:
     return requested_action
 
 
+def single_violation_rules(component_id: str, parameter: str, action: Optional[str]):
+    """For the common event with exactly ONE violation the decision of ``orchestrate`` depends only on the value:
+    returns [(threshold, selected_action), ...] to test in order (value > threshold -> selected_action), and the
+    fallback action.  Derived from the same tables, so ``orchestrate`` stays the single statement of the rules
+    (tests/test_maintenance_host.py checks the two against each other)."""
+    h = _HIERARCHY.get(infer_component_type(component_id), {})
+    if not action:
+        return [], "routine_maintenance"
+    rules = []
+    for name, encompasses, trig in h.get("comprehensive", []):
+        n_enc = 1 if action in encompasses else 0
+        if "multiple_major_actions" in trig and n_enc >= trig["multiple_major_actions"]:
+            return [], name
+        if "total_violations" in trig and 1 >= trig["total_violations"]:
+            return [], name
+        for key, thr in trig.items():
+            if key.endswith("_threshold") and key.replace("_threshold", "") == parameter:
+                rules.append((thr, name))
+    rule = h.get("promotion", {}).get(action)   # coordination needs a second action in the batch: never with one violation
+    if rule:
+        promote_to, conditions = rule
+        for cond in conditions:
+            if ">" in cond:
+                pn, thr = cond.split(">")
+                if pn.strip() == parameter:
+                    rules.append((float(thr.strip()), promote_to))
+    return rules, action
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # work orders
 # ---------------------------------------------------------------------------------------------------------------
@@ -388,12 +417,14 @@ class BatchedAutoMaintenance:
         else:   # auto_maintenance.py:452-466 (hours): CRITICAL = half the HIGH delay
             self.delays = {"EMERGENCY": 0.0, "CRITICAL": 0.5, "HIGH": 1.0, "MEDIUM": 4.0, "LOW": 24.0}
         self.books: Dict[int, _PlantBook] = {}
+        self._pending: Dict[int, List[WorkOrder]] = {}     # scheduled, not yet executed, per plant in creation order
         self.created_log: List[WorkOrder] = []
         self.executed_log: List[WorkOrder] = []
         self.event_log: List[dict] = []
         self._rows_by_component: Dict[str, List[int]] = {}
         for i, r in enumerate(table.rows):
             self._rows_by_component.setdefault(r.component_id, []).append(i)
+        self._single = [single_violation_rules(r.component_id, r.parameter, r.action) for r in table.rows]
         sim.set_thresholds(table.device_rows())
 
     # -- AutoMaintenanceSystem.update: auto_maintenance.py:200-236 ------------------------------------------------
@@ -403,9 +434,9 @@ class BatchedAutoMaintenance:
             return []
         self.last_check_time = t_minutes
         due: List[WorkOrder] = []
-        for plant in sorted(self.books):
-            for wo in self.books[plant].orders:   # creation order (WorkOrderManager.work_orders dict order)
-                if wo.status == "SCHEDULED" and t_minutes >= wo.planned_start:
+        for plant in sorted(self._pending):
+            for wo in self._pending[plant]:       # creation order (WorkOrderManager.work_orders dict order)
+                if t_minutes >= wo.planned_start:
                     due.append(wo)
                     if self.head_quirks:
                         break
@@ -419,6 +450,10 @@ class BatchedAutoMaintenance:
                 raise NotImplementedError(f"perform_maintenance on {wo.component_id} is not restated on the device")
             wo.status, wo.executed_at, wo.success = "COMPLETED", t_minutes, bool(st == 1)
             self.executed_log.append(wo)
+            pend = self._pending[wo.plant]
+            pend.remove(wo)
+            if not pend:
+                del self._pending[wo.plant]
             if wo.success and not self.head_quirks:   # record_maintenance_result -> _reset_threshold_cooldowns_for_maintenance
                 addressed = _COOLDOWN_RESET.get(wo.action, [])
                 rows = [i for i in self._rows_by_component.get(wo.component_id, []) if self.table.rows[i].parameter in addressed]
@@ -436,7 +471,10 @@ class BatchedAutoMaintenance:
         by_plant: Dict[int, Dict[str, List[int]]] = {}
         for plant, t in fired:
             by_plant.setdefault(plant, {}).setdefault(self.table.rows[t].component_id, []).append(t)
-        values = self.sim.read_threshold_values(sorted(by_plant), self.table)
+        try:
+            values = self.sim.read_threshold_values(sorted(by_plant), self.table, events=fired)
+        except TypeError:      # engines without the sparse form (tests' CPU stand-in)
+            values = self.sim.read_threshold_values(sorted(by_plant), self.table)
         created = []
         for plant in sorted(by_plant):
             # component order = table order (dict order of maintenance_thresholds), parameters in config order
@@ -448,8 +486,16 @@ class BatchedAutoMaintenance:
                     violations.append({"parameter": r.parameter, "value": values[(plant, t)], "threshold": r.threshold,
                                        "comparison": r.comparison, "action": r.action, "priority": r.priority,
                                        "component_id": r.sub_component})
-                action = orchestrate(cid, violations, violations[0]["action"])
-                priority = max((v["priority"] for v in violations), key=lambda p: _PRIORITY_RANK.get(p, 2))
+                if len(violations) == 1:
+                    rules, action = self._single[by_plant[plant][cid][0]]
+                    for thr, promoted in rules:
+                        if violations[0]["value"] > thr:
+                            action = promoted
+                            break
+                    priority = violations[0]["priority"]
+                else:
+                    action = orchestrate(cid, violations, violations[0]["action"])
+                    priority = max((v["priority"] for v in violations), key=lambda p: _PRIORITY_RANK.get(p, 2))
                 self.event_log.append({"t": t_minutes, "plant": plant, "component": cid, "action": action,
                                        "violations": violations})
                 sub = None
@@ -472,14 +518,15 @@ class BatchedAutoMaintenance:
             # minutes compared against an hours constant (sic): auto_maintenance.py:351-358
             if t_minutes - book.recent_triggers[key] < self.work_order_cooldown_hours:
                 return None
-        for wo in book.orders:
-            if wo.component_id == cid and wo.status in ("PLANNED", "SCHEDULED", "IN_PROGRESS") and wo.action == action:
+        for wo in self._pending.get(plant, ()):
+            if wo.component_id == cid and wo.action == action:      # an active order for the same component and action
                 return None
         book.n_created += 1
         prio = priority.upper() if priority.upper() in self.delays else "MEDIUM"
         wo = WorkOrder(f"WO-{book.n_created:06d}", plant, cid, action, prio, t_minutes,
                        t_minutes + self.delays[prio] * 60.0, sub)
         book.orders.append(wo)
+        self._pending.setdefault(plant, []).append(wo)
         book.recent_triggers[key] = t_minutes
         self.created_log.append(wo)
         return wo

@@ -132,3 +132,21 @@ def test_scenario_host_logic_on_oracle(name):
         sim, g, lambda s, cfg: M.BatchedAutoMaintenance(s, M.ThresholdTable(cfg), aggressive=True), check_state)
     compare_logs(maint, log)
     assert len(log["created"]) >= 1 and len(log["executed"]) >= 1
+
+
+def test_single_violation_fast_path_equals_orchestrate():
+    """BatchedAutoMaintenance precomputes the decision for one-violation events; it must agree with orchestrate()
+    for every threshold row of the reference configuration, below and above every rule threshold."""
+    M = _maint()
+    tab = M.ThresholdTable(_template_maintenance_config())
+    for r in tab.rows:
+        rules, fallback = M.single_violation_rules(r.component_id, r.parameter, r.action)
+        probes = [0.0, 1e9] + [t * f for t, _ in rules for f in (0.999, 1.001)]
+        for val in probes:
+            want = M.orchestrate(r.component_id, [{"parameter": r.parameter, "value": val, "action": r.action}], r.action)
+            got = fallback
+            for thr, promoted in rules:
+                if val > thr:
+                    got = promoted
+                    break
+            assert got == want, (r.component_id, r.parameter, val)
