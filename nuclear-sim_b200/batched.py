@@ -88,7 +88,7 @@ class BatchedNuclearPlantSimulator:
         dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         with torch.cuda.device(dev_index):
             # SoA slab: field-major [n_state, n_plants]
-            self.slab = torch.from_numpy(np.ascontiguousarray(initial_state.T)).to(self.device)
+            self.slab = torch.from_numpy(np.array(initial_state.T, dtype=np.float64, order="C", copy=True)).to(self.device)
             self._initial = self.slab.clone()
             h = ctypes.c_void_p()
             _clib.check(self.L.nps_create(self.n_plants, dev_index, ctypes.byref(h)))

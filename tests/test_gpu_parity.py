@@ -297,3 +297,36 @@ def test_step_host_async_equals_step_host():
         for x, y in zip(out_a[i], out_b[i]):
             assert torch.equal(x, y), f"step {i}"
     assert torch.equal(a.slab, b.slab)
+
+
+def test_vector_env_and_checkpoint_resume(tmp_path):
+    """Vectorised NuclearPlantEnv surface (sim.py:911-940) with in-place reset of scrammed plants, and a checkpoint that
+    resumes bit for bit."""
+    import torch
+    from nuclear_sim_b200 import load_snapshot, field_index
+    from nuclear_sim_b200.env import BatchedNuclearPlantEnv, load_checkpoint, save_checkpoint
+    s0, params = load_snapshot("pwr3000_reactor_dt1")
+    n = 64
+    st = np.tile(s0, (n, 1))
+    ix = field_index()
+    st[::8, ix["pri.fuel_temperature"]] = 1600.0          # every 8th plant scrams on its first step (scram_logic.py:19)
+    env = BatchedNuclearPlantEnv(_sim(st, params), auto_reset=True, seed=3)
+    assert env.action_space_size == 15 and env.observation_space_size == 22
+    obs, rew, done, info = env.step(torch.full((n,), 8))
+    assert obs.shape == (n, 22) and rew.shape == (n,) and done.dtype == torch.bool
+    assert done.cpu().numpy().tolist() == [(i % 8 == 0) for i in range(n)]
+    assert "terminal_observation" in info and info["terminal_observation"].shape == (8, 22)
+    # scrammed plants were reset in place (back to the 1600 C initial state), the others kept stepping
+    assert float(env.sim.state.scram_status.sum()) == 0.0
+    assert (info["episode_steps"].cpu().numpy() == 1).all() and int(env.episode_steps.sum()) == n - 8
+    # checkpoint / resume
+    env2 = BatchedNuclearPlantEnv(_sim(np.tile(s0, (n, 1)), params), auto_reset=False, seed=5)
+    for _ in range(3):
+        env2.step(torch.randint(0, 15, (n,), generator=torch.Generator().manual_seed(1)))
+    path = str(tmp_path / "ck.pt")
+    save_checkpoint(env2.sim, path)
+    resumed = load_checkpoint(path)
+    acts = torch.full((1, n), 1, dtype=torch.int8)
+    a = env2.sim.step(actions=acts, K=4)
+    b = resumed.step(actions=acts, K=4)
+    assert torch.equal(env2.sim.slab, resumed.slab) and torch.equal(a["observation"], b["observation"])
