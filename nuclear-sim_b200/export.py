@@ -23,6 +23,12 @@ from ._layout import field_index
 from .maintenance import load_reference_columns
 
 
+# FeedwaterPumpLubricationSystem.maintenance_action_flags keys: feedwater/pump_lubrication.py:90-104
+PUMP_MAINTENANCE_FLAGS = ("oil_change", "oil_top_off", "bearing_replacement", "seal_replacement", "component_overhaul",
+                          "system_cleaning", "bearing_inspection", "impeller_inspection", "impeller_replacement",
+                          "lubrication_system_check", "motor_inspection", "oil_analysis", "vibration_analysis")
+
+
 class ColumnSchema:
     """Reference column order + how to obtain each column from a PlantState vector."""
 
@@ -35,6 +41,13 @@ class ColumnSchema:
         for name, e in cols.items():
             if name == "time":
                 continue
+            leaf = name.rsplit(".", 1)[-1]
+            if leaf.endswith("_occurred") and "feedwater_FWP-" in name:
+                # one-shot flags set by perform_maintenance and cleared by the next get_state_dict
+                # (feedwater/pump_lubrication.py:642-643, 1636-1641): true only in the row of the step that executed it
+                comp = name.split(".")[1].replace("feedwater_", "")
+                self.names.append(name); self.kind.append(("event", (comp, leaf[:-len("_occurred")]), e["type"]))
+                continue
             if e.get("field") in ix:
                 self.names.append(name); self.kind.append(("field", ix[e["field"]], e["type"]))
             elif e.get("derived") == "pump_sum_wear":
@@ -43,6 +56,9 @@ class ColumnSchema:
                 self.names.append(name); self.kind.append(("sum_wear", w, e["type"]))
             elif "const" in e:
                 self.names.append(name); self.kind.append(("const", e["const"], e["type"]))
+            elif e.get("expr") and all(f in ix for f in e.get("fields", [])):
+                # a rescaled field or an aggregate over repeated units (found by value on live plants, see make_column_map.py)
+                self.names.append(name); self.kind.append((e["expr"], ([ix[f] for f in e["fields"]], float(e.get("scale", 1.0))), e["type"]))
             else:
                 self.unavailable.append(name)
 
@@ -58,19 +74,32 @@ class ColumnSchema:
                 need.append(payload)
             elif how == "sum_wear":
                 need += list(payload)
+            elif how not in ("const", "event"):
+                need += list(payload[0])
         return sorted(set(need))
 
-    def row(self, state: np.ndarray, which: Sequence[int]) -> list:
+    def row(self, state: np.ndarray, which: Sequence[int], events=frozenset()) -> list:
+        """events: {(component_id, action)} executed in the step this row closes."""
         out = []
         for i in which:
             how, payload, typ = self.kind[i]
+            if how == "event":
+                comp, action = payload
+                out.append(any(c == comp and (action == "maintenance_action" or a == action) and a in PUMP_MAINTENANCE_FLAGS
+                               for c, a in events))
+                continue
             if how == "field":
                 v = float(state[payload])
             elif how == "sum_wear":
                 w = state[payload]
                 v = float(w[0] + max(w[1], w[2], w[3]) + w[4])
-            else:
+            elif how == "const":
                 v = payload
+            else:
+                x, scale = state[payload[0]], payload[1]
+                v = {"scaled": lambda: x[0], "sum": lambda: x.sum(), "mean": lambda: x.sum() / len(x), "max": lambda: x.max(),
+                     "min": lambda: x.min(), "mean_abs": lambda: np.abs(x).sum() / len(x), "max_abs": lambda: np.abs(x).max()}[how]()
+                v = float(v) * scale
             if typ in ("bool", "bool_"):
                 out.append(bool(v))
             elif typ == "int":
@@ -87,27 +116,29 @@ class TrajectoryStore:
         self.start_datetime = start_datetime or _dt.datetime(2024, 1, 1)
         self.times: List[_dt.datetime] = []
         self.rows: List[np.ndarray] = []
+        self.events: List[frozenset] = []
         self.max_rows = int(max_rows)
         self.schema = ColumnSchema()
 
-    def add_row(self, when: _dt.datetime, state: np.ndarray) -> None:
+    def add_row(self, when: _dt.datetime, state: np.ndarray, events=frozenset()) -> None:
         self.times.append(when)
         self.rows.append(np.array(state, dtype=np.float64, copy=True))
+        self.events.append(frozenset(events))
         if len(self.rows) > self.max_rows:       # StateManager trims the oldest rows when over capacity
-            del self.rows[0]; del self.times[0]
+            del self.rows[0]; del self.times[0]; del self.events[0]
 
     def clear(self) -> None:
-        self.times.clear(); self.rows.clear()
+        self.times.clear(); self.rows.clear(); self.events.clear()
 
     def _write(self, filename: str, which: Sequence[int], time_range=None) -> int:
         n = 0
         with open(filename, "w", newline="") as fh:
             w = csv.writer(fh)
             w.writerow(["time"] + [self.schema.names[i] for i in which])
-            for t, s in zip(self.times, self.rows):
+            for t, s, ev in zip(self.times, self.rows, self.events):
                 if time_range is not None and not (time_range[0] <= t <= time_range[1]):
                     continue
-                w.writerow([t.isoformat()] + self.schema.row(s, which))
+                w.writerow([t.isoformat()] + self.schema.row(s, which, ev))
                 n += 1
         return n
 

@@ -313,6 +313,7 @@ class NuclearPlantSimulator:
         info.update({"time": self._elapsed_minutes, "thermal_power": float(row[ix["pri.thermal_power_mw"]]),
                      "scram_activated": bool(row[ix["pri.scram_activated"]]),
                      "reactivity": float(row[ix["pri.total_reactivity_pcm"]])})
+        executed_now = frozenset()
         if self.enable_state_management and self._maint is not None:
             try:    # sim.py:209-223: execute due work orders, then collect states (threshold check)
                 executed = self._maint.update(self._elapsed_minutes)
@@ -322,6 +323,7 @@ class NuclearPlantSimulator:
                             {"component_id": wo.component_id, "action_type": wo.action, "success": wo.success,
                              "effectiveness": 1.0 if wo.success else 0.0, "timestamp": self._elapsed_minutes})
                 if executed:
+                    executed_now = frozenset((wo.component_id, wo.action) for wo in executed)
                     info["maintenance_work_orders"] = [vars(wo) for wo in executed]
                     self._cache = None
                     row = self._row()
@@ -332,7 +334,7 @@ class NuclearPlantSimulator:
             except Exception as e:     # the reference swallows maintenance failures into warnings (sim.py:214-216)
                 warnings.warn(f"Maintenance system update failed: {e}")
         if self.enable_state_management:
-            self.state_manager.store.add_row(self.state_manager.current_datetime, row)
+            self.state_manager.store.add_row(self.state_manager.current_datetime, row, executed_now)
         if self.enable_secondary:
             g = lambda f, d: float(row[ix[f]]) if np.isfinite(row[ix[f]]) else d
             info.update({"electrical_power": g("sec.electrical_power_output", 0.0),

@@ -141,6 +141,57 @@ def main():
             entry["varies"] = bool(np.ptp(arr) > 0)
             n_direct += 1
         out[c] = entry
+    # second pass: columns that are a constant, a rescaled field, or an aggregate over the repeated units
+    import re
+    idx = {n: i for i, n in enumerate(names)}
+    groups = {}
+    for n in names:
+        m = re.match(r"^(sgs\.sg|fw\.pump|turb\.bearing|turb\.stage|cond\.ejector)\[(\d+)\]\.(.+)$", n)
+        if m:
+            groups.setdefault((m.group(1), m.group(3)), []).append(n)
+        m = re.match(r"^(.*)\[(\d+)\]$", n)          # plain arrays (sec.prev_sg_levels[i], fw.lc_level_errors[i], ...)
+        if m:
+            groups.setdefault(("array", m.group(1)), []).append(n)
+    scales = [1.0, 1e-6, 1e-3, 1e3, 1e6, 100.0, 0.01, 60.0, 1 / 60.0, 3600.0, 1 / 3600.0]
+
+    def close(a, b):
+        return np.all(np.abs(a - b) <= 1e-12 * np.maximum(1.0, np.abs(b)))
+    n_second = 0
+    for c in cols:
+        e = out[c]
+        if e.get("field") or e.get("derived") or "const" in e or not e.get("numeric"):
+            continue
+        try:
+            arr = np.array([float(r.get(c)) for r in rows], dtype=np.float64)
+        except (TypeError, ValueError):
+            continue
+        if not np.ptp(arr) > 0:
+            e["const"] = float(arr[0]); n_second += 1
+            continue
+        pref = preferred_prefix(c) or ""
+        found = None
+        for sc_ in scales[1:]:
+            hits = [f for f in names if close(states[:, idx[f]] * sc_, arr)]
+            hits = [f for f in hits if f.startswith(pref)] or hits
+            if len(hits) == 1:
+                found = {"expr": "scaled", "fields": hits, "scale": sc_}
+                break
+        if not found:
+            for (unit, leaf), members in groups.items():
+                cols_ = states[:, [idx[f] for f in members]]
+                for op, val in (("sum", cols_.sum(1)), ("mean", cols_.sum(1) / len(members)), ("max", cols_.max(1)), ("min", cols_.min(1)),
+                                ("mean_abs", np.abs(cols_).sum(1) / len(members)), ("max_abs", np.abs(cols_).max(1))):
+                    for sc_ in (1.0, 1e-6, 1e-3, 1e3, 100.0):
+                        if np.ptp(val) > 0 and close(val * sc_, arr):
+                            found = {"expr": op, "fields": members, "scale": sc_}
+                            break
+                    if found:
+                        break
+                if found:
+                    break
+        if found:
+            e.update(found); n_second += 1
+    print(f"second pass: {n_second} more columns (constants / rescaled / unit aggregates)")
     path = os.path.join(_REPO, "nuclear-sim_b200", "data", "reference_columns.json")
     with open(path, "w") as fh:
         json.dump({"columns": out, "n_columns": len(cols), "n_direct": n_direct}, fh, indent=0, sort_keys=False)

@@ -70,6 +70,20 @@ def test_reference_runner_on_facade_equals_reference_runner(action, hours):
     assert ev(r_ref) == ev(r_our) and len(ev(r_ref)) >= 1
     me = lambda r: [(e["time_hours"], e["component_id"], e["action_type"], e["work_order_id"], e["success"]) for e in r.maintenance_events]
     assert me(r_ref) == me(r_our)
+    # every exportable logged column equals the reference's DataFrame column, row by row
+    df = r_ref.simulator.state_manager.data
+    store = r_our.simulator.state_manager.store
+    assert len(df) == len(store.rows)
+    sc = store.schema
+    which = sc.select()
+    ours = np.array([[float(v) for v in sc.row(row, which, ev)] for row, ev in zip(store.rows, store.events)])
+    bad = []
+    for j, i in enumerate(which):
+        ref_col = df[sc.names[i]].to_numpy(dtype=float)
+        if not np.all(np.abs(ours[:, j] - ref_col) <= 1e-9 * np.maximum(1e-6, np.abs(ref_col))):
+            bad.append(sc.names[i])
+    assert not bad, f"{len(bad)} exported columns differ from the reference, e.g. {bad[:6]}"
+    assert len(which) >= 730
     for a, b in zip(r_ref.simulation_data, r_our.simulation_data):
         for k in ("time_minutes", "maintenance_events", "threshold_violations_count", "maintenance_history_count"):
             assert a[k] == b[k], k
