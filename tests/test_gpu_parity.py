@@ -330,3 +330,19 @@ def test_vector_env_and_checkpoint_resume(tmp_path):
     a = env2.sim.step(actions=acts, K=4)
     b = resumed.step(actions=acts, K=4)
     assert torch.equal(env2.sim.slab, resumed.slab) and torch.equal(a["observation"], b["observation"])
+
+
+def test_cuda_batched_timing_sweep():
+    """The batched TimingOptimizer replacement on the CUDA engine: 512 candidate oil levels in one batch; the committed
+    initial level reproduces the reference's trigger time and the curve is monotone."""
+    import json
+    import os
+    from nuclear_sim_b200 import optimize as O, field_index
+    g = np.load(os.path.join(U.GOLDEN, "maint_oil_top_off.npz"), allow_pickle=False)
+    log = json.loads(str(g["log"]))
+    fld = "fw.pump[0].lub.oil_level"
+    level0 = float(g["state0"][field_index()[fld]])
+    vals = np.sort(np.append(np.linspace(58.2, 61.5, 511), level0))
+    hrs = O.trigger_time_sweep(g["state0"], g["params"], log["maintenance_system"], fld, vals, "oil_top_off", 5.0, component_id="FWP-1")
+    assert hrs[int(np.nonzero(vals == level0)[0][0])] == log["created"][0]["t"] / 60.0
+    assert not np.isnan(hrs).any() and np.all(np.diff(hrs) >= 0) and hrs[-1] > hrs[0]

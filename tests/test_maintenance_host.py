@@ -150,3 +150,25 @@ def test_single_violation_fast_path_equals_orchestrate():
                     got = promoted
                     break
             assert got == want, (r.component_id, r.parameter, val)
+
+
+def test_batched_timing_sweep_and_optimizer():
+    """TimingOptimizer as one batched sweep (CPU stand-in engine): the committed initial oil level reproduces the
+    reference's trigger time (140 min, maint_oil_top_off fixture), trigger time grows with the initial level, and the
+    optimiser lands a 2.0 h target within the timestep."""
+    from nuclear_sim_b200 import optimize as O
+    g = np.load(os.path.join(U.GOLDEN, "maint_oil_top_off.npz"), allow_pickle=False)
+    log = json.loads(str(g["log"]))
+    cfg = log["maintenance_system"]
+    fac = lambda st, p, dev: U.OracleSim(st, p)
+    fld = "fw.pump[0].lub.oil_level"
+    from nuclear_sim_b200 import field_index
+    level0 = float(g["state0"][field_index()[fld]])
+    vals = np.array([58.5, 59.0, level0, 61.0])
+    hrs = O.trigger_time_sweep(g["state0"], g["params"], cfg, fld, vals, "oil_top_off", 5.0, component_id="FWP-1", engine_factory=fac)
+    assert hrs[2] == log["created"][0]["t"] / 60.0
+    assert np.all(np.diff(hrs) > 0)
+    v, t, sweeps = O.optimize_for_target_timing(g["state0"], g["params"], cfg, fld, 58.1, 62.0, "oil_top_off", 2.0,
+                                                tolerance_hours=5.0 / 60.0, component_id="FWP-1", n_candidates=24,
+                                                engine_factory=fac)
+    assert abs(t - 2.0) <= 5.0 / 60.0 and sweeps <= 2 and 58.1 < v < level0
