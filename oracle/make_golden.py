@@ -184,7 +184,68 @@ def cfg5():
     run_scenario("cfg5_degradation", plants, 288, [1, 12, 144, 288], lambda p, t, sim: NO)
 
 
-ALL = {"cfg1": cfg1, "cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5}
+def cfg6():
+    """Secondary-side trips and alarms (BASELINE config #4's "safety-system trips with divergent per-plant control flow"
+    on the secondary side): each plant starts from the standard plant with ONE degraded condition written into the
+    reference's own objects before the first step, so every protection / trip branch runs in the reference itself."""
+    plants = _plants(["oil_top_off"] * 8, dt=1.0, heat_source="constant", noise_enabled=False)
+
+    def pumps(rp):
+        return list(rp.sim.secondary_physics.feedwater_system.pump_system.pumps.values())
+    # 0: lubrication oil nearly gone on FWP-1 (level alarms / lubrication trip path, pump_lubrication.py:1536-1580)
+    pumps(plants[0])[0].lubrication_system.oil_level = 6.0
+    # 1: NPSH collapse on FWP-2 (frozen at its IC value by the _initial_conditions_applied quirk): cavitation + NPSH trips
+    pumps(plants[1])[1].state.npsh_available = 6.0
+    # 2: SG-1 level above the 16.0 m pump-trip limit (pump_system.py:277-333)
+    plants[2].sim.secondary_physics.steam_generator_system.steam_generators[1].water_level = 16.3
+    # 3: hot turbine bearing (bearing-temperature trip with its delay timer, enhanced_physics.py:348-437)
+    list(plants[3].sim.secondary_physics.turbine.rotor_dynamics.bearings.values())[1].metal_temperature = 135.0
+    # 4: condenser air in-leakage x60 (vacuum alarms / low-vacuum turbine trip, vacuum_system.py:407-423)
+    plants[4].sim.secondary_physics.condenser.vacuum_system.current_air_leakage *= 60.0
+    # 5: badly contaminated, wet, acidic oil on FWP-3 (oil-quality alarms and trips, lubrication_base.py:434-500)
+    L = pumps(plants[5])[2].lubrication_system
+    L.oil_contamination_level, L.oil_moisture_content, L.oil_acidity_number = 48.0, 0.5, 3.5
+    # 6: feedwater pH far out of band (pH controller FAILED mode, ph_control_system.py:396-441)
+    plants[6].sim.secondary_physics.water_chemistry.ph = 7.2
+    # 7: heavy wear on every FWP-4 component (performance degradation, vibration, wear trips)
+    W = pumps(plants[7])[3].lubrication_system.component_wear
+    for k in W:
+        W[k] = 45.0
+    run_scenario("cfg6_secondary_trips", plants, 240, [1, 2, 3, 5, 8, 12, 20, 40, 80, 160, 240], lambda p, t, sim: NO)
+
+
+def cfg7():
+    """Turbine protection trips and severe fouling states, prepared the same way as cfg6."""
+    plants = _plants(["oil_top_off"] * 6, dt=1.0, heat_source="constant", noise_enabled=False)
+    sec = lambda i: plants[i].sim.secondary_physics
+    # 0: rotor overspeed (overspeed trip + overspeed event counter, enhanced_physics.py:348-437, rotor_dynamics.py:897-902)
+    sec(0).turbine.rotor_dynamics.rotor_speed = 4100.0
+    # 1: all four bearings hot (bearing-temperature trip after its delay)
+    for b in sec(1).turbine.rotor_dynamics.bearings.values():
+        b.metal_temperature = 150.0
+    # 2: thick TSP deposits on SG-0 (severe / critical fouling stage, shutdown and replacement flags, tsp_fouling_model.py:394-445)
+    d = sec(2).steam_generator_system.steam_generators[0].tsp_fouling.deposits
+    for lv in range(7):
+        d.magnetite_thickness[lv], d.copper_thickness[lv], d.silica_thickness[lv], d.biological_thickness[lv] = 3.6, 1.8, 2.7, 0.9
+    # 3: thick tube-interior scale on SG-2 (replacement flag, thermal resistance saturation)
+    t = sec(3).steam_generator_system.steam_generators[2].tube_interior_fouling
+    t.scale_thickness = 2.6
+    t.scale_composition = {k: v * 2.6 / max(1e-9, sum(t.scale_composition.values())) for k, v in t.scale_composition.items()} \
+        if sum(t.scale_composition.values()) > 0 else t.scale_composition
+    # 4: a quarter of the condenser tubes plugged, thick fouling (heat-transfer limit, vacuum degradation)
+    c = sec(4).condenser
+    c.tube_degradation.plugged_tube_count = 21000
+    c.tube_degradation.active_tube_count = 63000
+    c.fouling_model.biofouling_thickness, c.fouling_model.scale_thickness = 1.5, 0.8
+    # 5: large rotor vibration / thrust displacement
+    rd = sec(5).turbine.rotor_dynamics
+    for b in rd.bearings.values():
+        b.vibration_displacement = 30.0
+    rd.thrust_bearing_displacement = 1.4 if hasattr(rd, "thrust_bearing_displacement") else 0.0
+    run_scenario("cfg7_turbine_trips_fouling", plants, 240, [1, 2, 3, 5, 8, 12, 20, 40, 80, 160, 240], lambda p, t, sim: NO)
+
+
+ALL = {"cfg1": cfg1, "cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5, "cfg6": cfg6, "cfg7": cfg7}
 
 if __name__ == "__main__":
     if not R.reference_available():

@@ -9,7 +9,7 @@ from tests import _util as U
 
 pytestmark = pytest.mark.gpu
 
-SCENARIOS = ["cfg1_oil_top_off", "cfg2_steady", "cfg3_loadfollow", "cfg4_scram", "cfg5_degradation"]
+SCENARIOS = ["cfg1_oil_top_off", "cfg2_steady", "cfg3_loadfollow", "cfg4_scram", "cfg5_degradation", "cfg6_secondary_trips", "cfg7_turbine_trips_fouling"]
 
 
 def _sim(state0, params):

@@ -8,7 +8,7 @@ import pytest
 
 from tests import _util as U
 
-SCENARIOS = ["cfg1_oil_top_off", "cfg2_steady", "cfg3_loadfollow", "cfg4_scram", "cfg5_degradation"]
+SCENARIOS = ["cfg1_oil_top_off", "cfg2_steady", "cfg3_loadfollow", "cfg4_scram", "cfg5_degradation", "cfg6_secondary_trips", "cfg7_turbine_trips_fouling"]
 
 
 @pytest.mark.parametrize("name", SCENARIOS)
