@@ -29,6 +29,7 @@ NPS_HD double cond_h_g(double p_mpa) {
 // SteamJetEjector.update_state: condenser/vacuum_pump.py:470-536 (+ :96-275)
 NPS_HD void ejector_update(EjectorState& e, const PlantParams& p, int i, double suction_pressure, double required_capacity,
                            double motive_p, double motive_t, double dt, double& capacity_out, double& steam_out) {
+    NPS_TOUCH(e.is_operating); NPS_TOUCH(e.overall_performance_factor); NPS_TOUCH(e.nozzle_fouling_factor); NPS_TOUCH(e.diffuser_fouling_factor); NPS_TOUCH(e.nozzle_erosion_factor); NPS_TOUCH(e.operating_hours);
     e.suction_pressure = suction_pressure;
     e.motive_steam_pressure_actual = motive_p;
     e.motive_steam_temp_actual = motive_t;
@@ -182,6 +183,7 @@ struct CondenserResult {
 NPS_HD void condenser_update(CondenserState& C, const PlantParams& p, double steam_pressure, double steam_temperature,
                              double steam_flow, double steam_quality, double cw_flow, double cw_temp_in,
                              double motive_p, double motive_t, double dt, CondenserResult& out) {
+    NPS_TOUCH(C.td_active_tube_count); NPS_TOUCH(C.td_vibration_damage_accumulation); NPS_TOUCH(C.td_average_wall_thickness); NPS_TOUCH(C.td_corrosion_damage_accumulation); NPS_TOUCH(C.td_plugged_tube_count); NPS_TOUCH(C.td_operating_hours); NPS_TOUCH(C.cooling_water_outlet_temp); NPS_TOUCH(C.fl_biofouling_thickness); NPS_TOUCH(C.fl_scale_thickness); NPS_TOUCH(C.fl_corrosion_product_thickness); NPS_TOUCH(C.fl_time_since_cleaning); NPS_TOUCH(C.fl_distribution_factor); NPS_TOUCH(C.vs_condenser_pressure); NPS_TOUCH(C.operating_hours); NPS_TOUCH(C.vs_current_air_leakage); NPS_TOUCH(C.vs_air_mass_in_condenser); NPS_TOUCH(C.vc_rotation_timer); NPS_TOUCH(C.vs_operating_hours);
     C.steam_inlet_pressure = steam_pressure;
     C.steam_inlet_temperature = steam_temperature;
     C.steam_inlet_flow = steam_flow;

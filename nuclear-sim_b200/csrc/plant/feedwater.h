@@ -233,6 +233,8 @@ NPS_HD void fwp_simulate_sensors(FWPumpState& u, const PlantParams& p, const Pum
 // (primary/coolant/pump_models.py:104-146); dt in minutes as passed by the feedwater system.
 NPS_HD void fwp_update(FWPumpState& u, const PlantParams& p, const PumpSysCond& sc, double dt) {
     const double max_speed = 110.0, speed_ramp_rate = 15.0, startup_time = 20.0, coastdown_time = 60.0;
+    NPS_TOUCH(u.speed_setpoint); NPS_TOUCH(u.flow_demand); NPS_TOUCH(u.ic_applied); NPS_TOUCH(u.suction_pressure);
+    NPS_TOUCH(u.npsh_available); NPS_TOUCH(u.discharge_pressure); NPS_TOUCH(u.pump_flow_degradation);
     int status = (int)u.status;
     // _update_pump_dynamics
     if (status == PUMP_RUNNING) {
@@ -367,6 +369,8 @@ NPS_HD void feedwater_update(FeedwaterState& fw, WaterChemState& wc, const Plant
                              const SGState* prefetch_next = nullptr) {
     const int nsg = 3;
     const MakeupWater mk = {7.2, 100.0, 300.0, 30.0, 8.0};
+    NPS_TOUCH(fw.lc_quality_integral_error); NPS_TOUCH(fw.n_running_prev); NPS_TOUCH(fw.cav_n_events); NPS_TOUCH(fw.cav_accumulated_damage); NPS_TOUCH(fw.operating_hours); NPS_TOUCH(fw.cav_time_in_cavitation);
+    for (int i = 0; i < 3; ++i) { NPS_TOUCH(fw.lc_level_integral_errors[i]); NPS_TOUCH(fw.lc_previous_level_errors[i]); }
     wc_update(wc, true, mk, 0.02, dt);
 
     // ThreeElementControl.calculate_flow_demands: feedwater/level_control.py:157-363

@@ -76,6 +76,17 @@
 #define NPS_PREFETCH_FAR(obj) ((void)0)
 #endif
 
+// NPS_TOUCH(field): a volatile read whose value is dropped.  Put in a group at the top of a function it starts the
+// DRAM round trips of every state field the function is about to read, all at once; the function's own reads a few
+// hundred instructions later then find the lines in L1 (or merge with the fill in flight) instead of paying one round
+// trip each.  Works at function granularity only: 16 KB of L1 per warp does not keep a line for thousands of
+// instructions (profiles/r01_tuning_variants.txt (2), (9)).  Host builds: nothing.
+#if defined(__CUDA_ARCH__) && !defined(NPS_NO_TOUCH)
+#define NPS_TOUCH(x) do { double nps_t__ = *reinterpret_cast<const volatile double*>(&(x)); (void)nps_t__; } while (0)
+#else
+#define NPS_TOUCH(x) ((void)0)
+#endif
+
 namespace nps {
 
 // Python builtin max(a, b): returns a unless b > a.  (max(0, nan) == 0, max(nan, 0) is nan)

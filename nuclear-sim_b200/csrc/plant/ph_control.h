@@ -31,6 +31,7 @@ NPS_HD double np_sum_small(int n, Get get) {
 
 NPS_HD void ph_control_update(PHControlState& s, double current_ph, double dt, double z, const double* u,
                               bool emit_outputs = true) {
+    NPS_TOUCH(s.ph_sensor_status); NPS_TOUCH(s.measured_ph); NPS_TOUCH(s.ph_setpoint); NPS_TOUCH(s.ammonia_tank_level); NPS_TOUCH(s.morpholine_tank_level); NPS_TOUCH(s.control_mode); NPS_TOUCH(s.controller_enabled); NPS_TOUCH(s.integral_sum); NPS_TOUCH(s.previous_error); NPS_TOUCH(s.ammonia_supply_available); NPS_TOUCH(s.ammonia_pump_status); NPS_TOUCH(s.dev_count); NPS_TOUCH(s.dev_head); NPS_TOUCH(s.tic_initialized); NPS_TOUCH(s.tic_sum); NPS_TOUCH(s.tic_total_time); NPS_TOUCH(s.total_chemical_consumed); NPS_TOUCH(s.control_actions_count);
     const double dt_minutes = dt * 60.0;
     s.operating_hours += dt;
     // _apply_sensor_dynamics: :274-291

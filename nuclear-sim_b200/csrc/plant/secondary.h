@@ -37,6 +37,8 @@ NPS_HD_SHARED double secondary_sat_temp(double p_mpa) {
 NPS_HD void secondary_update(PlantState& st, const PlantParams& p, const PrimaryConditions& pc, double load_demand,
                              double cooling_water_temp, double dt, const StepInput& in) {
     SecondaryState& S = st.sec;
+    NPS_TOUCH(S.has_previous_feedwater_temp); NPS_TOUCH(S.previous_feedwater_temp); NPS_TOUCH(S.has_previous_sg_conditions); NPS_TOUCH(S.operating_hours);
+    for (int i = 0; i < 3; ++i) { NPS_TOUCH(S.prev_sg_levels[i]); NPS_TOUCH(S.prev_sg_steam_flows[i]); NPS_TOUCH(S.prev_sg_steam_qualities[i]); }
     S.load_demand = load_demand;
     S.feedwater_temperature = 227.0;
     S.cooling_water_temperature = cooling_water_temp;

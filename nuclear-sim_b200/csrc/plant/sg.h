@@ -91,6 +91,11 @@ NPS_HD void tsp_recompute_restriction(SGState& g) {
 NPS_HD void tsp_update(SGState& g, const PlantParams& p, double temperature, double flow_velocity, double dt_hours) {
     double dt_seconds = dt_hours * 3600.0;
     double dty = dt_seconds / (365.25 * 24.0 * 3600.0);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+    for (int lv = 0; lv < 7; ++lv) { NPS_TOUCH(g.tsp_thickness[lv][0]); NPS_TOUCH(g.tsp_thickness[lv][1]); NPS_TOUCH(g.tsp_thickness[lv][2]); NPS_TOUCH(g.tsp_thickness[lv][3]); }
+#endif
+    NPS_TOUCH(g.tsp_last_cleaning_time); NPS_TOUCH(g.tsp_cumulative_power_loss);
     g.tsp_operating_years += dty;
     g.tsp_last_cleaning_time += dty;
     double dt_years = dt_hours / (365.25 * 24.0);
@@ -151,8 +156,13 @@ NPS_HD double tif_thermal_resistance(const SGState& g) {
 // TubeInteriorFouling.update_fouling_state: tube_interior_fouling.py:273-325 (+ :117-188, 245-271)
 NPS_HD void tif_update(SGState& g, double temperature, double flow_velocity, double dt_seconds) {
     double dty = dt_seconds / (365.25 * 24.0 * 3600.0);
-    g.tif_operating_years += dty;
-    g.tif_last_cleaning_time += dty;
+    // inputs as one group of independent loads (see lub_update_oil_quality)
+    const double years0 = g.tif_operating_years, since0 = g.tif_last_cleaning_time, thick0 = g.tif_scale_thickness;
+    const double c0 = g.tif_comp[0], c1 = g.tif_comp[1], c2 = g.tif_comp[2], loss0 = g.tif_cumulative_performance_loss;
+    g.tif_operating_years = years0 + dty;
+    g.tif_last_cleaning_time = since0 + dty;
+    g.tif_scale_thickness = thick0; g.tif_comp[0] = c0; g.tif_comp[1] = c1; g.tif_comp[2] = c2;
+    g.tif_cumulative_performance_loss = loss0;
     // chemistry dict passed by SteamGenerator.update_state: B 1000, Li 2.0, pH 7.2, O2 0.005
     double tk = temperature + 273.15, rk = 320.0 + 273.15;
     double temp_factor = exp(-65000.0 / (8.314 * tk)) / exp(-65000.0 / (8.314 * rk));
@@ -180,6 +190,7 @@ NPS_HD void tif_update(SGState& g, double temperature, double flow_velocity, dou
 // SteamGenerator.update_state: steam_generator.py:664-848 (dt in seconds)
 NPS_HD void sg_update(SGState& g, const PlantParams& p, double t_in, double t_out, double primary_flow,
                       double steam_flow_out, double feedwater_flow_in, double feedwater_temp, double dt) {
+    NPS_TOUCH(g.water_level); NPS_TOUCH(g.steam_quality); NPS_TOUCH(g.steam_flow_rate); NPS_TOUCH(g.feedwater_flow_rate); NPS_TOUCH(g.tsp_heat_transfer_degradation); NPS_TOUCH(g.tif_scale_thermal_resistance); NPS_TOUCH(g.tsp_fouling_fraction); NPS_TOUCH(g.tsp_operating_years);
     // --- calculate_heat_transfer: steam_generator.py:150-314 ---
     double sat_temp = sg_sat_temp(g.secondary_pressure);
     double d1 = t_in - sat_temp, d2 = t_out - sat_temp;

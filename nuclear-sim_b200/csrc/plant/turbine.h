@@ -387,6 +387,7 @@ NPS_HD void turbine_update(TurbineState& T, const PlantParams& p, const SGSystem
 
     // RotorDynamicsModel.update_state: rotor_dynamics.py:956-1070
     {
+        NPS_TOUCH(T.rotor_speed); NPS_TOUCH(T.overspeed_events); NPS_TOUCH(T.rotor_temperature); NPS_TOUCH(T.thermal_bow); NPS_TOUCH(T.rotor_operating_hours); NPS_TOUCH(T.prot_trip_reasons); NPS_TOUCH(T.prot_timer_overspeed); NPS_TOUCH(T.prot_timer_vibration); NPS_TOUCH(T.prot_timer_bearing_temp); NPS_TOUCH(T.operating_hours);
         const double dt_seconds = dt * 3600.0;
         double total_friction = 0.0;
         for (int b = 0; b < 4; ++b)
@@ -412,7 +413,7 @@ NPS_HD void turbine_update(TurbineState& T, const PlantParams& p, const SGSystem
         const double steam_thrust = (100.0 * load_demand) / 4;
         NPS_UNIT_LOOP
         for (int b = 0; b < 4; ++b) {
-            TurbineBearingState& B = T.bearing[b];
+            TurbineBearingState B = T.bearing[b];   // 11 fields: one group of loads, written back after the block
             // calculate_bearing_loads: rotor_dynamics.py:83-130 (TB-003 is the thrust bearing)
             double thrust_load = (b == 2) ? steam_thrust : 0.0;
             double thermal_load = fabs(T.thermal_expansion) * p.rd_bearing_stiffness / 1000.0;
@@ -451,6 +452,7 @@ NPS_HD void turbine_update(TurbineState& T, const PlantParams& p, const SGSystem
             B.clearance_increase += tw * 0.01;
             B.efficiency_factor = B.wear_factor * 0.9 + 0.1;
             B.operating_hours += dt;
+            T.bearing[b] = B;
         }
         // VibrationMonitor.calculate_vibration_response: rotor_dynamics.py:624-705
         double avg_k = (0.0 + p.rd_bearing_stiffness + p.rd_bearing_stiffness + p.rd_bearing_stiffness + p.rd_bearing_stiffness) / 4;
@@ -489,6 +491,10 @@ NPS_HD void turbine_update(TurbineState& T, const PlantParams& p, const SGSystem
 
     // MetalTemperatureTracker.update_temperatures: enhanced_physics.py:73-165 (14 stage outlet temps)
     {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+        for (int i = 0; i < 14; ++i) { NPS_TOUCH(T.th_blade_temperatures[i]); if (i < 8) NPS_TOUCH(T.th_rotor_temperatures[i]); if (i < 6) NPS_TOUCH(T.th_casing_temperatures[i]); }
+#endif
         const double tc = p.tt_thermal_time_constant / 3600.0;
         for (int i = 0; i < 8; ++i) {
             double target = T.stage[i].outlet_temperature - 50.0;

@@ -38,6 +38,7 @@ NPS_HD_SHARED void wc_composite(WaterChemState& w) {
 
 // update_chemistry: water_chemistry.py:322-389.  `has_makeup` mirrors `if makeup_water_quality:`.
 NPS_HD_SHARED void wc_update(WaterChemState& w, bool has_makeup, const MakeupWater& mk, double blowdown, double dt) {
+    NPS_TOUCH(w.operating_hours); NPS_TOUCH(w.last_treatment_time); NPS_TOUCH(w.pending_effects); NPS_TOUCH(w.pend_ammonia_dose_rate); NPS_TOUCH(w.pend_morpholine_dose_rate); NPS_TOUCH(w.ph); NPS_TOUCH(w.pend_ph_setpoint); NPS_TOUCH(w.antiscalant_concentration); NPS_TOUCH(w.corrosion_inhibitor_level); NPS_TOUCH(w.hardness); NPS_TOUCH(w.total_dissolved_solids); NPS_TOUCH(w.chloride); NPS_TOUCH(w.chlorine_residual); NPS_TOUCH(w.iron_concentration); NPS_TOUCH(w.silica_concentration); NPS_TOUCH(w.alkalinity);
     double dt_hours;
     if (dt > 100) dt_hours = dt / 3600.0;
     else if (dt > 1) dt_hours = dt / 60.0;
