@@ -14,7 +14,7 @@ namespace nps {
 NPS_HD_SHARED double cond_sat_temp(double p_mpa) {
     if (p_mpa <= 0.001) return 10.0;
     double p_bar = np_clip(p_mpa * 10.0, 0.01, 100.0);
-    double t = 1730.63 / (8.07131 - log10(p_bar)) - 233.426;
+    double t = 1730.63 / (8.07131 - nps_log10(p_bar)) - 233.426;
     if (p_mpa >= 0.005 && p_mpa <= 0.01) t = np_clip(t, 35.0, 45.0);
     return np_clip(t, 10.0, 374.0);
 }
@@ -228,14 +228,14 @@ NPS_HD void condenser_update(CondenserState& C, const PlantParams& p, double ste
         double antiscalant = C.wc.antiscalant_concentration, inhibitor = C.wc.corrosion_inhibitor_level;
         const double dissolved_oxygen = 8.0;
         // biofouling
-        double tf = exp(p.cd_fl_biofouling_temp_coefficient * (wt - 25.0));
+        double tf = nps_exp(p.cd_fl_biofouling_temp_coefficient * (wt - 25.0));
         double clf = 1.0 / (1.0 + chlorine * 2.0);
         double nf = nutrient * p.cd_fl_biofouling_nutrient_factor;
         double gr = (p.cd_fl_biofouling_base_rate * tf * clf * nf);
         double thf = 1.0 / (1.0 + C.fl_biofouling_thickness / 2.0);
         double bio_inc = py_max(0.0, gr * thf * (dt / 1000.0));
         // scale
-        double stf = exp(p.cd_fl_scale_temp_coefficient * (wt - 25.0) / 10.0);
+        double stf = nps_exp(p.cd_fl_scale_temp_coefficient * (wt - 25.0) / 10.0);
         double hf = (hardness / 150.0) * p.cd_fl_scale_hardness_coefficient;
         double phf = py_max(0.1, (ph - 6.0) / 2.0);
         double af = 1.0 / (1.0 + antiscalant / 5.0);
@@ -243,7 +243,7 @@ NPS_HD void condenser_update(CondenserState& C, const PlantParams& p, double ste
         double sthf = 1.0 / (1.0 + C.fl_scale_thickness / 1.0);
         double scale_inc = py_max(0.0, fr * sthf * (dt / 1000.0));
         // corrosion products
-        double ctf = exp((wt - 25.0) / 20.0);
+        double ctf = nps_exp((wt - 25.0) / 20.0);
         double of = dissolved_oxygen * p.cd_fl_corrosion_oxygen_coefficient;
         double cphf = 1.0 + fabs(ph - p.cd_fl_corrosion_ph_optimum) / 2.0;
         double inf = 1.0 / (1.0 + inhibitor / 10.0);
@@ -280,7 +280,7 @@ NPS_HD void condenser_update(CondenserState& C, const PlantParams& p, double ste
         double d1 = py_max(sat - cw_temp_in, 0.1), d2 = py_max(sat - t_out, 0.1);
         double lmtd;
         if (fabs(d1 - d2) < 0.1) lmtd = (d1 + d2) / 2.0;
-        else if (d1 > 0 && d2 > 0) lmtd = (d1 - d2) / log(d1 / d2);
+        else if (d1 > 0 && d2 > 0) lmtd = (d1 - d2) / nps_log(d1 / d2);
         else lmtd = (d1 + d2) / 2.0;
         double air_conc = (C.vs_air_partial_pressure / py_max(0.001, C.vs_condenser_pressure));
         double h_steam = p.cd_steam_side_htc * (1.0 - 0.5 * air_conc);

@@ -366,7 +366,7 @@ NPS_HD void feedwater_update(FeedwaterState& fw, WaterChemState& wc, const Plant
                              const double* sg_levels, const double* sg_steam_flows, const double* sg_steam_qualities,
                              double manual_total_flow, double fw_temperature, double suction_pressure,
                              double discharge_pressure, double dt, FeedwaterResult& out,
-                             const SGState* prefetch_next = nullptr) {
+                             const SGState* prefetch_next = nullptr, ReportState* rep = nullptr) {
     const int nsg = 3;
     const MakeupWater mk = {7.2, 100.0, 300.0, 30.0, 8.0};
     NPS_TOUCH(fw.lc_quality_integral_error); NPS_TOUCH(fw.n_running_prev); NPS_TOUCH(fw.cav_n_events); NPS_TOUCH(fw.cav_accumulated_damage); NPS_TOUCH(fw.operating_hours); NPS_TOUCH(fw.cav_time_in_cavitation);
@@ -563,6 +563,36 @@ NPS_HD void feedwater_update(FeedwaterState& fw, WaterChemState& wc, const Plant
         if (avg_risk > 0.8) n_trips++;
         if (wear_for_protection / 4 > 85.0) n_trips++;
         fw.prot_system_trip_active = as_flag(n_trips > 0);
+
+        if (rep) {   // len(active_alarms): the alarm branches of the same checks (protection_system.py:59-124,483-678)
+            int n_alarms = 0;
+            for (int k = 0; k < 4; ++k) {
+                const FWPumpState& u = fw.pump[k];
+                if (u.npsh_available < 18.0) n_alarms++;
+                if (!(u.suction_pressure < p.fw_prot_low_suction_pressure_trip) && u.suction_pressure < 0.3) n_alarms++;
+                if (!(u.discharge_pressure > p.fw_prot_high_discharge_pressure_trip) && u.discharge_pressure > 9.0) n_alarms++;
+                if (u.vibration_level > 5.0) n_alarms++;
+                if (u.lub.oil_temperature + 5.0 > 80.0) n_alarms++;
+                if (u.motor_temperature > 100.0) n_alarms++;
+            }
+            {
+                double lf = p.fw_prot_low_flow_trip;
+                double low_alarm = (lf < 1.0) ? (lf * 1500.0) * 2.0 : 100.0;
+                double high_alarm = (1.3 * 1500.0) * 0.9;
+                if (prot_total_flow < low_alarm) n_alarms++;
+                if (prot_total_flow > high_alarm) n_alarms++;
+            }
+            for (int i = 0; i < 3; ++i) {
+                double level = sg_levels[i];
+                if (!(level > 16.5) && level > 15.5) n_alarms++;
+                if (level < 10.0) n_alarms++;
+                else if (level < 11.0) n_alarms++;
+            }
+            if (!(fw.diag_health_score < 0.3) && fw.diag_health_score < 0.5) n_alarms++;
+            if (!(avg_risk > 0.8) && avg_risk > 0.5) n_alarms++;
+            if (!(wear_for_protection / 4 > 85.0) && wear_for_protection / 4 > 50.0) n_alarms++;
+            rep->fw_prot_active_alarms_count = (double)n_alarms;
+        }
     }
 
     fw.total_flow_rate = total_flow;

@@ -108,6 +108,7 @@ NPS_HD double np_clip(double x, double lo, double hi) {
 // ARE the correctly rounded pow(x, 2) and pow(x, 0.5), i.e. at least as close to glibc's (<= 0.52 ulp) as libdevice
 // pow is.  The exponent is a literal at
 // most call sites, so the test folds away; the wear exponents are batch-uniform parameters (uniform branch).
+NPS_HD_SHARED double nps_pow_general(double x, double y) { return pow(x, y); }
 NPS_HD double py_pow(double x, double y) {
 #if defined(__CUDA_ARCH__) && !defined(NPS_GENERIC_POW)
     if (y == 2.0) return x * x;
@@ -120,8 +121,13 @@ NPS_HD double py_pow(double x, double y) {
         if (y == 0.25) return sqrt(sqrt(x));
     }
 #endif
-    return pow(x, y);
+    return nps_pow_general(x, y);
 }
+// libm calls through one shared body each on the device (see NPS_HD_SHARED): log / log10 / exp expand to 60-100 SASS
+// instructions per call site when inlined, and the kernel is instruction-fetch bound (20 % of stall samples).
+NPS_HD_SHARED double nps_log(double x) { return log(x); }
+NPS_HD_SHARED double nps_log10(double x) { return log10(x); }
+NPS_HD_SHARED double nps_exp(double x) { return exp(x); }
 NPS_HD double py_abs(double x) { return fabs(x); }
 NPS_HD double np_sign(double x) { return (x > 0.0) ? 1.0 : ((x < 0.0) ? -1.0 : ((x == 0.0) ? 0.0 : x)); }
 NPS_HD bool   is_true(double flag) { return flag != 0.0; }

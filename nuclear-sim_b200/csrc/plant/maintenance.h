@@ -18,6 +18,7 @@
 #include "sg.h"
 #include "turbine.h"
 #include "condenser.h"
+#include "report.h"
 
 namespace nps {
 
@@ -315,13 +316,21 @@ NPS_HD int maintain_condenser(CondenserState& C, const PlantParams& p, int actio
 
 // One request: (target, action, arg).  Targets without a perform_maintenance restatement report
 // MS_UNSUPPORTED_TARGET so the host can refuse instead of silently diverging.
-NPS_HD int maintenance_apply(PlantState& st, const PlantParams& p, int target, int action, int arg) {
+NPS_HD int maintenance_apply_target(PlantState& st, const PlantParams& p, int target, int action, int arg) {
     if (target >= MT_PUMP0 && target < MT_PUMP0 + 4) return maintain_pump(st.fw.pump[target - MT_PUMP0], action, arg);
     if (target >= MT_SG0 && target < MT_SG0 + 3) return maintain_sg(st.sgs.sg[target - MT_SG0], action);
     if (target >= MT_STAGE0 && target < MT_STAGE0 + 14) return maintain_stage(st.turb.stage[target - MT_STAGE0], p, target - MT_STAGE0, action);
     if (target == MT_CONDENSER) return maintain_condenser(st.cond, p, action);
     if (target == MT_TURBINE && action == MA_OTHER) return MS_FAILED;   // enhanced_physics.py:1259-1266 (unknown type)
     return MS_UNSUPPORTED_TARGET;
+}
+
+// The reference logs its state row AFTER maintenance (sim.py:209-223), and the report-only columns are computed from
+// the component state at that moment, so they are refreshed here.
+NPS_HD int maintenance_apply(PlantState& st, const PlantParams& p, int target, int action, int arg) {
+    const int rc = maintenance_apply_target(st, p, target, action, arg);
+    if (is_true(p.enable_secondary)) plant_report_state(st, p);
+    return rc;
 }
 
 }  // namespace nps

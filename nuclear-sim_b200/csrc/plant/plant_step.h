@@ -7,6 +7,7 @@
 #include "prefetch.h"
 #include "primary.h"
 #include "secondary.h"
+#include "report.h"
 
 namespace nps {
 
@@ -84,6 +85,7 @@ NPS_HD void plant_step(PlantState& st, const PlantParams& p, const StepInput& in
         st.sim.load_demand = st.pri.power_level;   // sim.py:161 (percent; overrides the caller)
         secondary_update(st, p, pc, st.sim.load_demand, st.sim.cooling_water_temp, dt, in);
         plant_secondary_to_primary(st);
+        if (in.emit_outputs) plant_report_state(st, p);
     }
     // state_manager.advance_time(dt) / self.time += dt : sim.py:183-194 (minutes)
     st.sim.time_minutes += dt;

@@ -84,7 +84,7 @@ NPS_HD double total_reactivity_pcm(const PrimaryState& s) {
     double xenon = (s.xenon_concentration / 1.0e15) * -1800.0;
     double samarium = (s.samarium_concentration / 5.0e14) * -600.0;
     double depletion = 3340.0 + -0.15 * s.fuel_burnup;
-    double bp = s.burnable_poison_worth * exp(-0.0002 * s.fuel_burnup);
+    double bp = s.burnable_poison_worth * nps_exp(-0.0002 * s.fuel_burnup);
     double total = 0.0 + rods;
     total += boron; total += doppler; total += mod_t; total += mod_void; total += pressure;
     total += xenon; total += samarium; total += depletion; total += bp;

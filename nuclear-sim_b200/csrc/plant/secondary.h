@@ -26,7 +26,7 @@ NPS_HD_SHARED double secondary_sat_temp(double p_mpa) {
     double ratio = p_mpa / p_ref;
     double t;
     if (ratio > 0) {
-        double tk = 1.0 / (1.0 / t_ref_k - (r_v / h_fg) * log(ratio));
+        double tk = 1.0 / (1.0 / t_ref_k - (r_v / h_fg) * nps_log(ratio));
         t = tk - 273.15;
     } else {
         t = t_ref;
@@ -67,7 +67,15 @@ NPS_HD void secondary_update(PlantState& st, const PlantParams& p, const Primary
     // STEP 1 feedwater: :445-491
     FeedwaterResult fwr;
     feedwater_update(st.fw, st.wc_main, p, S.prev_sg_levels, S.prev_sg_steam_flows, S.prev_sg_steam_qualities,
-                     est_total_flow, 40.0, 0.5, 7.4, dt, fwr, &st.sgs.sg[0]);
+                     est_total_flow, 40.0, 0.5, 7.4, dt, fwr, &st.sgs.sg[0], in.emit_outputs ? &st.rep : nullptr);
+    if (in.emit_outputs) {   // the SG conditions the feedwater system was given: feedwater/physics.py:685-688,1142-1145
+        ReportState& R = st.rep;
+        // np.mean of 3 values: add.reduce seeds the accumulator with element 0 and adds the pairwise sum of the rest
+        R.fw_avg_sg_level = (S.prev_sg_levels[0] + (S.prev_sg_levels[1] + S.prev_sg_levels[2])) / 3.0;
+        R.fw_avg_sg_pressure = (S.prev_sg_pressures[0] + (S.prev_sg_pressures[1] + S.prev_sg_pressures[2])) / 3.0;
+        R.fw_total_steam_flow = ((0.0 + S.prev_sg_steam_flows[0]) + S.prev_sg_steam_flows[1]) + S.prev_sg_steam_flows[2];
+        R.fw_avg_steam_quality = (S.prev_sg_steam_qualities[0] + (S.prev_sg_steam_qualities[1] + S.prev_sg_steam_qualities[2])) / 3.0;
+    }
     // STEP 2 steam generators: :493-535 ('sg_i' keys are absent from sg_flow_distribution -> equal split)
     double fw_flows[3];
     for (int i = 0; i < 3; ++i) fw_flows[i] = fwr.total_flow_rate / 3;
@@ -144,6 +152,38 @@ NPS_HD void secondary_update(PlantState& st, const PlantParams& p, const Primary
     S.sg_avg_pressure = avg_p;
     S.sg_avg_temperature = avg_t;
     S.condenser_pressure = cr.condenser_pressure;
+
+    if (in.emit_outputs) {   // HeatFlowTracker: :680-744 and heat_flow_tracker.py:248-327 (all MW)
+        ReportState& R = st.rep;
+        const double sg_in = total_heat_transfer / 1e6;
+        const double steam_out = total_heat_transfer * 0.98 / 1e6;
+        const double sg_losses = total_heat_transfer * 0.02 / 1e6;
+        const double mech = tr.mechanical_power;
+        const double turb_losses = mech * 0.05;
+        const double pump_work = fwr.total_power_consumption;
+        const double fw_losses = fwr.total_power_consumption * 0.1;
+        const double total_losses = (sg_losses + turb_losses + fw_losses);
+        const double rejection = sg_in - mech - total_losses;
+        const double cond_losses = rejection * 0.01;
+        const double gen_out = mech * 0.985;
+        const double gen_losses = mech - gen_out;
+        const double aux = gen_out * 0.02;
+        const double net = gen_out - aux;
+        const double e_in = (sg_in + pump_work);
+        const double e_out = (net + rejection + sg_losses + turb_losses + cond_losses + fw_losses + gen_losses + 0.0);
+        R.hf_steam_enthalpy_flow = steam_out;
+        R.hf_turbine_work_output = mech;
+        R.hf_condenser_heat_rejection = rejection;
+        R.hf_net_electrical_output = net;
+        R.hf_energy_balance_error = e_in - e_out;
+        if (e_in > 0) {
+            R.hf_energy_balance_percent = ((e_in - e_out) / e_in) * 100.0;
+            R.hf_overall_efficiency = net / e_in;
+        } else {
+            R.hf_energy_balance_percent = 0.0;
+            R.hf_overall_efficiency = 0.0;   // a fresh HeatFlowState() every step: heat_flow_tracker.py:255
+        }
+    }
 }
 
 }  // namespace nps

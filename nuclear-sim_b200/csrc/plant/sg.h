@@ -18,7 +18,7 @@ NPS_HD_SHARED double sg_sat_temp(double p_mpa) {
     double p_bar = p_mpa * 10.0;
     double t;
     if (p_bar > 0) {
-        double ln_p = log(p_bar);
+        double ln_p = nps_log(p_bar);
         t = 42.6776 + 34.5194 * ln_p + 2.8896 * py_pow(ln_p, 2.0) + 0.1153 * py_pow(ln_p, 3.0);
     } else {
         t = 10.0;
@@ -101,15 +101,15 @@ NPS_HD void tsp_update(SGState& g, const PlantParams& p, double temperature, dou
     double dt_years = dt_hours / (365.25 * 24.0);
 
     double temp_kelvin = temperature + 273.15;
-    double temp_factor = exp(-45000.0 / (8.314 * temp_kelvin));
-    temp_factor = temp_factor / exp(-45000.0 / (8.314 * 573.15));
+    double temp_factor = nps_exp(-45000.0 / (8.314 * temp_kelvin));
+    temp_factor = temp_factor / nps_exp(-45000.0 / (8.314 * 573.15));
     double ph_factor = 1.0 + 0.5 * fabs(p.sgwc_ph - 9.2);
     double velocity_factor = py_pow(flow_velocity / 3.0, 0.5);
     velocity_factor = np_clip(velocity_factor, 0.5, 2.0);
     double magnetite_rate = (2.5 * (1.0 + p.sgwc_iron * 1.5) * temp_factor * ph_factor * velocity_factor);
     double copper_rate = (0.8 * (1.0 + p.sgwc_copper * 2.0) * temp_factor * velocity_factor);
     double silica_rate = (1.2 * (1.0 + p.sgwc_silica / 100.0 * 1.8) * temp_factor * ph_factor);
-    double bio_temp_factor = (temperature < 60) ? 1.0 : exp(-(temperature - 60) / 20);
+    double bio_temp_factor = (temperature < 60) ? 1.0 : nps_exp(-(temperature - 60) / 20);
     double bio_rate = (0.5 * (1.0 + p.sgwc_dissolved_oxygen * 10.0) * bio_temp_factor * velocity_factor);
 
     const double max_thickness = 0.023 / 2.0 * 1000.0 * 0.9;
@@ -165,13 +165,13 @@ NPS_HD void tif_update(SGState& g, double temperature, double flow_velocity, dou
     g.tif_cumulative_performance_loss = loss0;
     // chemistry dict passed by SteamGenerator.update_state: B 1000, Li 2.0, pH 7.2, O2 0.005
     double tk = temperature + 273.15, rk = 320.0 + 273.15;
-    double temp_factor = exp(-65000.0 / (8.314 * tk)) / exp(-65000.0 / (8.314 * rk));
+    double temp_factor = nps_exp(-65000.0 / (8.314 * tk)) / nps_exp(-65000.0 / (8.314 * rk));
     double boric = 1.0 / (1.0 + 1000.0 / 1000.0 * 0.5);
     double lithium = py_max(0.5, 1.0 + (2.0 - 2.0) * 0.1);
     double ph_factor = 1.0 + 0.5 * fabs(7.2 - 7.2);
     double velocity_factor = np_clip(py_pow(flow_velocity / 5.0, -0.6), 0.5, 2.0);
     double oxygen = 1.0 + 0.005 * 10.0;
-    double saturation = exp(-g.tif_scale_thickness / 2.0);
+    double saturation = nps_exp(-g.tif_scale_thickness / 2.0);
     double rate = (0.001 * temp_factor * boric * lithium * ph_factor * velocity_factor * oxygen * saturation);
     g.tif_scale_formation_rate = np_clip(rate, 0.0, 0.1);
     double inc = g.tif_scale_formation_rate * dty;
@@ -194,7 +194,7 @@ NPS_HD void sg_update(SGState& g, const PlantParams& p, double t_in, double t_ou
     // --- calculate_heat_transfer: steam_generator.py:150-314 ---
     double sat_temp = sg_sat_temp(g.secondary_pressure);
     double d1 = t_in - sat_temp, d2 = t_out - sat_temp;
-    double lmtd = (fabs(d1 - d2) < 1.0) ? (d1 + d2) / 2.0 : (d1 - d2) / log(d1 / d2);
+    double lmtd = (fabs(d1 - d2) < 1.0) ? (d1 + d2) / 2.0 : (d1 - d2) / nps_log(d1 / d2);
     double flow_factor = py_pow(primary_flow / p.sg_primary_design_flow, 0.8);
     double h_primary = p.sg_primary_htc * flow_factor;
     double pressure_factor = py_pow(g.secondary_pressure / p.sg_design_pressure_secondary, 0.15);
@@ -264,7 +264,7 @@ NPS_HD void sg_update(SGState& g, const PlantParams& p, double t_in, double t_ou
     double demand_factor = (p.sg_secondary_design_flow > 0) ? actual_steam / p.sg_secondary_design_flow : 0.0;
     eq_p += -demand_factor * 0.5;
     eq_p = np_clip(eq_p, 3.0, 8.5);
-    double decay = exp(-dt / 60.0);
+    double decay = nps_exp(-dt / 60.0);
     double base_new_p = eq_p + (P - eq_p) * decay;
     double corr = 0.0;
     if (actual_fw < 0.1 && actual_steam > 100.0) {

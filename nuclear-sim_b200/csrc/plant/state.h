@@ -515,6 +515,49 @@ struct SecondaryState {
     double power_reduction_factor;
 };
 
+// ---- report-only quantities ------------------------------------------------------------------------
+// Values the reference computes on the fly in its get_state_dict() methods (or keeps in HeatFlowTracker) for the state
+// log and nowhere else; nothing on the step path reads them.  They are written on the last fused substep only
+// (StepInput.emit_outputs) and refreshed by the maintenance kernel, so a logged row sees what the reference's
+// collect_states (simulator/state/state_manager.py:152-211, called after maintenance: sim.py:209-223) would see.
+//   sg_*            SteamGenerator.get_state_dict: steam_generator/steam_generator.py:944-986
+//   sgs_*           EnhancedSteamGeneratorPhysics.get_state_dict: steam_generator/enhanced_physics.py:689-723
+//   fwp_*           FeedwaterPumpLubricationSystem properties: feedwater/pump_lubrication.py:225-233,1619-1620
+//   fw_avg_* ...    EnhancedFeedwaterPhysics.get_state_dict: feedwater/physics.py:1142-1145 (the SG conditions it was
+//                   LAST GIVEN, i.e. the previous step's: systems/secondary/__init__.py:447-491)
+//   fw_diag_*       PerformanceDiagnostics.get_state_dict: feedwater/performance_monitoring.py:650-662
+//                   (fw_diag_total_wear: WearTrackingModel is never advanced on the lubrication-system path,
+//                   performance_monitoring.py:473-491, so it keeps its initial value; the step does not touch it)
+//   fw_prot_*       FeedwaterProtectionSystem.get_state_dict: feedwater/protection_system.py:778
+//   hf_*            HeatFlowTracker: systems/secondary/__init__.py:680-744, heat_flow_tracker.py:248-327
+struct ReportState {
+    double sg_primary_flow_restriction_factor[3];
+    double sg_secondary_flow_restriction_factor[3];
+    double sg_max_primary_flow_capacity[3];
+    double sg_max_steam_flow_capacity[3];
+    double sg_max_feedwater_flow_capacity[3];
+    double sg_fouling_energy_penalty_mw[3];
+    double sg_total_pump_power_mw[3];
+    double sgs_total_fouling_impact;
+    double sgs_fouling_maintenance_needed;
+    double fwp_efficiency_factor[4];
+    double fwp_flow_factor[4];
+    double fw_avg_sg_level;
+    double fw_avg_sg_pressure;
+    double fw_total_steam_flow;
+    double fw_avg_steam_quality;
+    double fw_diag_maintenance_urgency;
+    double fw_diag_total_wear;
+    double fw_prot_active_alarms_count;
+    double hf_steam_enthalpy_flow;
+    double hf_turbine_work_output;
+    double hf_condenser_heat_rejection;
+    double hf_net_electrical_output;
+    double hf_overall_efficiency;
+    double hf_energy_balance_error;
+    double hf_energy_balance_percent;
+};
+
 struct PlantState {
     PrimaryState pri;
     SimState sim;
@@ -525,6 +568,7 @@ struct PlantState {
     CondenserState cond;
     PHControlState ph;
     SecondaryState sec;
+    ReportState rep;
 };
 
 // ---- batch-uniform parameters ------------------------------------------------------------

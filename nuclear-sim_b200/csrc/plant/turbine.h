@@ -17,7 +17,7 @@ namespace nps {
 NPS_HD_SHARED double turb_sat_temp(double p_mpa) {
     if (p_mpa <= 0.001) return 10.0;
     double p_bar = np_clip(p_mpa * 10.0, 0.01, 100.0);
-    double t = 1730.63 / (8.07131 - log10(p_bar)) - 233.426;
+    double t = 1730.63 / (8.07131 - nps_log10(p_bar)) - 233.426;
     return np_clip(t, 10.0, 374.0);
 }
 NPS_HD_SHARED double turb_h_g(double p_mpa) {   // stage_system.py:468-473
@@ -72,10 +72,10 @@ NPS_HD double stage_steam_enthalpy(double t, double p_mpa) { TurbSatMemo m; turb
 // TurbineStage._steam_entropy: stage_system.py:445-456
 NPS_HD double stage_steam_entropy(double t, double p_mpa, TurbSatMemo& m) {
     double sat = turb_sat_temp_m(m, p_mpa);
-    double s_f = 4.18 * log((sat + 273.15) / 273.15);
+    double s_f = 4.18 * nps_log((sat + 273.15) / 273.15);
     double s_fg = 2257.0 / (sat + 273.15);
     double s_g = s_f + s_fg;
-    if (t > sat) return s_g + 2.1 * log((t + 273.15) / (sat + 273.15));
+    if (t > sat) return s_g + 2.1 * nps_log((t + 273.15) / (sat + 273.15));
     return s_g;
 }
 // EnhancedTurbinePhysics._steam_enthalpy: enhanced_physics.py:1285-1293

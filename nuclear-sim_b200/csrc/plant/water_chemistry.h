@@ -23,10 +23,10 @@ NPS_HD_SHARED void wc_composite(WaterChemState& w) {
     double silica_particle = w.silica_concentration / 20.0;
     w.particle_content = 1.0 + (tds_factor + iron_particle + silica_particle) * 0.1;
     w.particle_content = np_clip(w.particle_content, 0.5, 2.0);
-    double A = (log10(w.total_dissolved_solids) - 1) / 10;
-    double B = -13.12 * log10(25.0 + 273) + 34.55;
-    double C = log10(w.hardness) - 0.4;
-    double D = log10(w.alkalinity);
+    double A = (nps_log10(w.total_dissolved_solids) - 1) / 10;
+    double B = -13.12 * nps_log10(25.0 + 273) + 34.55;
+    double C = nps_log10(w.hardness) - 0.4;
+    double D = nps_log10(w.alkalinity);
     double ph_sat = (9.3 + A + B) - (C + D);
     w.scaling_tendency = w.ph - ph_sat;
     w.corrosion_tendency = 2 * ph_sat - w.ph;
@@ -86,7 +86,7 @@ NPS_HD_SHARED void wc_update(WaterChemState& w, bool has_makeup, const MakeupWat
         w.antiscalant_concentration += (5.0 - w.antiscalant_concentration) * dose_rate;
         w.corrosion_inhibitor_level += (10.0 - w.corrosion_inhibitor_level) * dose_rate;
         double decay = 0.1 * dt_hours;
-        w.chlorine_residual *= exp(-decay);
+        w.chlorine_residual *= nps_exp(-decay);
         w.chlorine_residual += (1.0 - w.chlorine_residual) * dose_rate;
         double ce = (w.chlorine_residual > 0.2) ? 1.0 : 0.5;
         double ae = (w.antiscalant_concentration > 2.0) ? 1.0 : 0.7;

@@ -8,12 +8,14 @@
 The reference builds each row from Python ``get_state_dict()`` calls (789 columns).  The batched engine carries the
 same quantities as PlantState fields; data/reference_columns.json (written by oracle/make_column_map.py from a live
 plant) names the field behind every column.  Columns that are constants in the reference are written as that constant;
-columns that are derived report values which the engine does not carry are listed in ``unavailable_columns`` and left
-out (the reference's own consumers of these files — the runners' fwp.csv / secondary.csv — read them by name).
+the values the reference computes on the fly for the log (flow restrictions, heat-flow bookkeeping, alarm counts ...)
+are the ReportState fields the step kernel writes (csrc/plant/report.h).  Anything without a source would be listed in
+``ColumnSchema.unavailable``; with the round-1 schema that list is empty (788 of 788 columns).
 """
 from __future__ import annotations
 
 import csv
+import re
 import datetime as _dt
 from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 
@@ -22,6 +24,9 @@ import numpy as np
 from ._layout import field_index
 from .maintenance import load_reference_columns
 
+
+# PumpStatus values (systems/primary/coolant/pump_models.py:19-26) in the order of the status code in csrc/plant/state.h
+PUMP_STATUS_NAMES = ("running", "stopped", "starting", "stopping", "tripped")
 
 # FeedwaterPumpLubricationSystem.maintenance_action_flags keys: feedwater/pump_lubrication.py:90-104
 PUMP_MAINTENANCE_FLAGS = ("oil_change", "oil_top_off", "bearing_replacement", "seal_replacement", "component_overhaul",
@@ -48,6 +53,15 @@ class ColumnSchema:
                 comp = name.split(".")[1].replace("feedwater_", "")
                 self.names.append(name); self.kind.append(("event", (comp, leaf[:-len("_occurred")]), e["type"]))
                 continue
+            m = re.match(r"secondary\.feedwater_FWP-(\d+)\.status$", name)
+            if m:    # PumpStatus.value string (feedwater/pump_system.py:1068) from the status code (csrc/plant/state.h)
+                self.names.append(name); self.kind.append(("pump_status", ix[f"fw.pump[{int(m.group(1)) - 1}].status"], "str"))
+                continue
+            if leaf == "heat_flow_energy_balance_ok" and "rep.hf_energy_balance_percent" in ix:
+                # HeatFlowTracker.validate_energy_balance: |percent error| < validation_tolerance * 100
+                # (systems/secondary/heat_flow_tracker.py:224,342)
+                self.names.append(name); self.kind.append(("balance_ok", ix["rep.hf_energy_balance_percent"], "bool"))
+                continue
             if e.get("field") in ix:
                 self.names.append(name); self.kind.append(("field", ix[e["field"]], e["type"]))
             elif e.get("derived") == "pump_sum_wear":
@@ -70,7 +84,7 @@ class ColumnSchema:
         need = []
         for i in which:
             how, payload, _ = self.kind[i]
-            if how == "field":
+            if how in ("field", "pump_status", "balance_ok"):
                 need.append(payload)
             elif how == "sum_wear":
                 need += list(payload)
@@ -87,6 +101,12 @@ class ColumnSchema:
                 comp, action = payload
                 out.append(any(c == comp and (action == "maintenance_action" or a == action) and a in PUMP_MAINTENANCE_FLAGS
                                for c, a in events))
+                continue
+            if how == "pump_status":
+                out.append(PUMP_STATUS_NAMES[int(state[payload])])
+                continue
+            if how == "balance_ok":
+                out.append(bool(abs(float(state[payload])) < 0.01 * 100))
                 continue
             if how == "field":
                 v = float(state[payload])

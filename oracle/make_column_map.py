@@ -88,6 +88,21 @@ def preferred_prefix(col: str):
     return "sec."
 
 
+def report_field(col: str):
+    """ReportState field (csrc/plant/state.h) that carries a per-unit report column, by construction of its name."""
+    import re
+    parts = col.split(".")
+    if len(parts) < 3:
+        return None
+    m = re.match(r"feedwater_FWP-(\d+)$", parts[1])
+    if m:
+        return f"rep.fwp_{parts[2]}[{int(m.group(1)) - 1}]"
+    m = re.match(r"steam_generator_SG-(\d+)$", parts[1])
+    if m:
+        return f"rep.sg_{parts[2]}[{int(m.group(1))}]"
+    return None
+
+
 STAGE_KEYS = ("inlet_pressure", "outlet_pressure", "inlet_temperature", "outlet_temperature", "power_output", "efficiency",
               "extraction_flow", "loading_factor", "blade_condition", "deposit_thickness", "operating_hours")
 
@@ -128,6 +143,9 @@ def main():
         if cand:
             pref = preferred_prefix(c)
             inside = [f for f in cand if pref and f.startswith(pref)]
+            rep = report_field(c)          # report-only quantity of THIS unit (ReportState arrays are indexed by unit)
+            if rep in cand:
+                inside = [rep]
             if not inside and not np.ptp(arr) > 0:
                 entry["const"] = float(arr[0])     # a constant that happens to equal unrelated fields: not a mapping
                 out[c] = entry

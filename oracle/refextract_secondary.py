@@ -517,10 +517,48 @@ def secondary(sec, d):
     d[P + "power_reduction_factor"] = (float(last["electrical_power_mw"]) / tnet if tnet else (1.0 if not last else 0.0))
 
 
+def report(sec, d):
+    """ReportState: what the reference's get_state_dict() methods / HeatFlowTracker report at this moment."""
+    P = "rep."
+    sgs = sec.steam_generator_system
+    for i, sg in enumerate(sgs.steam_generators):
+        sd = sg.get_state_dict()
+        for name in ("primary_flow_restriction_factor", "secondary_flow_restriction_factor",
+                     "max_primary_flow_capacity", "max_steam_flow_capacity", "max_feedwater_flow_capacity",
+                     "fouling_energy_penalty_mw", "total_pump_power_mw"):
+            d[f"{P}sg_{name}[{i}]"] = float(sd[name])
+    sd = sgs.get_state_dict()
+    d[P + "sgs_total_fouling_impact"] = float(sd["system_total_fouling_impact"])
+    d[P + "sgs_fouling_maintenance_needed"] = float(sd["system_fouling_maintenance_needed"])
+    fw = sec.feedwater_system
+    for k, pump in enumerate(fw.pump_system.pumps.values()):
+        L = pump.lubrication_system
+        d[f"{P}fwp_efficiency_factor[{k}]"] = float(L.pump_efficiency_factor)
+        d[f"{P}fwp_flow_factor[{k}]"] = float(L.pump_flow_factor)
+    fd = fw.get_state_dict()
+    d[P + "fw_avg_sg_level"] = float(fd["feedwater_avg_sg_level"])
+    d[P + "fw_avg_sg_pressure"] = float(fd["feedwater_avg_sg_pressure"])
+    d[P + "fw_total_steam_flow"] = float(fd["feedwater_total_steam_flow"])
+    d[P + "fw_avg_steam_quality"] = float(fd["feedwater_avg_steam_quality"])
+    dd = fw.diagnostics.get_state_dict()
+    d[P + "fw_diag_maintenance_urgency"] = float(dd["diagnostics_maintenance_urgency"])
+    d[P + "fw_diag_total_wear"] = float(dd["diagnostics_total_wear"])
+    d[P + "fw_prot_active_alarms_count"] = float(len(fw.protection_system.active_alarms))
+    hs = sec.heat_flow_tracker.heat_flow_state
+    d[P + "hf_steam_enthalpy_flow"] = float(hs.steam_enthalpy_flow)
+    d[P + "hf_turbine_work_output"] = float(hs.turbine_work_output)
+    d[P + "hf_condenser_heat_rejection"] = float(hs.condenser_heat_rejection)
+    d[P + "hf_net_electrical_output"] = float(hs.net_electrical_output)
+    d[P + "hf_overall_efficiency"] = float(hs.overall_thermal_efficiency)
+    d[P + "hf_energy_balance_error"] = float(hs.energy_balance_error)
+    d[P + "hf_energy_balance_percent"] = float(hs.energy_balance_percent_error)
+
+
 def extract(sim, d):
     if not (sim.enable_secondary and sim.secondary_physics is not None):
         return
     sec = sim.secondary_physics
+    report(sec, d)
     water_chem(sec.water_chemistry, "wc_main.", d)
     feedwater(sec.feedwater_system, d)
     steam_generators(sec.steam_generator_system, d)
