@@ -237,9 +237,10 @@ def main():
         acts_h[i] = torch.from_numpy(a); mags_h[i] = torch.from_numpy(m)
         noise_h[i] = torch.from_numpy(sc.noise_inputs(pid, i * ksub, ksub))
     acts_d, mags_d, noise_d = acts_h.to(dev), mags_h.to(dev), noise_h.to(dev)
-    obs_h = [torch.empty((22, n), dtype=torch.float64).pin_memory() for _ in range(2)]
-    rew_h = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(2)]
-    done_h = [torch.empty(n, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    D = sim.pipe_depth       # launches nps_step_host_async keeps in flight; one set of pinned result buffers per slot
+    obs_h = [torch.empty((22, n), dtype=torch.float64).pin_memory() for _ in range(D)]
+    rew_h = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(D)]
+    done_h = [torch.empty(n, dtype=torch.uint8).pin_memory() for _ in range(D)]
 
     def barrier():
         if world > 1:
@@ -273,8 +274,8 @@ def main():
 
     # ------------------------------------------------------------------ end-to-end arm (host buffers through the C ABI)
     # Every step: pinned host inputs -> device, 32 substeps, observation/reward/done -> pinned host, and the host reads
-    # the step's reward.  nps_step_host_async keeps two launches in flight so the copies of step i+1 overlap the kernel
-    # of step i; the host consumes step i's result while step i+1 runs.
+    # the step's reward.  nps_step_host_async keeps up to D launches in flight: the input copies of later steps overlap
+    # the kernel of step i, and the host consumes step i's result while the next steps run.
     sim.reset()
     for i in range(W):
         sim.step_host(acts_h[i], mags_h[i], noise_h[i], None, ksub, obs_h[0], rew_h[0], done_h[0])
@@ -283,14 +284,14 @@ def main():
     reward_sum, tickets = 0.0, []
     e0.record()
     for i in range(K):
-        b = i & 1
-        if i >= 2:
-            sim.wait(tickets[i - 2])
+        b = i % D
+        if i >= D:
+            sim.wait(tickets[i - D])
             reward_sum += float(rew_h[b].mean())
         tickets.append(sim.step_host_async(acts_h[W + i], mags_h[W + i], noise_h[W + i], None, ksub, obs_h[b], rew_h[b], done_h[b]))
-    for i in range(max(0, K - 2), K):
+    for i in range(max(0, K - D), K):
         sim.wait(tickets[i])
-        reward_sum += float(rew_h[i & 1].mean())
+        reward_sum += float(rew_h[i % D].mean())
     e1.record()
     barrier()
     te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)

@@ -69,11 +69,14 @@ int nps_step_host(nps_handle* h, double* d_state, const int8_t* h_action, const 
                   const double* h_noise, const double* h_setpoint, int k_substeps, double* h_obs, double* h_reward,
                   uint8_t* h_done, void* cuda_stream);
 
-/* Pipelined form of nps_step_host for a driver that steps in a loop: returns at once with a ticket (0 or 1); the
- * host->device copies run on an internal copy stream into one of two staging sets, so the inputs of launch i+1 travel
- * while launch i computes, and the results of launch i travel while launch i+1 computes.  Host buffers must be pinned
- * and must stay untouched until nps_wait(ticket) returns (inputs) / are valid after it returns (outputs).  At most two
- * launches may be outstanding: wait for ticket t before issuing the call that will reuse it. */
+/* Pipelined form of nps_step_host for a driver that steps in a loop: returns at once with a ticket in
+ * [0, NPS_PIPE_DEPTH); the host->device copies run on an internal copy stream into one of NPS_PIPE_DEPTH staging sets,
+ * so the inputs of later launches travel while launch i computes, and the results of launch i travel while launch i+1
+ * computes.  Host buffers must be pinned and must stay untouched until nps_wait(ticket) returns (inputs) / are valid
+ * after it returns (outputs).  At most NPS_PIPE_DEPTH launches may be outstanding: tickets are handed out round-robin,
+ * so wait for the ticket of call i - NPS_PIPE_DEPTH before issuing call i. */
+#define NPS_PIPE_DEPTH 4
+int nps_pipe_depth(void);
 int nps_step_host_async(nps_handle* h, double* d_state, const int8_t* h_action, const double* h_magnitude,
                         const double* h_noise, const double* h_setpoint, int k_substeps, double* h_obs, double* h_reward,
                         uint8_t* h_done, void* cuda_stream);

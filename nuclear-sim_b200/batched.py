@@ -152,7 +152,8 @@ class BatchedNuclearPlantSimulator:
         self.n_launches += 1
 
     def step_host_async(self, h_actions, h_magnitudes, h_noise, h_setpoint, K, h_obs, h_reward, h_done) -> int:
-        """Pipelined step_host (nps_step_host_async): returns a ticket; wait(ticket) makes the outputs valid."""
+        """Pipelined step_host (nps_step_host_async): returns a ticket; wait(ticket) makes the outputs valid.
+        Up to ``pipe_depth`` calls may be outstanding: wait for call i - pipe_depth before issuing call i."""
         def hp(t):
             return ctypes.c_void_p(t.data_ptr()) if t is not None else None
         stream = torch.cuda.current_stream(self.device).cuda_stream
@@ -165,6 +166,11 @@ class BatchedNuclearPlantSimulator:
 
     def wait(self, ticket: int) -> None:
         _clib.check(self.L.nps_wait(self._h, int(ticket)))
+
+    @property
+    def pipe_depth(self) -> int:
+        """Launches step_host_async may have outstanding; tickets are handed out round-robin over this many slots."""
+        return int(self.L.nps_pipe_depth())
 
     def get_observation(self) -> torch.Tensor:
         stream = torch.cuda.current_stream(self.device).cuda_stream

@@ -11,6 +11,8 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <cstdlib>
+#include <cstdio>
 #include <vector>
 #include <algorithm>
 #include <cmath>
@@ -48,12 +50,15 @@ struct nps_handle {
     Threshold* d_thresholds = nullptr; int n_thresholds = 0; int n_live_thresholds = 0;
     int32_t* d_logged = nullptr; int n_logged = 0;
     int32_t* d_gather_fields = nullptr; double* d_gather_out = nullptr; int gather_cap = 0;
-    // nps_step_host_async: two staging sets so the host->device copy of launch i+1 overlaps the kernel of launch i
+    // nps_step_host_async: NPS_PIPE_DEPTH staging sets, so the host->device copy of a launch is issued several
+    // kernels ahead of its use (a sporadically slow PCIe transfer then costs nothing) and overlaps the running kernel
     struct Pipe {
         int8_t* d_action = nullptr; double* d_mag = nullptr; double* d_noise = nullptr; double* d_setpoint = nullptr;
         double* d_obs = nullptr; double* d_reward = nullptr; uint8_t* d_done = nullptr;
         cudaEvent_t in_done = nullptr, kernel_done = nullptr, out_done = nullptr;
-    } pipe[2];
+        cudaEvent_t t_in0 = nullptr, t_k0 = nullptr;   // NPS_PIPE_TRACE=1: timed events around the input copy and the kernel
+    } pipe[NPS_PIPE_DEPTH];
+    bool pipe_trace = false;
     cudaStream_t copy_stream = nullptr, out_stream = nullptr;   // host->device and device->host on separate streams
     int pipe_k = 0; int64_t pipe_count = 0;
 };
@@ -392,9 +397,13 @@ static int ensure_pipe(nps_handle* h, int k) {
             NPS_CUDA(cudaMalloc(&q.d_obs, (size_t)NPS_OBS_DIM * h->n * sizeof(double)));
             NPS_CUDA(cudaMalloc(&q.d_reward, (size_t)h->n * sizeof(double)));
             NPS_CUDA(cudaMalloc(&q.d_done, (size_t)h->n));
-            NPS_CUDA(cudaEventCreateWithFlags(&q.in_done, cudaEventDisableTiming));
-            NPS_CUDA(cudaEventCreateWithFlags(&q.kernel_done, cudaEventDisableTiming));
-            NPS_CUDA(cudaEventCreateWithFlags(&q.out_done, cudaEventDisableTiming));
+            const char* tr = getenv("NPS_PIPE_TRACE");
+            h->pipe_trace = tr && tr[0] == '1';
+            const unsigned fl = h->pipe_trace ? cudaEventDefault : cudaEventDisableTiming;
+            NPS_CUDA(cudaEventCreateWithFlags(&q.in_done, fl));
+            NPS_CUDA(cudaEventCreateWithFlags(&q.kernel_done, fl));
+            NPS_CUDA(cudaEventCreateWithFlags(&q.out_done, fl));
+            if (h->pipe_trace) { NPS_CUDA(cudaEventCreate(&q.t_in0)); NPS_CUDA(cudaEventCreate(&q.t_k0)); }
         }
     }
     h->pipe_k = k;
@@ -409,17 +418,19 @@ int nps_step_host_async(nps_handle* h, double* d_state, const int8_t* h_action, 
     NPS_CUDA(cudaSetDevice(h->device));
     if (ensure_pipe(h, k_substeps)) return -1;
     cudaStream_t s = (cudaStream_t)cuda_stream;
-    const int slot = (int)(h->pipe_count++ & 1);
+    const int slot = (int)(h->pipe_count++ % NPS_PIPE_DEPTH);
     nps_handle::Pipe& q = h->pipe[slot];
     const size_t kn = (size_t)k_substeps * h->n;
-    // the staging set may still be read by the launch issued two calls ago
+    // the staging set may still be read by the launch issued NPS_PIPE_DEPTH calls ago
     NPS_CUDA(cudaStreamWaitEvent(h->copy_stream, q.kernel_done, 0));
+    if (h->pipe_trace) NPS_CUDA(cudaEventRecord(q.t_in0, h->copy_stream));
     if (h_action) NPS_CUDA(cudaMemcpyAsync(q.d_action, h_action, kn, cudaMemcpyHostToDevice, h->copy_stream));
     if (h_magnitude) NPS_CUDA(cudaMemcpyAsync(q.d_mag, h_magnitude, kn * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
     if (h_noise) NPS_CUDA(cudaMemcpyAsync(q.d_noise, h_noise, kn * NPS_NOISE_PER_STEP * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
     if (h_setpoint) NPS_CUDA(cudaMemcpyAsync(q.d_setpoint, h_setpoint, kn * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
     NPS_CUDA(cudaEventRecord(q.in_done, h->copy_stream));
     NPS_CUDA(cudaStreamWaitEvent(s, q.in_done, 0));
+    if (h->pipe_trace) NPS_CUDA(cudaEventRecord(q.t_k0, s));
     if (nps_step(h, d_state, h_action ? q.d_action : nullptr, h_magnitude ? q.d_mag : nullptr, h_noise ? q.d_noise : nullptr,
                  h_setpoint ? q.d_setpoint : nullptr, k_substeps, h_obs ? q.d_obs : nullptr, h_reward ? q.d_reward : nullptr,
                  h_done ? q.d_done : nullptr, cuda_stream)) return -1;
@@ -433,9 +444,20 @@ int nps_step_host_async(nps_handle* h, double* d_state, const int8_t* h_action, 
     return slot;
 }
 
+int nps_pipe_depth(void) { return NPS_PIPE_DEPTH; }
+
 int nps_wait(nps_handle* h, int ticket) {
-    if (!h || ticket < 0 || ticket > 1 || !h->pipe[ticket].out_done) return fail("nps_wait: bad ticket");
+    if (!h || ticket < 0 || ticket >= NPS_PIPE_DEPTH || !h->pipe[ticket].out_done) return fail("nps_wait: bad ticket");
     NPS_CUDA(cudaEventSynchronize(h->pipe[ticket].out_done));
+    if (h->pipe_trace) {   // where one pipelined step spent its time on the device
+        nps_handle::Pipe& q = h->pipe[ticket];
+        float copy_ms = 0, gap_ms = 0, kern_ms = 0, out_ms = 0;
+        cudaEventElapsedTime(&copy_ms, q.t_in0, q.in_done);
+        cudaEventElapsedTime(&gap_ms, q.in_done, q.t_k0);
+        cudaEventElapsedTime(&kern_ms, q.t_k0, q.kernel_done);
+        cudaEventElapsedTime(&out_ms, q.kernel_done, q.out_done);
+        fprintf(stderr, "[nps pipe] slot %d in %.2f gap %.2f kernel %.2f out %.2f ms\n", ticket, copy_ms, gap_ms, kern_ms, out_ms);
+    }
     return 0;
 }
 

@@ -267,16 +267,18 @@ def test_cuda_scalar_facade_runs_maintenance_scenario(tmp_path):
 
 
 def test_step_host_async_equals_step_host():
-    """The pipelined host-buffer entry point (two launches in flight) produces the same state and outputs as the
-    synchronous one, step for step."""
+    """The pipelined host-buffer entry point (pipe_depth launches in flight) produces the same state and outputs as
+    the synchronous one, step for step."""
     import torch
     from nuclear_sim_b200 import load_snapshot
     from nuclear_sim_b200 import scenarios as sc
-    n, k, steps = 2048, 3, 5
+    n, k, steps = 2048, 3, 11
     s0, params = load_snapshot("pwr3000_reactor_dt1")
     pid = np.arange(n)
     st = sc.randomized_states(s0, pid)
     a, b = _sim(st, params), _sim(st, params)
+    D = b.pipe_depth
+    assert D >= 2
     pin = lambda t: t.pin_memory()
     acts = [pin(torch.from_numpy(sc.load_following_inputs(pid, i * k, k)[0])) for i in range(steps)]
     mags = [pin(torch.from_numpy(sc.load_following_inputs(pid, i * k, k)[1])) for i in range(steps)]
@@ -287,10 +289,10 @@ def test_step_host_async_equals_step_host():
         a.step_host(acts[i], mags[i], noise[i], None, k, *out_a[i])
     tickets = []
     for i in range(steps):
-        if i >= 2:
-            b.wait(tickets[i - 2])
+        if i >= D:
+            b.wait(tickets[i - D])
         tickets.append(b.step_host_async(acts[i], mags[i], noise[i], None, k, *out_b[i]))
-    for t in tickets[-2:]:
+    for t in tickets[-D:]:
         b.wait(t)
     torch.cuda.synchronize()
     for i in range(steps):
