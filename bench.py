@@ -34,12 +34,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 PLANTS_PER_GPU = 65536
-SUBSTEPS = 32
+SUBSTEPS = 64                        # fused substeps per launch (profiles/r01_tuning_variants.txt (20): 32 / 64 / 128)
 FLOP_PER_PLANT_STEP = 2.0e4          # SURVEY.md §8d canonical figure (FP64 flop-equivalents)
 METRIC = "plant-steps/sec"
 UNIT = "plant-steps/s"
 WORKLOAD = ("cfg3: 65,536 plants per GPU, randomized ICs, reactor heat source, load-following/power-ramp "
-            "rod + feedwater actions, dt=1.0, 32 fused substeps per launch")
+            f"rod + feedwater actions, dt=1.0, {SUBSTEPS} fused substeps per launch")
 
 
 def _n_live_fields():
@@ -187,7 +187,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--plants-per-gpu", type=int, default=PLANTS_PER_GPU)
@@ -273,7 +273,7 @@ def main():
     value = world * n * ksub * K / (t_ms * 1e-3)
 
     # ------------------------------------------------------------------ end-to-end arm (host buffers through the C ABI)
-    # Every step: pinned host inputs -> device, 32 substeps, observation/reward/done -> pinned host, and the host reads
+    # Every step: pinned host inputs -> device, the fused substeps, observation/reward/done -> pinned host, and the host reads
     # the step's reward.  nps_step_host_async keeps up to D launches in flight: the input copies of later steps overlap
     # the kernel of step i, and the host consumes step i's result while the next steps run.
     sim.reset()
