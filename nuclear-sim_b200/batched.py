@@ -199,6 +199,11 @@ class BatchedNuclearPlantSimulator:
     def observe_plant(self, plant: int) -> np.ndarray:
         return self.get_observation()[plant].cpu().numpy().copy()
 
+    def reward_plant(self, plant: int) -> float:
+        """calculate_reward() of one plant's current state (nps_observe fills obs and reward together)."""
+        self.get_observation()
+        return float(self._reward[plant].item())
+
     def reset_plant(self, plant: int) -> None:
         self.slab[:, plant] = self._initial[:, plant]
 

@@ -347,10 +347,32 @@ class NuclearPlantSimulator:
     def get_observation(self) -> np.ndarray:
         return self._engine.observe_plant(self._p)
 
+    def calculate_reward(self, secondary_result: dict = None) -> float:
+        """sim.py:500-544 on the current state.  Called by hand it is the primary-side reward unless the caller passes a
+        step's secondary result, exactly as in the reference; step() returns the full reward computed on the device."""
+        s = self.state
+        base = -abs(s.power_level - 100) / 100
+        if s.fuel_temperature > 800:
+            base += -(s.fuel_temperature - 800) / 100
+        else:
+            base += 0
+        base += -(s.coolant_pressure - 16) if s.coolant_pressure > 16 else 0
+        base += -100 if s.scram_status else 0
+        if secondary_result is None:
+            return base
+        sec = (secondary_result["thermal_efficiency"] - 0.30) * 10
+        sec += -abs(secondary_result["electrical_power_mw"] - self.load_demand / 100.0 * 1100.0) / 100
+        p_sg = secondary_result["sg_avg_pressure"]
+        sec += -abs(p_sg - 6.895) * 5 if (p_sg < 5.0 or p_sg > 8.0) else 0
+        p_c = secondary_result["condenser_pressure"]
+        sec += -(p_c - 0.007) * 100 if p_c > 0.01 else 0
+        return base + sec * 0.5
+
     def reset(self, start_at_steady_state: bool = True) -> np.ndarray:
         self._engine.reset_plant(self._p)
         self._cache = None
         self._elapsed_minutes = 0.0
+        self.time = 0.0          # sim.py:573 (the reference, too, only has this attribute after a reset)
         if self.state_manager is not None:
             self.state_manager.clear_data()
             self.state_manager.current_datetime = self.state_manager.start_datetime

@@ -175,6 +175,9 @@ class OracleSim:
     def observe_plant(self, plant):
         return self._observe()[0][plant]
 
+    def reward_plant(self, plant):
+        return float(self._observe()[1][plant])
+
     def reset_plant(self, plant):
         self.st[plant] = self._initial[plant]
 
