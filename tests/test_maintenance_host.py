@@ -172,3 +172,25 @@ def test_batched_timing_sweep_and_optimizer():
                                                 tolerance_hours=5.0 / 60.0, component_id="FWP-1", n_candidates=24,
                                                 engine_factory=fac)
     assert abs(t - 2.0) <= 5.0 / 60.0 and sweeps <= 2 and 58.1 < v < level0
+
+
+def test_batch_optimize_timing_several_actions_in_one_batch():
+    """ICOptimizer.batch_optimize_timing as batched sweeps (CPU stand-in engine): two actions with different fields and
+    targets share one batch; each group answers exactly what a dedicated single-action sweep answers."""
+    from nuclear_sim_b200 import optimize as O
+    g = np.load(os.path.join(U.GOLDEN, "maint_oil_top_off.npz"), allow_pickle=False)
+    cfg = json.loads(str(g["log"]))["maintenance_system"]
+    fac = lambda st, p, dev: U.OracleSim(st, p)
+    f1, f2 = "fw.pump[0].lub.oil_level", "fw.pump[1].lub.oil_level"
+    v1, v2 = np.array([58.5, 59.5, 60.5]), np.array([59.0, 60.0])
+    both = O.trigger_time_sweep_multi(g["state0"], g["params"], cfg, [(f1, v1, "oil_top_off", "FWP-1"),
+                                                                       (f2, v2, "oil_top_off", "FWP-2")], 5.0, engine_factory=fac)
+    solo1 = O.trigger_time_sweep(g["state0"], g["params"], cfg, f1, v1, "oil_top_off", 5.0, component_id="FWP-1", engine_factory=fac)
+    solo2 = O.trigger_time_sweep(g["state0"], g["params"], cfg, f2, v2, "oil_top_off", 5.0, component_id="FWP-2", engine_factory=fac)
+    np.testing.assert_array_equal(both[0], solo1)
+    np.testing.assert_array_equal(both[1], solo2)
+    res = O.batch_optimize_timing(g["state0"], g["params"], cfg,
+                                  {"oil_top_off": (f1, 58.1, 62.0, 2.0, "FWP-1")}, tolerance_hours=5.0 / 60.0,
+                                  n_candidates=24, engine_factory=fac)
+    v, t, sweeps = res["oil_top_off"]
+    assert abs(t - 2.0) <= 5.0 / 60.0 and sweeps <= 2
