@@ -48,6 +48,18 @@ def _n_live_fields():
     return sum(1 for ln in open(path) if ln.strip() and not ln.startswith("#"))
 
 
+def _measured_issue_fraction(n, ksub, launch_s, sm_mhz):
+    """Share of the SMs' issue slots (148 SMs x 4 warp-instructions per cycle) the step kernel uses: executed
+    warp-instructions per plant-substep from the committed ncu capture x this run's plants and launch time."""
+    path = os.path.join(ROOT, "profiles", "r01_step_kernel_traffic.json")
+    try:
+        t = json.load(open(path))
+        per = t["warp_instructions_executed"] / (t["plants"] * t["substeps"])
+        return per * n * ksub / (launch_s * 148 * 4 * sm_mhz * 1e6)
+    except Exception:
+        return None
+
+
 def _measured_traffic(n, ksub):
     """DRAM bytes per launch of nps_step_kernel from the committed ncu capture (profiles/r01_step_kernel_traffic.json),
     scaled per plant-substep; None when the capture is for a different build."""
@@ -348,10 +360,13 @@ def main():
                          "traffic": traffic, "peak_source": peak_src, "kernel": "nps_step_kernel",
                          "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_launch_s * 1e3,
                          "algorithmic_bytes_per_plant_step": bytes_per_launch / (n * ksub), "n_live_fields": n_live,
-                         "note": "per-substep streaming of the live state (it cannot be resident: 4.7 MB per SM); "
-                                 "frac_if_state_resident is the K-amortised figure of SURVEY 8d",
+                         "note": "per-substep streaming of the live state (it cannot be resident: 4.8 MB per SM); "
+                                 "frac_if_state_resident is the K-amortised figure of SURVEY 8d; issue_slot_frac is the "
+                                 "share of the issue roofline (148 SMs x 4 warp-instructions/cycle), the bound that "
+                                 "actually binds this scalar FP64 path (DESIGN.md 5)",
                          "frac_if_state_resident": resident_bytes_per_launch / avg_launch_s / 1e9 / peak,
                          "dram_gbs_actual": (traffic / avg_launch_s / 1e9) if traffic else None,
+                         "issue_slot_frac": _measured_issue_fraction(n, ksub, avg_launch_s, clocks["sm_mhz"] or 1965.0),
                          "fp64_tflops_at_2e4_flop_per_plant_step": fp64_tflops,
                          "fp64_frac_of_37_tflops": fp64_tflops / 37.0},
         }

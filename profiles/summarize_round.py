@@ -40,6 +40,7 @@ def main():
     r, w = float(g("dram__bytes_read.sum")) * 1e9, float(g("dram__bytes_write.sum")) * 1e9
     json.dump({"kernel": "nps_step_kernel<448,1>", "plants": n, "substeps": k, "dram_bytes_read": r, "dram_bytes_write": w,
                "duration_ms_under_ncu": float(g("gpu__time_duration.sum")),
+               "warp_instructions_executed": float(g("smsp__inst_executed.sum")),
                "source": f"profiles/{TAG}_ncu_full_step_kernel_final.csv (ncu --set full, one launch)"},
               open(os.path.join(P, f"{TAG}_step_kernel_traffic.json"), "w"), indent=1)
     shutil.copy(os.path.join(G, "launches.csv"), os.path.join(P, f"{TAG}_launches_bench_final.csv"))
