@@ -61,6 +61,7 @@ struct nps_handle {
     bool pipe_trace = false;
     cudaStream_t copy_stream = nullptr, out_stream = nullptr;   // host->device and device->host on separate streams
     int pipe_k = 0; int64_t pipe_count = 0;
+    int n_sms = 148; bool log_row_tile_only = false;   // NPS_LOG_ROW_TILE=1 forces the shared-memory tile kernel
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -237,6 +238,91 @@ __global__ void nps_log_row_kernel(const double* __restrict__ slab, const int32_
 }
 
 // ------------------------------------------------------------------------------------------------
+// trajectory ring-buffer row, TMA path (sm_100a): a logged field of all plants is one contiguous row of the slab, so a
+// ring row is n_logged row copies.  Each CTA is one warp whose lane 0 drives a kLogStages-deep pipeline of
+// cp.async.bulk transfers: global -> shared (completion on an mbarrier) and shared -> global (bulk async-group); no
+// thread touches the data.  Work items are (field, 16 KB chunk of plants), dealt round-robin to a persistent grid of
+// kLogCtasPerSm CTAs per SM.  Needs 16-byte aligned rows, i.e. an even plant count; otherwise nps_log_row_kernel runs.
+// ------------------------------------------------------------------------------------------------
+constexpr int kLogStageBytes = 16384;
+constexpr int kLogStages = 4;
+constexpr int kLogCtasPerSm = 3;
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(32) nps_log_row_tma_kernel(const double* __restrict__ slab, const int32_t* __restrict__ fields,
+                                                             int n_logged, double* __restrict__ ring_row, int64_t n,
+                                                             int chunks_per_field) {
+    extern __shared__ __align__(128) unsigned char stage_mem[];
+    __shared__ uint64_t bar[kLogStages];
+    if (threadIdx.x != 0) return;                      // one driver thread; the copies are done by the TMA unit
+    for (int s = 0; s < kLogStages; ++s) mbar_init(&bar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const int64_t total = (int64_t)n_logged * chunks_per_field;
+    const int64_t first = blockIdx.x, stride = gridDim.x;
+    const int64_t count = (total > first) ? (total - first + stride - 1) / stride : 0;
+    constexpr int64_t kChunkPlants = kLogStageBytes / 8;
+    auto locate = [&](int64_t k, const double*& src, double*& dst, uint32_t& bytes) {
+        const int64_t item = first + k * stride;
+        const int f = (int)(item / chunks_per_field);
+        const int64_t p0 = (item - (int64_t)f * chunks_per_field) * kChunkPlants;
+        const int64_t np = (n - p0 < kChunkPlants) ? (n - p0) : kChunkPlants;
+        src = slab + (int64_t)fields[f] * n + p0;
+        dst = ring_row + (int64_t)f * n + p0;
+        bytes = (uint32_t)(np * 8);
+    };
+    auto load = [&](int64_t k) {
+        const double* src; double* dst; uint32_t bytes;
+        locate(k, src, dst, bytes);
+        const int s = (int)(k % kLogStages);
+        mbar_expect_tx(&bar[s], bytes);
+        bulk_g2s(stage_mem + (size_t)s * kLogStageBytes, src, bytes, &bar[s]);
+    };
+    for (int64_t k = 0; k < count && k < kLogStages; ++k) load(k);
+    for (int64_t k = 0; k < count; ++k) {
+        const int s = (int)(k % kLogStages);
+        mbar_wait(&bar[s], (uint32_t)((k / kLogStages) & 1));
+        const double* src; double* dst; uint32_t bytes;
+        locate(k, src, dst, bytes);
+        bulk_s2g(dst, stage_mem + (size_t)s * kLogStageBytes, bytes);
+        // refill the stage whose store was issued one iteration ago (its shared-memory read has had time to finish)
+        if (k >= 1 && k - 1 + kLogStages < count) {
+            bulk_wait_read<1>();
+            load(k - 1 + kLogStages);
+        }
+    }
+    bulk_wait_read<0>();
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before the kernel ends
+}
+
+// ------------------------------------------------------------------------------------------------
 // maintenance effects: one thread per affected plant applies that plant's requests in order.  Sparse by nature
 // (work orders fire for a handful of plants per check), so the whole record is loaded and stored.
 // ------------------------------------------------------------------------------------------------
@@ -284,6 +370,9 @@ int nps_create(int64_t n_plants, int device, nps_handle** out) {
     nps_handle* h = new nps_handle();
     h->n = n_plants; h->device = device;
     std::memset(&h->params, 0, sizeof(PlantParams));
+    cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, device);
+    { const char* e = getenv("NPS_LOG_ROW_TILE"); h->log_row_tile_only = e && e[0] == '1'; }
+    NPS_CUDA(cudaFuncSetAttribute(nps_log_row_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLogStages * kLogStageBytes));
     // the step kernel keeps one PlantState per thread in local memory
 #if defined(NPS_STEP_BLOCK)
     NPS_CUDA(cudaFuncSetCacheConfig(nps_step_kernel<NPS_STEP_BLOCK, NPS_STEP_MINBLOCKS>, cudaFuncCachePreferL1));
@@ -524,8 +613,18 @@ int nps_log_row(nps_handle* h, const double* d_state, double* d_ring, int64_t ri
     if (!h || !d_state || !d_ring || ring_rows <= 0) return fail("nps_log_row: bad arguments");
     if (h->n_logged == 0) return fail("nps_log_row: no logged fields set");
     double* row = d_ring + (write_index % ring_rows) * (int64_t)h->n_logged * h->n;
-    dim3 grid((unsigned)((h->n + kLogTilePlants - 1) / kLogTilePlants), (unsigned)((h->n_logged + kLogTileFields - 1) / kLogTileFields));
-    nps_log_row_kernel<<<grid, kLogTilePlants, 0, (cudaStream_t)cuda_stream>>>(d_state, h->d_logged, h->n_logged, row, h->n);
+    const bool aligned = (h->n % 2 == 0) && ((reinterpret_cast<uintptr_t>(d_state) | reinterpret_cast<uintptr_t>(d_ring)) % 16 == 0);
+    if (aligned && !h->log_row_tile_only) {
+        const int chunks = (int)((h->n * 8 + kLogStageBytes - 1) / kLogStageBytes);
+        const int64_t items = (int64_t)h->n_logged * chunks;
+        int grid = h->n_sms * kLogCtasPerSm;
+        if (grid > items) grid = (int)items;
+        nps_log_row_tma_kernel<<<grid, 32, kLogStages * kLogStageBytes, (cudaStream_t)cuda_stream>>>(
+            d_state, h->d_logged, h->n_logged, row, h->n, chunks);
+    } else {
+        dim3 grid((unsigned)((h->n + kLogTilePlants - 1) / kLogTilePlants), (unsigned)((h->n_logged + kLogTileFields - 1) / kLogTileFields));
+        nps_log_row_kernel<<<grid, kLogTilePlants, 0, (cudaStream_t)cuda_stream>>>(d_state, h->d_logged, h->n_logged, row, h->n);
+    }
     NPS_CUDA(cudaGetLastError());
     return 0;
 }

@@ -165,6 +165,32 @@ def test_threshold_flags_and_ring_buffer():
     np.testing.assert_array_equal(log[-1, 0], sim.state.power_level.cpu().numpy())
 
 
+@pytest.mark.parametrize("n", [2, 1000, 2050, 4098, 1001, 4097])
+def test_ring_buffer_row_is_a_bitwise_gather(n):
+    """nps_log_row on both of its kernels: even plant counts take the TMA bulk-copy pipeline (2050 / 4098: a ragged last
+    16 KB chunk; 2: a 16-byte transfer), odd ones the shared-memory tile kernel.  Every logged field, every plant, every
+    ring slot must be the slab's bits; the ring wraps after `rows` writes."""
+    import torch
+    from nuclear_sim_b200 import field_names, load_snapshot
+    s0, params = load_snapshot("pwr3000_oil_top_off_dt5")
+    rng = np.random.RandomState(n)
+    st = np.tile(s0, (n, 1)) * (1.0 + 1e-3 * rng.standard_normal((n, 1)))
+    sim = _sim(st, params)
+    names = list(field_names())
+    picked = [names[i] for i in sorted(rng.choice(len(names), size=97, replace=False))]
+    sim.set_logged_fields(picked, ring_rows=3)
+    want = []
+    for step in range(5):
+        sim.step()
+        sim.log_row()
+        want.append(np.stack([sim.state[f].cpu().numpy() for f in picked]))
+    torch.cuda.synchronize()
+    log = sim.drain_log()
+    assert log.shape == (3, 97, n)
+    for got, ref in zip(log, want[-3:]):
+        np.testing.assert_array_equal(got.view(np.uint64), ref.view(np.uint64))
+
+
 # ---- maintenance: flag kernel -> work orders -> effects on the device state --------------------------------------
 MAINT_SCENARIOS = ["oil_top_off", "tsp_chemical_cleaning", "oil_change", "scale_removal"]
 
