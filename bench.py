@@ -196,6 +196,29 @@ def run_reference(args):
     return 0
 
 
+def _bind_to_gpu_numa_node(torch, local: int):
+    """Run this rank on the CPUs of its GPU's NUMA node, BEFORE the pinned staging buffers are allocated (first touch
+    places them on that node): with eight ranks on a two-socket host the e2e arm otherwise pulls half of its input
+    stream across the socket interconnect.  No-op when the platform does not expose the topology (numa_node = -1)."""
+    try:
+        p = torch.cuda.get_device_properties(local)
+        bdf = f"{getattr(p, 'pci_domain_id', 0):04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus |= set(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -224,6 +247,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_node = _bind_to_gpu_numa_node(torch, local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -350,7 +374,7 @@ def main():
                        "plants_per_gpu": n, "substeps_per_step": ksub, "n_state_fields": N_STATE,
                        "state_bytes_per_gpu": state_bytes,
                        "l2": "inputs larger than L2 (state slab %.0f MB per GPU is streamed every launch)" % (state_bytes / 1e6),
-                       "mean_power_percent_after_run": mean_power},
+                       "mean_power_percent_after_run": mean_power, "rank0_numa_node": numa_node},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "mean_reward_readback": loss_check},
             "gpu_launches": launches,
