@@ -65,3 +65,22 @@ def test_product_does_not_touch_oracle():
                 for line in text.splitlines():
                     if re.match(r"\s*(from|import)\s+oracle\b", line):
                         raise AssertionError(f"{f} imports oracle: {line}")
+
+
+def test_plain_c_example_compiles_and_links(tmp_path):
+    """examples/step_from_c.c builds against include/nps_b200.h and links against the in-tree library with nothing but
+    gcc and the CUDA runtime: the boundary really is a C ABI (no compute call here - there is no GPU)."""
+    import os
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib_dir = os.path.join(root, "nuclear-sim_b200", "_lib")
+    if not (shutil.which("gcc") and os.path.exists("/usr/local/cuda/include/cuda_runtime_api.h")
+            and os.path.exists(os.path.join(lib_dir, "libnps_b200.so"))):
+        import pytest
+        pytest.skip("gcc / CUDA headers / built library not present")
+    exe = str(tmp_path / "step_from_c")
+    subprocess.check_call(["gcc", "-O2", "-Wall", "-Werror", "-I", os.path.join(root, "include"), "-I", "/usr/local/cuda/include",
+                           os.path.join(root, "examples", "step_from_c.c"), "-o", exe, "-L", lib_dir, "-lnps_b200",
+                           "-L", "/usr/local/cuda/lib64", "-lcudart", f"-Wl,-rpath,{lib_dir}"])
+    assert os.path.getsize(exe) > 0

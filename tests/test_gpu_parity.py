@@ -2,6 +2,8 @@
 (b) the host oracle on seeded batches; plus size-independent properties at BASELINE sizes."""
 import ctypes
 
+import os
+
 import numpy as np
 import pytest
 
@@ -374,3 +376,28 @@ def test_cuda_batched_timing_sweep():
     hrs = O.trigger_time_sweep(g["state0"], g["params"], log["maintenance_system"], fld, vals, "oil_top_off", 5.0, component_id="FWP-1")
     assert hrs[int(np.nonzero(vals == level0)[0][0])] == log["created"][0]["t"] / 60.0
     assert not np.isnan(hrs).any() and np.all(np.diff(hrs) >= 0) and hrs[-1] > hrs[0]
+
+
+def test_c_abi_from_plain_c(tmp_path):
+    """examples/step_from_c.c (gcc, no Python / torch on its side) steps 96 identical plants through the C ABI; the state,
+    observation and reward it writes are the Python host API's, bit for bit."""
+    import subprocess
+    from nuclear_sim_b200 import load_snapshot
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "step_from_c")
+    lib_dir = os.path.join(root, "nuclear-sim_b200", "_lib")
+    subprocess.check_call(["gcc", "-O2", "-I", os.path.join(root, "include"), "-I", "/usr/local/cuda/include",
+                           os.path.join(root, "examples", "step_from_c.c"), "-o", exe, "-L", lib_dir, "-lnps_b200",
+                           "-L", "/usr/local/cuda/lib64", "-lcudart", f"-Wl,-rpath,{lib_dir}"])
+    s0, params = load_snapshot("pwr3000_reactor_dt1")
+    np.concatenate([s0, params]).astype(np.float64).tofile(str(tmp_path / "plant.bin"))
+    n, launches, k = 96, 3, 5
+    out = subprocess.run([exe, str(tmp_path / "plant.bin"), str(n), str(launches), str(k), str(tmp_path / "out.bin")],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    got = np.fromfile(str(tmp_path / "out.bin"))
+    sim = _sim(np.tile(s0, (n, 1)), params)
+    for _ in range(launches):
+        res = sim.step(K=k)
+    want = np.concatenate([sim.state_numpy()[0], res["observation"][0].cpu().numpy(), [float(res["reward"][0])]])
+    np.testing.assert_array_equal(got.view(np.uint64), want.view(np.uint64))
