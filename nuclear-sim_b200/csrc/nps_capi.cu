@@ -48,6 +48,7 @@ struct nps_handle {
     double* d_obs = nullptr; double* d_reward = nullptr; uint8_t* d_done = nullptr;
     int staged_k = 0;
     Threshold* d_thresholds = nullptr; int n_thresholds = 0; int n_live_thresholds = 0;
+    int32_t* d_word_start = nullptr;   // live rows are sorted by table row: [word w] = d_thresholds[d_word_start[w] .. d_word_start[w + 1])
     int32_t* d_logged = nullptr; int n_logged = 0;
     int32_t* d_gather_fields = nullptr; double* d_gather_out = nullptr; int gather_cap = 0;
     // nps_step_host_async: NPS_PIPE_DEPTH staging sets, so the host->device copy of a launch is issued several
@@ -145,7 +146,7 @@ __global__ void nps_observe_kernel(const double* __restrict__ slab, const __grid
 }
 
 // ------------------------------------------------------------------------------------------------
-// threshold flag kernel: one thread per plant evaluates every threshold row; cooldown stamps in SoA;
+// threshold flag kernel: one thread per (plant, flag word) evaluates the live threshold rows of that word; cooldown stamps in SoA;
 // __ballot_sync compacts "this plant fired something" into one word per warp for the host drain.
 // ------------------------------------------------------------------------------------------------
 // Logged columns that are pure functions of carried fields.  code = -(2 + 4 * kind + unit):
@@ -166,52 +167,59 @@ __device__ __forceinline__ double threshold_derived(const double* __restrict__ s
 
 constexpr int kThrRowsPerThread = 8;
 __global__ void __launch_bounds__(128)
-nps_threshold_kernel(const double* __restrict__ slab, const Threshold* __restrict__ live, int n_live, int time_field,
-                     double* __restrict__ last_fired, uint32_t* __restrict__ flags, uint32_t* __restrict__ any_warp, int64_t n) {
-    // thread = (plant, group of 8 LIVE rows).  Inert rows never reach the device loop; the 8 cooldown stamps and the 8
-    // values of a group are independent loads issued back to back, so the kernel streams instead of chasing 2 x 90
-    // dependent loads per plant (that version ran at 11 % of the HBM roofline, this one is measured in profiles/).
+nps_threshold_kernel(const double* __restrict__ slab, const Threshold* __restrict__ live, const int32_t* __restrict__ word_start,
+                     int time_field, double* __restrict__ last_fired, uint32_t* __restrict__ flags,
+                     uint32_t* __restrict__ any_warp, int64_t n) {
+    // thread = (plant, flag word).  A flag word covers 32 consecutive rows of the caller's table; the thread evaluates
+    // the LIVE rows among them (inert rows never reach the device) and OWNS that word: one plain coalesced store, no
+    // atomics and no clearing pass.  The rows of the word are staged in shared memory once per block; the cooldown
+    // stamps and values of 8 rows at a time are independent loads issued back to back, so the kernel streams instead of
+    // chasing 2 x 90 dependent loads per plant (that first version ran at 11 % of the HBM roofline; profiles/).
+    __shared__ Threshold rows[32];
+    const int w = blockIdx.y;
+    const int ws = word_start[w], cnt = word_start[w + 1] - ws;
+    if ((int)threadIdx.x < cnt) rows[threadIdx.x] = live[ws + threadIdx.x];
+    __syncthreads();
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int r0 = blockIdx.y * kThrRowsPerThread;
-    bool any = false;
-    if (p < n) {
+    uint32_t bits = 0;
+    if (p < n && cnt > 0) {
         const double now = slab[(int64_t)time_field * n + p];
-        double last[kThrRowsPerThread], val[kThrRowsPerThread];
+        for (int j0 = 0; j0 < cnt; j0 += kThrRowsPerThread) {
+            double last[kThrRowsPerThread], val[kThrRowsPerThread];
 #pragma unroll
-        for (int j = 0; j < kThrRowsPerThread; ++j) {
-            const int r = r0 + j;
-            if (r < n_live) {
-                const Threshold th = live[r];
-                last[j] = last_fired[(int64_t)th.row * n + p];
-                val[j] = (th.field >= 0) ? slab[(int64_t)th.field * n + p] : threshold_derived(slab, n, p, th.field);
+            for (int j = 0; j < kThrRowsPerThread; ++j) {
+                if (j0 + j < cnt) {
+                    const Threshold& th = rows[j0 + j];
+                    last[j] = last_fired[(int64_t)th.row * n + p];
+                    val[j] = (th.field >= 0) ? slab[(int64_t)th.field * n + p] : threshold_derived(slab, n, p, th.field);
+                }
             }
-        }
 #pragma unroll
-        for (int j = 0; j < kThrRowsPerThread; ++j) {
-            const int r = r0 + j;
-            if (r >= n_live) break;
-            const Threshold th = live[r];
-            // _is_threshold_in_cooldown: state_manager.py:1267-1305 (checked before the value is looked at)
-            if ((now - last[j]) < th.cooldown) continue;
-            const double v = val[j];
-            bool fire;
-            switch (th.cmp) {   // _check_threshold_condition: state_manager.py:1412-1442
-                case 0: fire = v > th.value; break;
-                case 1: fire = v < th.value; break;
-                case 2: fire = v >= th.value; break;
-                case 3: fire = v <= th.value; break;
-                case 4: fire = fabs(v - th.value) < 1e-3; break;
-                case 5: fire = fabs(v - th.value) >= 1e-3; break;
-                default: fire = false; break;
-            }
-            if (fire) {
-                last_fired[(int64_t)th.row * n + p] = now;   // _record_threshold_violation_time
-                atomicOr(&flags[(int64_t)(th.row >> 5) * n + p], 1u << (th.row & 31));
-                any = true;
+            for (int j = 0; j < kThrRowsPerThread; ++j) {
+                if (j0 + j >= cnt) break;
+                const Threshold& th = rows[j0 + j];
+                // _is_threshold_in_cooldown: state_manager.py:1267-1305 (checked before the value is looked at)
+                if ((now - last[j]) < th.cooldown) continue;
+                const double v = val[j];
+                bool fire;
+                switch (th.cmp) {   // _check_threshold_condition: state_manager.py:1412-1442
+                    case 0: fire = v > th.value; break;
+                    case 1: fire = v < th.value; break;
+                    case 2: fire = v >= th.value; break;
+                    case 3: fire = v <= th.value; break;
+                    case 4: fire = fabs(v - th.value) < 1e-3; break;
+                    case 5: fire = fabs(v - th.value) >= 1e-3; break;
+                    default: fire = false; break;
+                }
+                if (fire) {
+                    last_fired[(int64_t)th.row * n + p] = now;   // _record_threshold_violation_time
+                    bits |= 1u << (th.row & 31);
+                }
             }
         }
     }
-    const unsigned ballot = __ballot_sync(0xffffffffu, any);
+    if (p < n) flags[(int64_t)w * n + p] = bits;
+    const unsigned ballot = __ballot_sync(0xffffffffu, bits != 0);
     if ((threadIdx.x & 31) == 0 && ballot && any_warp) atomicOr(&any_warp[p >> 5], ballot);
 }
 
@@ -388,7 +396,7 @@ void nps_destroy(nps_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaFree(h->d_setpoint); cudaFree(h->d_action); cudaFree(h->d_mag); cudaFree(h->d_noise);
-    cudaFree(h->d_obs); cudaFree(h->d_reward); cudaFree(h->d_done); cudaFree(h->d_thresholds);
+    cudaFree(h->d_obs); cudaFree(h->d_reward); cudaFree(h->d_done); cudaFree(h->d_thresholds); cudaFree(h->d_word_start);
     cudaFree(h->d_logged); cudaFree(h->d_gather_fields); cudaFree(h->d_gather_out);
     for (auto& q : h->pipe) {
         cudaFree(q.d_action); cudaFree(q.d_mag); cudaFree(q.d_noise); cudaFree(q.d_setpoint);
@@ -564,6 +572,7 @@ int nps_set_thresholds(nps_handle* h, const int32_t* field, const int32_t* compa
     if (!h || n_thresholds < 0) return fail("nps_set_thresholds: bad arguments");
     NPS_CUDA(cudaSetDevice(h->device));
     cudaFree(h->d_thresholds); h->d_thresholds = nullptr; h->n_thresholds = 0;
+    cudaFree(h->d_word_start); h->d_word_start = nullptr;
     if (n_thresholds == 0) return 0;
     std::vector<Threshold> t;      // live rows only (field != -1), each remembering its row index in the caller's table
     for (int i = 0; i < n_thresholds; ++i) {
@@ -573,6 +582,12 @@ int nps_set_thresholds(nps_handle* h, const int32_t* field, const int32_t* compa
     if (!t.empty()) {
         NPS_CUDA(cudaMalloc(&h->d_thresholds, sizeof(Threshold) * t.size()));
         NPS_CUDA(cudaMemcpy(h->d_thresholds, t.data(), sizeof(Threshold) * t.size(), cudaMemcpyHostToDevice));
+        const int n_words = (n_thresholds + 31) / 32;
+        std::vector<int32_t> ws(n_words + 1, 0);
+        for (const Threshold& th : t) ws[th.row / 32 + 1]++;
+        for (int w = 0; w < n_words; ++w) ws[w + 1] += ws[w];
+        NPS_CUDA(cudaMalloc(&h->d_word_start, sizeof(int32_t) * ws.size()));
+        NPS_CUDA(cudaMemcpy(h->d_word_start, ws.data(), sizeof(int32_t) * ws.size(), cudaMemcpyHostToDevice));
     }
     h->n_thresholds = n_thresholds;
     h->n_live_thresholds = (int)t.size();
@@ -585,12 +600,14 @@ int nps_check_thresholds(nps_handle* h, const double* d_state, double* d_last_fi
     if (h->n_thresholds == 0) return fail("nps_check_thresholds: no thresholds set");
     cudaStream_t s = (cudaStream_t)cuda_stream;
     const int n_words = (h->n_thresholds + 31) / 32;
-    NPS_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(uint32_t) * (size_t)n_words * h->n, s));
     if (d_any_warp) NPS_CUDA(cudaMemsetAsync(d_any_warp, 0, sizeof(uint32_t) * (size_t)((h->n + 31) / 32), s));
-    if (h->n_live_thresholds == 0) return 0;
+    if (h->n_live_thresholds == 0) {   // nothing can fire: all flag words are zero
+        NPS_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(uint32_t) * (size_t)n_words * h->n, s));
+        return 0;
+    }
     const int block = 128;
-    dim3 grid((unsigned)((h->n + block - 1) / block), (unsigned)((h->n_live_thresholds + kThrRowsPerThread - 1) / kThrRowsPerThread));
-    nps_threshold_kernel<<<grid, block, 0, s>>>(d_state, h->d_thresholds, h->n_live_thresholds, kTimeMinutesField, d_last_fired,
+    dim3 grid((unsigned)((h->n + block - 1) / block), (unsigned)n_words);   // every flag word is written by its owner
+    nps_threshold_kernel<<<grid, block, 0, s>>>(d_state, h->d_thresholds, h->d_word_start, kTimeMinutesField, d_last_fired,
                                                d_flags, d_any_warp, h->n);
     NPS_CUDA(cudaGetLastError());
     return 0;
