@@ -343,6 +343,34 @@ def main():
     d2h = n * (22 * 8 + 8 + 1)
     loss_check = reward_sum / K
 
+    # the same loop with device-side noise (nps_set_device_rng): only actions and magnitudes travel (9 B per plant-step)
+    sim.reset()
+    sim.set_device_rng(20260118, plant_offset=rank * n)
+    tickets = []
+    for i in range(min(W, D)):
+        tickets.append(sim.step_host_async(acts_h[i], mags_h[i], None, None, ksub, obs_h[i % D], rew_h[i % D], done_h[i % D]))
+    for t_ in tickets:
+        sim.wait(t_)
+    barrier()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tickets = []
+    r0.record()
+    for i in range(K):
+        b = i % D
+        if i >= D:
+            sim.wait(tickets[i - D])
+            reward_sum += float(rew_h[b].mean())
+        tickets.append(sim.step_host_async(acts_h[W + i], mags_h[W + i], None, None, ksub, obs_h[b], rew_h[b], done_h[b]))
+    for i in range(max(0, K - D), K):
+        sim.wait(tickets[i])
+    r1.record()
+    barrier()
+    tr = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+    e2e_rng_value = world * n * ksub * K / (float(tr.item()) * 1e-3)
+    sim.set_device_rng(None)
+
     # ------------------------------------------------------------------ trajectory summaries: the only collective
     summary = torch.stack([sim.state.power_level, sim.state.electrical_power_output, sim.state.fuel_temperature,
                            sim.state.scram_status]).t().contiguous()
@@ -377,6 +405,10 @@ def main():
                        "mean_power_percent_after_run": mean_power, "rank0_numa_node": numa_node},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "mean_reward_readback": loss_check},
+            "e2e_device_rng": {"value": e2e_rng_value, "unit": UNIT, "h2d_bytes_per_step": ksub * n * (1 + 8),
+                               "d2h_bytes_per_step": d2h,
+                               "note": "same pipelined host-buffer loop, the five random draws per plant-step generated "
+                                       "on the device (Philox4x32-10) instead of copied from the host"},
             "gpu_launches": launches,
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
                        "samples": clocks["samples"]},

@@ -62,6 +62,16 @@ int nps_step(nps_handle* h, double* d_state, const int8_t* d_action, const doubl
              const double* d_noise, const double* d_setpoint, int k_substeps, double* d_obs, double* d_reward,
              uint8_t* d_done, void* cuda_stream);
 
+/* Device-side noise.  The reference draws its per-step noise inside its Python objects (constant_heat_source.py:178,
+ * ph_control_system.py:288,409-420); parity runs pass those very streams in d_noise.  A production batch that passes
+ * d_noise == NULL can instead have every (plant, step) draw its five numbers on the device from Philox4x32-10 keyed by
+ * `seed` (counter = (plant_offset + plant, step)): reproducible, independent of batch shape, k_substeps and the number
+ * of GPUs when plant_offset is the rank's first global plant id.  `first_step` is the step index of the next launch;
+ * every launch advances it by k_substeps.  enabled = 0 restores "no noise array = no noise".
+ * nps_device_rng_draws evaluates the same generator on the host (z_heat, z_ph, u0, u1, u2). */
+int nps_set_device_rng(nps_handle* h, int enabled, uint64_t seed, uint64_t plant_offset, uint64_t first_step);
+int nps_device_rng_draws(uint64_t seed, uint64_t plant, uint64_t step, double* out5);
+
 /* Same step with HOST buffers for the per-step inputs and outputs (pinned or pageable): the
  * host->device copies of action/magnitude/noise and the device->host copies of obs/reward/done are
  * issued on the stream inside the call, which returns after they complete. State stays on device. */

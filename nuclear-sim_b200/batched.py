@@ -141,6 +141,13 @@ class BatchedNuclearPlantSimulator:
         self.n_launches += 1
         return {"observation": self._obs.t(), "reward": self._reward, "done": self._done.bool()}
 
+    def set_device_rng(self, seed: Optional[int], plant_offset: int = 0, first_step: int = 0) -> None:
+        """Device-side noise (nps_set_device_rng): with a seed, step(noise=None) draws every plant-step's five random
+        numbers on the GPU (Philox4x32-10, counter = (plant_offset + plant, step)); None switches it off again.
+        Give each rank its first global plant id as plant_offset and the result does not depend on the sharding."""
+        _clib.check(self.L.nps_set_device_rng(self._h, 0 if seed is None else 1, int(seed or 0) & (2 ** 64 - 1),
+                                              int(plant_offset), int(first_step)))
+
     def step_host(self, h_actions, h_magnitudes, h_noise, h_setpoint, K, h_obs, h_reward, h_done) -> None:
         """Reference-facing call with HOST (pinned) per-step buffers: copies in, K substeps, copies out."""
         def hp(t):

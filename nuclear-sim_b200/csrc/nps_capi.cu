@@ -20,6 +20,7 @@
 #include "../../include/nps_b200.h"
 #include "plant/plant_step.h"
 #include "plant/maintenance.h"
+#include "plant/rng.h"
 #include "fields_gen.inc"
 
 using namespace nps;
@@ -37,6 +38,8 @@ constexpr int kNParams = (int)(sizeof(PlantParams) / sizeof(double));
 static_assert(kNState == NPS_GEN_N_STATE, "state.h and fields_gen.inc disagree; rerun the build");
 static_assert(kNParams == NPS_GEN_N_PARAMS, "state.h and fields_gen.inc disagree; rerun the build");
 
+// device-side noise (csrc/plant/rng.h): used when the caller passes no noise array and nps_set_device_rng enabled it
+struct RngConfig { uint64_t seed; uint64_t plant_offset; uint64_t step0; int enabled; int pad; };
 struct Threshold { int field; int cmp; double value; double cooldown; int row; int pad; };
 
 struct nps_handle {
@@ -62,6 +65,7 @@ struct nps_handle {
     bool pipe_trace = false;
     cudaStream_t copy_stream = nullptr, out_stream = nullptr;   // host->device and device->host on separate streams
     int pipe_k = 0; int64_t pipe_count = 0;
+    RngConfig rng = {0, 0, 0, 0, 0};
     int n_sms = 148; bool log_row_tile_only = false;   // NPS_LOG_ROW_TILE=1 forces the shared-memory tile kernel
 };
 
@@ -85,7 +89,7 @@ __global__ void __launch_bounds__(BLOCK, MINBLOCKS)
 nps_step_kernel(double* __restrict__ slab, const __grid_constant__ PlantParams prm, const int8_t* __restrict__ action,
                 const double* __restrict__ magnitude, const double* __restrict__ noise,
                 const double* __restrict__ setpoint, int k_substeps, int64_t n,
-                double* __restrict__ obs, double* __restrict__ reward, uint8_t* __restrict__ done) {
+                double* __restrict__ obs, double* __restrict__ reward, uint8_t* __restrict__ done, const RngConfig rng) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     PlantState st;
@@ -100,6 +104,9 @@ NPS_PRAGMA_UNROLL(NPS_COPY_UNROLL)
         if (noise) {
             const double* z = noise + (int64_t)k * NPS_NOISE_PER_STEP * n + p;
             in.z_heat = z[0]; in.z_ph = z[n]; in.u_ph[0] = z[2 * n]; in.u_ph[1] = z[3 * n]; in.u_ph[2] = z[4 * n];
+        } else if (rng.enabled) {
+            const StepDraws d = plant_step_draws(rng.seed, rng.plant_offset + (uint64_t)p, rng.step0 + (uint64_t)k);
+            in.z_heat = d.z_heat; in.z_ph = d.z_ph; in.u_ph[0] = d.u_ph[0]; in.u_ph[1] = d.u_ph[1]; in.u_ph[2] = d.u_ph[2];
         } else {
             in.z_heat = 0.0; in.z_ph = 0.0; in.u_ph[0] = 1.0; in.u_ph[1] = 1.0; in.u_ph[2] = 1.0;
         }
@@ -425,16 +432,18 @@ int nps_step(nps_handle* h, double* d_state, const int8_t* d_action, const doubl
     if (!h || !d_state) return fail("nps_step: null argument");
     if (k_substeps <= 0) return fail("nps_step: k_substeps must be positive");
     cudaStream_t s = (cudaStream_t)cuda_stream;
+    RngConfig rng = h->rng;
+    if (rng.enabled && !d_noise) h->rng.step0 += (uint64_t)k_substeps;   // the next launch continues the stream
 #if defined(NPS_STEP_BLOCK)
     nps_step_kernel<NPS_STEP_BLOCK, NPS_STEP_MINBLOCKS><<<(int)((h->n + NPS_STEP_BLOCK - 1) / NPS_STEP_BLOCK), NPS_STEP_BLOCK, 0, s>>>(
-        d_state, h->params, d_action, d_magnitude, d_noise, d_setpoint, k_substeps, h->n, d_obs, d_reward, d_done);
+        d_state, h->params, d_action, d_magnitude, d_noise, d_setpoint, k_substeps, h->n, d_obs, d_reward, d_done, rng);
 #else
     if (h->n >= kLargeBatch)
         nps_step_kernel<448, 1><<<(int)((h->n + 447) / 448), 448, 0, s>>>(d_state, h->params, d_action, d_magnitude, d_noise,
-                                                                         d_setpoint, k_substeps, h->n, d_obs, d_reward, d_done);
+                                                                         d_setpoint, k_substeps, h->n, d_obs, d_reward, d_done, rng);
     else
         nps_step_kernel<64, 7><<<(int)((h->n + 63) / 64), 64, 0, s>>>(d_state, h->params, d_action, d_magnitude, d_noise,
-                                                                      d_setpoint, k_substeps, h->n, d_obs, d_reward, d_done);
+                                                                      d_setpoint, k_substeps, h->n, d_obs, d_reward, d_done, rng);
 #endif
     NPS_CUDA(cudaGetLastError());
     return 0;
@@ -542,6 +551,20 @@ int nps_step_host_async(nps_handle* h, double* d_state, const int8_t* h_action, 
 }
 
 int nps_pipe_depth(void) { return NPS_PIPE_DEPTH; }
+
+int nps_set_device_rng(nps_handle* h, int enabled, uint64_t seed, uint64_t plant_offset, uint64_t first_step) {
+    if (!h) return fail("nps_set_device_rng: null handle");
+    h->rng.enabled = enabled ? 1 : 0;
+    h->rng.seed = seed; h->rng.plant_offset = plant_offset; h->rng.step0 = first_step;
+    return 0;
+}
+
+int nps_device_rng_draws(uint64_t seed, uint64_t plant, uint64_t step, double* out5) {
+    if (!out5) return fail("nps_device_rng_draws: null output");
+    const StepDraws d = plant_step_draws(seed, plant, step);   // host evaluation of the same generator (libm transcendentals)
+    out5[0] = d.z_heat; out5[1] = d.z_ph; out5[2] = d.u_ph[0]; out5[3] = d.u_ph[1]; out5[4] = d.u_ph[2];
+    return 0;
+}
 
 int nps_wait(nps_handle* h, int ticket) {
     if (!h || ticket < 0 || ticket >= NPS_PIPE_DEPTH || !h->pipe[ticket].out_done) return fail("nps_wait: bad ticket");
