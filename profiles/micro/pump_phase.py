@@ -14,7 +14,14 @@ from nuclear_sim_b200 import BatchedNuclearPlantSimulator, load_snapshot, scenar
 
 
 def main():
-    L = ctypes.CDLL(os.path.join(ROOT, "profiles", "micro", "libpump_phase.so"))
+    so = os.path.join(ROOT, "profiles", "micro", "libpump_phase.so")
+    if not os.path.exists(so):      # the probe library is not part of the product build
+        import subprocess
+        subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-fmad=false",
+                               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared",
+                               "-I", os.path.join(ROOT, "nuclear-sim_b200", "csrc", "plant"), "-o", so,
+                               os.path.join(ROOT, "profiles", "micro", "pump_phase.cu")])
+    L = ctypes.CDLL(so)
     L.pump_phase_launch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     L.pump_phase_host.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]
     n = 65536
