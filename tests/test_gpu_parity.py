@@ -401,3 +401,31 @@ def test_c_abi_from_plain_c(tmp_path):
         res = sim.step(K=k)
     want = np.concatenate([sim.state_numpy()[0], res["observation"][0].cpu().numpy(), [float(res["reward"][0])]])
     np.testing.assert_array_equal(got.view(np.uint64), want.view(np.uint64))
+
+
+def test_error_conventions_through_the_abi():
+    """Return codes and nps_last_error(): nothing fails silently (include/nps_b200.h conventions)."""
+    import torch
+    from nuclear_sim_b200 import _clib, load_snapshot
+    L = _clib.lib()
+    s0, params = load_snapshot("pwr3000_reactor_dt1")
+    sim = _sim(np.tile(s0, (4, 1)), params)
+    h = ctypes.c_void_p()
+    assert L.nps_create(ctypes.c_int64(0), 0, ctypes.byref(h)) < 0 and b"bad arguments" in L.nps_last_error()
+    assert L.nps_create(ctypes.c_int64(4), 99, ctypes.byref(h)) < 0 and b"device index" in L.nps_last_error()
+    with pytest.raises(_clib.NpsError, match="k_substeps"):
+        sim.step(K=0)
+    with pytest.raises(_clib.NpsError, match="set_thresholds"):
+        sim.check_thresholds()
+    ring = torch.zeros(8, dtype=torch.float64, device="cuda")
+    assert L.nps_log_row(sim._h, ctypes.c_void_p(sim.slab.data_ptr()), ctypes.c_void_p(ring.data_ptr()), ctypes.c_int64(1),
+                         ctypes.c_int64(0), None) < 0 and b"no logged fields" in L.nps_last_error()
+    last = torch.zeros(4, dtype=torch.float64, device="cuda")
+    flags = torch.zeros(4, dtype=torch.int32, device="cuda")
+    assert L.nps_check_thresholds(sim._h, ctypes.c_void_p(sim.slab.data_ptr()), ctypes.c_void_p(last.data_ptr()),
+                                  ctypes.c_void_p(flags.data_ptr()), None, None) < 0 and b"no thresholds" in L.nps_last_error()
+    bad = np.array([10 ** 6], dtype=np.int32)
+    assert L.nps_set_logged_fields(sim._h, bad.ctypes.data_as(ctypes.c_void_p), 1) < 0 and b"out of range" in L.nps_last_error()
+    assert L.nps_wait(sim._h, 17) < 0 and b"bad ticket" in L.nps_last_error()
+    # a maintenance target without a restatement is refused, not ignored (status 2 -> the host raises)
+    assert sim.apply_maintenance([(0, 8, 0, 0)]) == [2]
