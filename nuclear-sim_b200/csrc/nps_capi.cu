@@ -73,7 +73,7 @@ struct nps_handle {
 // step kernel: thread-per-plant, state register/local resident across k substeps
 // ------------------------------------------------------------------------------------------------
 // Launch shapes (both 128 registers, 448 resident threads per SM, so 65,536 plants are ONE wave on 148 SMs):
-//   large batches  448 threads x 1 block/SM  - measured 2 % faster than 64 x 7 at 65,536 plants (profiles/r01_sweep_block_substeps.txt)
+//   large batches  448 threads x 1 block/SM  - measured 2 % faster than 64 x 7 at 65,536 plants (profiles/r01_tuning_variants.txt (7))
 //   small batches   64 threads x 7 blocks/SM - spreads a few thousand plants over all SMs instead of a handful
 // NPS_STEP_BLOCK / NPS_STEP_MINBLOCKS pin one shape for tuning builds.
 #ifndef NPS_COPY_UNROLL

@@ -49,7 +49,7 @@
 #define NPS_PF_NEAR_LEVEL 1
 #endif
 #ifndef NPS_PF_FAR_LEVEL
-#define NPS_PF_FAR_LEVEL 0   /* measured on B200 (profiles/r01_prefetch_variants.txt): far prefetch costs 12-25 %, near is neutral */
+#define NPS_PF_FAR_LEVEL 0   /* measured on B200 (profiles/r01_tuning_variants.txt (2)): far prefetch costs 12-25 %, near is neutral */
 #endif
 #if defined(__CUDA_ARCH__) && !defined(NPS_NO_PREFETCH)
 #define NPS_PF2_L1(a, off) do { asm volatile("prefetch.L1 [%0];" ::"l"((a) + (off))); \
