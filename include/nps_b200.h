@@ -72,6 +72,10 @@ int nps_step(nps_handle* h, double* d_state, const int8_t* d_action, const doubl
 int nps_set_device_rng(nps_handle* h, int enabled, uint64_t seed, uint64_t plant_offset, uint64_t first_step);
 int nps_device_rng_draws(uint64_t seed, uint64_t plant, uint64_t step, double* out5);
 
+/* Test hook: out[i] = x[i] ** y[i] through the step kernel's own power function (csrc/plant/hd.h py_pow: exact
+ * specialisations, csrc/plant/fastpow.h for positive finite bases, libdevice pow otherwise), device arrays. */
+int nps_selftest_pow(const double* d_x, const double* d_y, double* d_out, int64_t n, void* cuda_stream);
+
 /* Same step with HOST buffers for the per-step inputs and outputs (pinned or pageable): the
  * host->device copies of action/magnitude/noise and the device->host copies of obs/reward/done are
  * issued on the stream inside the call, which returns after they complete. State stays on device. */

@@ -550,6 +550,19 @@ int nps_step_host_async(nps_handle* h, double* d_state, const int8_t* h_action, 
     return slot;
 }
 
+__global__ void nps_selftest_pow_kernel(const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = py_pow(x[i], y[i]);
+}
+
+int nps_selftest_pow(const double* d_x, const double* d_y, double* d_out, int64_t n, void* cuda_stream) {
+    if (!d_x || !d_y || !d_out || n < 0) return fail("nps_selftest_pow: bad arguments");
+    if (n == 0) return 0;
+    nps_selftest_pow_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(d_x, d_y, d_out, n);
+    NPS_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int nps_pipe_depth(void) { return NPS_PIPE_DEPTH; }
 
 int nps_set_device_rng(nps_handle* h, int enabled, uint64_t seed, uint64_t plant_offset, uint64_t first_step) {

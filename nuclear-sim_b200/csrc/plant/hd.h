@@ -108,7 +108,18 @@ NPS_HD double np_clip(double x, double lo, double hi) {
 // ARE the correctly rounded pow(x, 2) and pow(x, 0.5), i.e. at least as close to glibc's (<= 0.52 ulp) as libdevice
 // pow is.  The exponent is a literal at
 // most call sites, so the test folds away; the wear exponents are batch-uniform parameters (uniform branch).
-NPS_HD_SHARED double nps_pow_general(double x, double y) { return pow(x, y); }
+// Every other exponent goes to nps_pow_general: fastpow.h for a positive finite base (all 78 general calls of a plant
+// step), libdevice pow for anything else.
+}  // namespace nps
+#include "fastpow.h"
+namespace nps {
+NPS_HD_SHARED double nps_pow_general(double x, double y) {
+#if defined(__CUDA_ARCH__) && !defined(NPS_LIBDEVICE_POW)
+    double r;
+    if (nps_pow_pos(x, y, r)) return r;     // positive finite base, moderate result: fastpow.h (<= 1.1 ulp)
+#endif
+    return pow(x, y);
+}
 NPS_HD double py_pow(double x, double y) {
 #if defined(__CUDA_ARCH__) && !defined(NPS_GENERIC_POW)
     if (y == 2.0) return x * x;

@@ -429,3 +429,41 @@ def test_error_conventions_through_the_abi():
     assert L.nps_wait(sim._h, 17) < 0 and b"bad ticket" in L.nps_last_error()
     # a maintenance target without a restatement is refused, not ignored (status 2 -> the host raises)
     assert sim.apply_maintenance([(0, 8, 0, 0)]) == [2]
+
+
+def test_device_pow_against_libm():
+    """The step kernel's power function (exact specialisations, fastpow.h, libdevice fallback) against numpy's pow
+    (glibc, < 1 ulp) on the operand classes of the model and on every special case: <= 2 ulp everywhere it is finite,
+    identical for exact cases and specials."""
+    import torch
+    from nuclear_sim_b200 import _clib
+    L = _clib.lib()
+    rng = np.random.RandomState(5)
+    n = 400000
+    x = 10.0 ** rng.uniform(-6, 6, n)
+    y = rng.uniform(-3, 4, n)
+    x[::7] = 1.0 + rng.uniform(-1e-3, 1e-3, len(x[::7]))                    # near 1
+    y[::11] = rng.choice([0.38, 0.8, 0.15, -0.6, 1.8, 2.2, 2.4, 1.6, 1.4, 1.3, 1.0 / 3, 2.0, 0.5, 3.0, 1.5, 0.25, 1.0, 0.0], len(y[::11]))
+    sx = np.array([0.0, -0.0, -2.0, -2.0, np.inf, np.nan, 5e-324, 1e-310, 2.0, 2.0, 1e300, 1e-300, 0.5, 1e150, 3.0])
+    sy = np.array([1.8, 1.8, 3.0, 0.5, 0.8, 1.2, 0.7, 0.7, np.inf, np.nan, 1.5, 1.5, 1100.0, 2.5, -2.0])
+    x, y = np.concatenate([x, sx]), np.concatenate([y, sy])
+    dx, dy = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    out = torch.empty_like(dx)
+    assert L.nps_selftest_pow(ctypes.c_void_p(dx.data_ptr()), ctypes.c_void_p(dy.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                              ctypes.c_int64(len(x)), None) == 0
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    with np.errstate(all="ignore"):
+        want = np.power(x, y)
+    fin = np.isfinite(want) & (want != 0)
+    ulps = np.abs(got[fin].view(np.int64) - want[fin].view(np.int64))
+    assert ulps.max() <= 2, (ulps.max(), x[fin][ulps.argmax()], y[fin][ulps.argmax()])
+    assert (ulps > 1).mean() < 1e-3
+    rest = ~fin
+    np.testing.assert_array_equal(np.isnan(got[rest]), np.isnan(want[rest]))
+    ok = ~np.isnan(want[rest])
+    np.testing.assert_array_equal(got[rest][ok], want[rest][ok])
+    # the exact specialisations are what they say they are: x*x (the correctly rounded square), x, 1
+    np.testing.assert_array_equal(got[y == 2.0], (x * x)[y == 2.0])
+    np.testing.assert_array_equal(got[(y == 1.0) & ~np.isnan(x)], x[(y == 1.0) & ~np.isnan(x)])
+    np.testing.assert_array_equal(got[(y == 0.0) & ~np.isnan(x)], 1.0)
