@@ -139,6 +139,8 @@ class BatchedNuclearPlantSimulator:
         _clib.check(self.L.nps_step(self._h, _ptr(self.slab), _ptr(a), _ptr(m), _ptr(z), _ptr(sp), int(K),
                                     _ptr(self._obs), _ptr(self._reward), _ptr(self._done), ctypes.c_void_p(stream)))
         self.n_launches += 1
+        if z is None and getattr(self, "_rng", None) is not None:
+            self._rng[2] += int(K)
         return {"observation": self._obs.t(), "reward": self._reward, "done": self._done.bool()}
 
     def set_device_rng(self, seed: Optional[int], plant_offset: int = 0, first_step: int = 0) -> None:
@@ -147,6 +149,8 @@ class BatchedNuclearPlantSimulator:
         Give each rank its first global plant id as plant_offset and the result does not depend on the sharding."""
         _clib.check(self.L.nps_set_device_rng(self._h, 0 if seed is None else 1, int(seed or 0) & (2 ** 64 - 1),
                                               int(plant_offset), int(first_step)))
+        # mirrored on the host so a checkpoint can resume the stream (env.save_checkpoint): [seed, offset, next step]
+        self._rng = None if seed is None else [int(seed) & (2 ** 64 - 1), int(plant_offset), int(first_step)]
 
     def step_host(self, h_actions, h_magnitudes, h_noise, h_setpoint, K, h_obs, h_reward, h_done) -> None:
         """Reference-facing call with HOST (pinned) per-step buffers: copies in, K substeps, copies out."""
@@ -157,6 +161,8 @@ class BatchedNuclearPlantSimulator:
                                          hp(h_setpoint), int(K), hp(h_obs), hp(h_reward), hp(h_done),
                                          ctypes.c_void_p(stream)))
         self.n_launches += 1
+        if h_noise is None and getattr(self, "_rng", None) is not None:
+            self._rng[2] += int(K)
 
     def step_host_async(self, h_actions, h_magnitudes, h_noise, h_setpoint, K, h_obs, h_reward, h_done) -> int:
         """Pipelined step_host (nps_step_host_async): returns a ticket; wait(ticket) makes the outputs valid.
@@ -169,6 +175,8 @@ class BatchedNuclearPlantSimulator:
         if t < 0:
             _clib.check(t)
         self.n_launches += 1
+        if h_noise is None and getattr(self, "_rng", None) is not None:
+            self._rng[2] += int(K)
         return int(t)
 
     def wait(self, ticket: int) -> None:

@@ -65,11 +65,13 @@ class BatchedNuclearPlantEnv:
 
 
 def save_checkpoint(sim, path: str, maintenance=None) -> None:
-    """Everything needed to resume a batch bit for bit: the SoA slab, the parameter block, threshold cooldown stamps."""
+    """Everything needed to resume a batch bit for bit: the SoA slab, the parameter block, threshold cooldown stamps,
+    and the position of the device-side noise stream when that mode is on."""
     thr = sim._thr
     torch.save({"slab": sim.slab.cpu(), "initial": sim._initial.cpu(), "params": torch.from_numpy(sim.params.copy()),
                 "n_plants": sim.n_plants, "n_launches": sim.n_launches,
                 "last_fired": None if thr is None else thr["last"].cpu(),
+                "device_rng": None if getattr(sim, "_rng", None) is None else [str(v) for v in sim._rng],
                 "maintenance_last_check": None if maintenance is None else maintenance.last_check_time}, path)
 
 
@@ -83,4 +85,7 @@ def load_checkpoint(path: str, device: str = "cuda:0", maintenance_table=None):
         sim.set_thresholds(maintenance_table.device_rows())
     if ck["last_fired"] is not None and sim._thr is not None:
         sim._thr["last"].copy_(ck["last_fired"].to(sim.device))
+    if ck.get("device_rng") is not None:
+        seed, offset, step = (int(v) for v in ck["device_rng"])
+        sim.set_device_rng(seed, plant_offset=offset, first_step=step)
     return sim

@@ -360,6 +360,16 @@ def test_vector_env_and_checkpoint_resume(tmp_path):
     a = env2.sim.step(actions=acts, K=4)
     b = resumed.step(actions=acts, K=4)
     assert torch.equal(env2.sim.slab, resumed.slab) and torch.equal(a["observation"], b["observation"])
+    # with device-side noise the checkpoint also carries the position of the stream
+    s1, p1 = load_snapshot("pwr3000_oil_top_off_dt5")           # constant heat source with noise enabled
+    live = _sim(np.tile(s1, (n, 1)), p1)
+    live.set_device_rng(11, plant_offset=500)
+    live.step(K=3); live.step(K=2)
+    save_checkpoint(live, path)
+    resumed = load_checkpoint(path)
+    live.step(K=4); resumed.step(K=4)
+    assert torch.equal(live.slab, resumed.slab)
+    assert len(torch.unique(live.state.power_level)) > 1        # the plants really drew different noise
 
 
 def test_cuda_batched_timing_sweep():
