@@ -34,6 +34,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 PLANTS_PER_GPU = 65536
+INPUT_SETS = 16
 SUBSTEPS = 64                        # fused substeps per launch (profiles/r01_tuning_variants.txt (20): 32 / 64 / 128)
 FLOP_PER_PLANT_STEP = 2.0e4          # SURVEY.md §8d canonical figure (FP64 flop-equivalents)
 METRIC = "plant-steps/sec"
@@ -261,8 +262,10 @@ def main():
     sim = BatchedNuclearPlantSimulator(n, sc.randomized_states(s0, pid), params, device=str(dev))
     state_bytes = sim.slab.numel() * 8
 
-    # per-step inputs for every warm-up and timed step (distinct per step), resident in HBM and mirrored in pinned host memory
-    total = W + K
+    # per-launch inputs (distinct for up to INPUT_SETS consecutive launches), resident in HBM and mirrored in pinned host memory
+    # at most INPUT_SETS distinct launches' worth of inputs, cycled: keeps pinned host memory (and its device mirror)
+    # bounded for any --steps / --warmup the caller chooses (one set is 206 MB at 64 substeps x 65,536 plants)
+    total = min(W + K, INPUT_SETS)
     acts_h = torch.empty((total, ksub, n), dtype=torch.int8).pin_memory()
     mags_h = torch.empty((total, ksub, n), dtype=torch.float64).pin_memory()
     noise_h = torch.empty((total, ksub, 5, n), dtype=torch.float64).pin_memory()
@@ -285,7 +288,7 @@ def main():
 
     # ------------------------------------------------------------------ device-resident arm (value)
     for i in range(W):
-        sim.step(actions=acts_d[i], magnitudes=mags_d[i], noise=noise_d[i], K=ksub)
+        sim.step(actions=acts_d[i % total], magnitudes=mags_d[i % total], noise=noise_d[i % total], K=ksub)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -295,7 +298,7 @@ def main():
     barrier()
     ev[0].record()
     for i in range(K):
-        sim.step(actions=acts_d[W + i], magnitudes=mags_d[W + i], noise=noise_d[W + i], K=ksub)
+        sim.step(actions=acts_d[(W + i) % total], magnitudes=mags_d[(W + i) % total], noise=noise_d[(W + i) % total], K=ksub)
         ev[i + 1].record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -317,7 +320,7 @@ def main():
     for i in range(W):       # warm-up through the SAME entry point: its staging sets are allocated on first use
         if i >= D:
             sim.wait(warm[i - D])
-        warm.append(sim.step_host_async(acts_h[i], mags_h[i], noise_h[i], None, ksub, obs_h[i % D], rew_h[i % D], done_h[i % D]))
+        warm.append(sim.step_host_async(acts_h[i % total], mags_h[i % total], noise_h[i % total], None, ksub, obs_h[i % D], rew_h[i % D], done_h[i % D]))
     for t in warm[-D:]:
         sim.wait(t)
     barrier()
@@ -329,7 +332,7 @@ def main():
         if i >= D:
             sim.wait(tickets[i - D])
             reward_sum += float(rew_h[b].mean())
-        tickets.append(sim.step_host_async(acts_h[W + i], mags_h[W + i], noise_h[W + i], None, ksub, obs_h[b], rew_h[b], done_h[b]))
+        tickets.append(sim.step_host_async(acts_h[(W + i) % total], mags_h[(W + i) % total], noise_h[(W + i) % total], None, ksub, obs_h[b], rew_h[b], done_h[b]))
     for i in range(max(0, K - D), K):
         sim.wait(tickets[i])
         reward_sum += float(rew_h[i % D].mean())
@@ -348,7 +351,7 @@ def main():
     sim.set_device_rng(20260118, plant_offset=rank * n)
     tickets = []
     for i in range(min(W, D)):
-        tickets.append(sim.step_host_async(acts_h[i], mags_h[i], None, None, ksub, obs_h[i % D], rew_h[i % D], done_h[i % D]))
+        tickets.append(sim.step_host_async(acts_h[i % total], mags_h[i % total], None, None, ksub, obs_h[i % D], rew_h[i % D], done_h[i % D]))
     for t_ in tickets:
         sim.wait(t_)
     barrier()
@@ -360,7 +363,7 @@ def main():
         if i >= D:
             sim.wait(tickets[i - D])
             reward_sum += float(rew_h[b].mean())
-        tickets.append(sim.step_host_async(acts_h[W + i], mags_h[W + i], None, None, ksub, obs_h[b], rew_h[b], done_h[b]))
+        tickets.append(sim.step_host_async(acts_h[(W + i) % total], mags_h[(W + i) % total], None, None, ksub, obs_h[b], rew_h[b], done_h[b]))
     for i in range(max(0, K - D), K):
         sim.wait(tickets[i])
     r1.record()
@@ -402,7 +405,8 @@ def main():
                        "plants_per_gpu": n, "substeps_per_step": ksub, "n_state_fields": N_STATE,
                        "state_bytes_per_gpu": state_bytes,
                        "l2": "inputs larger than L2 (state slab %.0f MB per GPU is streamed every launch)" % (state_bytes / 1e6),
-                       "mean_power_percent_after_run": mean_power, "rank0_numa_node": numa_node},
+                       "mean_power_percent_after_run": mean_power, "rank0_numa_node": numa_node,
+                       "distinct_input_sets": total},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "mean_reward_readback": loss_check},
             "e2e_device_rng": {"value": e2e_rng_value, "unit": UNIT, "h2d_bytes_per_step": ksub * n * (1 + 8),
