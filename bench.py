@@ -34,8 +34,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 PLANTS_PER_GPU = 65536
-INPUT_SETS = 16
-SUBSTEPS = 64                        # fused substeps per launch (profiles/r01_tuning_variants.txt (20): 32 / 64 / 128)
+INPUT_SETS = 12
+SUBSTEPS = 128                       # fused substeps per launch (profiles/r01_tuning_variants.txt (20): 32 / 64 / 128)
 FLOP_PER_PLANT_STEP = 2.0e4          # SURVEY.md §8d canonical figure (FP64 flop-equivalents)
 METRIC = "plant-steps/sec"
 UNIT = "plant-steps/s"
@@ -264,7 +264,7 @@ def main():
 
     # per-launch inputs (distinct for up to INPUT_SETS consecutive launches), resident in HBM and mirrored in pinned host memory
     # at most INPUT_SETS distinct launches' worth of inputs, cycled: keeps pinned host memory (and its device mirror)
-    # bounded for any --steps / --warmup the caller chooses (one set is 206 MB at 64 substeps x 65,536 plants)
+    # bounded for any --steps / --warmup the caller chooses (one set is 411 MB at 128 substeps x 65,536 plants)
     total = min(W + K, INPUT_SETS)
     acts_h = torch.empty((total, ksub, n), dtype=torch.int8).pin_memory()
     mags_h = torch.empty((total, ksub, n), dtype=torch.float64).pin_memory()
