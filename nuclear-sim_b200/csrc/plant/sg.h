@@ -102,7 +102,7 @@ NPS_HD void tsp_update(SGState& g, const PlantParams& p, double temperature, dou
 
     double temp_kelvin = temperature + 273.15;
     double temp_factor = nps_exp(-45000.0 / (8.314 * temp_kelvin));
-    temp_factor = temp_factor / nps_exp(-45000.0 / (8.314 * 573.15));
+    temp_factor = temp_factor / exp(-45000.0 / (8.314 * 573.15));   // constant argument: inlined so that it folds
     double ph_factor = 1.0 + 0.5 * fabs(p.sgwc_ph - 9.2);
     double velocity_factor = py_pow(flow_velocity / 3.0, 0.5);
     velocity_factor = np_clip(velocity_factor, 0.5, 2.0);
@@ -165,7 +165,7 @@ NPS_HD void tif_update(SGState& g, double temperature, double flow_velocity, dou
     g.tif_cumulative_performance_loss = loss0;
     // chemistry dict passed by SteamGenerator.update_state: B 1000, Li 2.0, pH 7.2, O2 0.005
     double tk = temperature + 273.15, rk = 320.0 + 273.15;
-    double temp_factor = nps_exp(-65000.0 / (8.314 * tk)) / nps_exp(-65000.0 / (8.314 * rk));
+    double temp_factor = nps_exp(-65000.0 / (8.314 * tk)) / exp(-65000.0 / (8.314 * rk));   // constant argument: folds
     double boric = 1.0 / (1.0 + 1000.0 / 1000.0 * 0.5);
     double lithium = py_max(0.5, 1.0 + (2.0 - 2.0) * 0.1);
     double ph_factor = 1.0 + 0.5 * fabs(7.2 - 7.2);

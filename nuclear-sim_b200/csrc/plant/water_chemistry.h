@@ -24,7 +24,7 @@ NPS_HD_SHARED void wc_composite(WaterChemState& w) {
     w.particle_content = 1.0 + (tds_factor + iron_particle + silica_particle) * 0.1;
     w.particle_content = np_clip(w.particle_content, 0.5, 2.0);
     double A = (nps_log10(w.total_dissolved_solids) - 1) / 10;
-    double B = -13.12 * nps_log10(25.0 + 273) + 34.55;
+    double B = -13.12 * log10(25.0 + 273) + 34.55;   // constant argument: inlined so that it folds
     double C = nps_log10(w.hardness) - 0.4;
     double D = nps_log10(w.alkalinity);
     double ph_sat = (9.3 + A + B) - (C + D);
