@@ -67,7 +67,7 @@ __device__ __forceinline__ bool nps_pow_pos(double x, double y, double& out) {
     for (int k = 22; k >= 12; k -= 2) { qe = fma(qe, r2, nps_pow_tab[k]); if (k - 1 >= 13) qo = fma(qo, r2, nps_pow_tab[k - 1]); }
     const double q = fma(qo, rr, qe);
     const double ex = 1.0 + fma(r2, q, rr);
-    out = __longlong_as_double(__double_as_longlong(ex) + ((long long)kd << 52));
+    out = __longlong_as_double(__double_as_longlong(ex) + ((long long)kd * (1LL << 52)));
     return true;
 }
 
