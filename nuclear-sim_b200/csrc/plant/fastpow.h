@@ -13,25 +13,57 @@
 // libdevice pow's own error bound, which is what the parity tolerances already absorb.  Outside the guarded range
 // (x not a positive normal number, |y| >= 1024, |y log x| >= 64) the caller falls back to libdevice pow.
 // Coefficients sit in constant memory so the FMA chain reads them as operands instead of materialising each 64-bit
-// literal with two moves.  Device only: the host build (test infrastructure) keeps libm pow, the reference's own function.
+// literal with two moves.  The step uses it on the device only: the host build (test infrastructure) keeps libm pow, the
+// reference's own function, and compiles this header just to test the algorithm without a GPU (nps_oracle_fastpow).
 #pragma once
+#include <string.h>
 #include "hd.h"
 
-#if defined(__CUDACC__)
 namespace nps {
 
 // 2/(2k+1), k = 1..12 (atanh series)  then  1/k!, k = 2..14 (exp series)
-__constant__ double nps_pow_tab[25] = {
-    2.0 / 3, 2.0 / 5, 2.0 / 7, 2.0 / 9, 2.0 / 11, 2.0 / 13, 2.0 / 15, 2.0 / 17, 2.0 / 19, 2.0 / 21, 2.0 / 23, 2.0 / 25,
-    1.0 / 2, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320, 1.0 / 362880, 1.0 / 3628800, 1.0 / 39916800,
-    1.0 / 479001600, 1.0 / 6227020800.0, 1.0 / 87178291200.0};
+#define NPS_POW_TAB { \
+    2.0 / 3, 2.0 / 5, 2.0 / 7, 2.0 / 9, 2.0 / 11, 2.0 / 13, 2.0 / 15, 2.0 / 17, 2.0 / 19, 2.0 / 21, 2.0 / 23, 2.0 / 25, \
+    1.0 / 2, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320, 1.0 / 362880, 1.0 / 3628800, 1.0 / 39916800, \
+    1.0 / 479001600, 1.0 / 6227020800.0, 1.0 / 87178291200.0}
+#if defined(__CUDACC__)
+__constant__ double nps_pow_tab_dev[25] = NPS_POW_TAB;
+#endif
+static const double nps_pow_tab_host[25] = NPS_POW_TAB;
+#if defined(__CUDA_ARCH__)
+#define nps_pow_tab nps_pow_tab_dev
+#else
+#define nps_pow_tab nps_pow_tab_host
+#endif
 
-__device__ __forceinline__ bool nps_pow_pos(double x, double y, double& out) {
-    const long long ix = __double_as_longlong(x);
+NPS_HD long long nps_bits(double v) {
+#if defined(__CUDA_ARCH__)
+    return __double_as_longlong(v);
+#else
+    long long b; memcpy(&b, &v, sizeof(b)); return b;
+#endif
+}
+NPS_HD double nps_from_bits(long long b) {
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double(b);
+#else
+    double v; memcpy(&v, &b, sizeof(v)); return v;
+#endif
+}
+NPS_HD double nps_rcp_f32(double g) {     // 1/g to single precision, correctly rounded on both sides
+#if defined(__CUDA_ARCH__)
+    return (double)__frcp_rn((float)g);
+#else
+    return (double)(1.0f / (float)g);
+#endif
+}
+
+NPS_HD bool nps_pow_pos(double x, double y, double& out) {
+    const long long ix = nps_bits(x);
     const int be = (int)((ix >> 52) & 0x7ff);
     if (!(ix > 0) || (unsigned)(be - 23) >= 2000u || !(fabs(y) < 1024.0)) return false;
     int e = be - 1023;
-    double m = __longlong_as_double((ix & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
+    double m = nps_from_bits((ix & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
     if (m > 1.4142135623730951) { m *= 0.5; e += 1; }
     const double f = m - 1.0;                       // exact
     const double g = m + 1.0;
@@ -39,7 +71,7 @@ __device__ __forceinline__ bool nps_pow_pos(double x, double y, double& out) {
     const double u = f / g;
     double r = fma(-u, g, f);
     r = fma(-u, g_lo, r);                           // f - u * (g + g_lo)
-    const double u_lo = r * (double)__frcp_rn((float)g);
+    const double u_lo = r * nps_rcp_f32(g);
     const double u2 = u * u;
     const double u4 = u2 * u2;
     double pe = nps_pow_tab[10], po = nps_pow_tab[11];     // even / odd halves of the series: two independent FMA chains
@@ -67,9 +99,10 @@ __device__ __forceinline__ bool nps_pow_pos(double x, double y, double& out) {
     for (int k = 22; k >= 12; k -= 2) { qe = fma(qe, r2, nps_pow_tab[k]); if (k - 1 >= 13) qo = fma(qo, r2, nps_pow_tab[k - 1]); }
     const double q = fma(qo, rr, qe);
     const double ex = 1.0 + fma(r2, q, rr);
-    out = __longlong_as_double(__double_as_longlong(ex) + ((long long)kd * (1LL << 52)));
+    out = nps_from_bits(nps_bits(ex) + ((long long)kd * (1LL << 52)));
     return true;
 }
 
+#undef nps_pow_tab
+#undef NPS_POW_TAB
 }  // namespace nps
-#endif

@@ -65,6 +65,17 @@ int nps_oracle_observe(const double* state, const double* params, int64_t n_plan
 
 }  // extern "C"
 
+// The device power function's algorithm (csrc/plant/fastpow.h) evaluated on the host, for testing it without a GPU.
+// The oracle's own plant_step never uses it (host py_pow is libm pow); taken[i] = 0 where the guarded range refuses.
+extern "C" int nps_oracle_fastpow(const double* x, const double* y, double* out, unsigned char* taken, int64_t n) {
+    for (int64_t i = 0; i < n; ++i) {
+        double r = 0.0;
+        taken[i] = nps::nps_pow_pos(x[i], y[i], r) ? 1 : 0;
+        out[i] = r;
+    }
+    return 0;
+}
+
 // maintenance effect on ONE plant (array-of-structs state): returns the MaintStatus code
 #include "maintenance.h"
 extern "C" int nps_oracle_apply_maintenance(double* state, const double* params, int target, int action, int arg) {
