@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_uint8, c_uint32, c_void_p
+from ctypes import POINTER, c_char_p, c_int, c_int64, c_void_p
 
 from . import _build
 

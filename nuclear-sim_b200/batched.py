@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import _clib
-from ._layout import N_PARAMS, N_STATE, field_index, field_names
+from ._layout import N_PARAMS, N_STATE, field_index
 
 OBS_DIM = 22
 NOISE_PER_STEP = 5

@@ -13,10 +13,8 @@ from __future__ import annotations
 
 from typing import Dict, Optional, Tuple
 
-import numpy as np
 import torch
 
-from ._layout import field_index
 
 N_ACTIONS = 15          # len(ControlAction): systems/primary/__init__.py:28-45
 
