@@ -20,6 +20,7 @@ import torch
 
 from . import _clib
 from ._layout import N_PARAMS, N_STATE, field_index
+from ._layout import field_names as _layout_field_names
 
 OBS_DIM = 22
 NOISE_PER_STEP = 5
@@ -342,6 +343,32 @@ class BatchedNuclearPlantSimulator:
         _clib.check(self.L.nps_set_logged_fields(self._h, ids.ctypes.data_as(ctypes.c_void_p), len(ids)))
         self._logged = {"names": list(names), "rows": int(ring_rows), "n": 0,
                         "ring": torch.empty((ring_rows, len(ids), self.n_plants), dtype=torch.float64, device=self.device)}
+
+    def set_logged_columns(self, prefix: Optional[str] = None, ring_rows: int = 256) -> int:
+        """Log what the reference's CSV columns starting with `prefix` need (None: every column, e.g. "secondary.feedwater_FWP-1.");
+        returns the number of fields per ring row."""
+        from .export import ColumnSchema
+        schema = ColumnSchema()
+        which = schema.select(prefix)
+        ids = schema.logged_fields(which)
+        names = _layout_field_names()
+        self.set_logged_fields([names[i] for i in ids], ring_rows)
+        self._logged["schema"], self._logged["which"], self._logged["ids"] = schema, which, ids
+        return len(ids)
+
+    def export_trajectory(self, plant: int, filename: str, start_datetime=None, dt_minutes: Optional[float] = None) -> int:
+        """The logged rows of one plant as the reference's wide CSV (same header names, same formatting as the scalar
+        facade's export_to_csv); rows written."""
+        import datetime as _dt
+        from .export import export_ring_to_csv
+        g = self._logged
+        if "schema" not in g:
+            raise _clib.NpsError("set_logged_columns() first")
+        ring = self.drain_log()
+        first = max(0, g["n"] - g["rows"]) + 1
+        dt = float(self.params[field_index("PlantParams")["dt"]]) if dt_minutes is None else float(dt_minutes)
+        return export_ring_to_csv(filename, ring, g["ids"], int(plant), start_datetime or _dt.datetime(2024, 1, 1), dt,
+                                  first_row_step=first, schema=g["schema"], which=g["which"])
 
     def log_row(self) -> None:
         g = self._logged

@@ -173,6 +173,33 @@ class TrajectoryStore:
         return self._write(filename, self.schema.select(f"{category}.{subcategory}."), time_range)
 
 
+def export_ring_to_csv(filename: str, ring: np.ndarray, logged_field_ids: Sequence[int], plant: int,
+                       start_datetime: _dt.datetime, dt_minutes: float, first_row_step: int = 1,
+                       schema: Optional[ColumnSchema] = None, which: Optional[Sequence[int]] = None,
+                       events: Optional[Sequence[frozenset]] = None) -> int:
+    """One plant's trajectory out of the device ring buffer (BatchedNuclearPlantSimulator.drain_log():
+    [rows, n_logged, n_plants]) as the reference's wide CSV (StateManager.export_to_csv, state_manager.py:296-386).
+    `logged_field_ids` are the PlantState indices of the ring's field axis; columns whose fields were not logged are
+    left out unless they are constants.  Row r is stamped start + (first_row_step + r) * dt."""
+    schema = schema or ColumnSchema()
+    have = {int(f): j for j, f in enumerate(logged_field_ids)}
+    which = list(schema.select() if which is None else which)
+    which = [i for i in which if set(schema.logged_fields([i])) <= set(have)]
+    n_state = len(field_index())
+    n = 0
+    with open(filename, "w", newline="") as fh:
+        w = csv.writer(fh)
+        w.writerow(["time"] + [schema.names[i] for i in which])
+        for r in range(ring.shape[0]):
+            state = np.full(n_state, np.nan)
+            for f, j in have.items():
+                state[f] = ring[r, j, plant]
+            t = start_datetime + _dt.timedelta(minutes=(first_row_step + r) * dt_minutes)
+            w.writerow([t.isoformat()] + schema.row(state, which, events[r] if events else frozenset()))
+            n += 1
+    return n
+
+
 # PlantDataLogger.extract_all_parameters (data/plant_data_logger.py:91-136): 22 parameters per step, in this order
 def plant_data_logger_parameters(state: np.ndarray, simulation_time: float) -> List[Tuple[str, object, str]]:
     ix = field_index()

@@ -477,3 +477,25 @@ def test_device_pow_against_libm():
     np.testing.assert_array_equal(got[y == 2.0], (x * x)[y == 2.0])
     np.testing.assert_array_equal(got[(y == 1.0) & ~np.isnan(x)], x[(y == 1.0) & ~np.isnan(x)])
     np.testing.assert_array_equal(got[(y == 0.0) & ~np.isnan(x)], 1.0)
+
+
+def test_batched_export_trajectory_in_reference_schema(tmp_path):
+    """Device ring buffer -> the reference's wide CSV for one plant of a batch: header and every value equal what the
+    host row store writes from the full states of the same steps."""
+    import datetime as dt
+    from nuclear_sim_b200 import load_snapshot
+    from nuclear_sim_b200.export import TrajectoryStore
+    from nuclear_sim_b200 import scenarios as sc
+    s0, params = load_snapshot("pwr3000_oil_top_off_dt5")
+    n = 10
+    sim = _sim(sc.randomized_states(s0, np.arange(n)), params)
+    n_fields = sim.set_logged_columns("secondary.steam_generator_SG-1.", ring_rows=8)
+    assert n_fields > 20
+    store = TrajectoryStore(dt.datetime(2024, 1, 1))
+    for k in range(6):
+        sim.step()
+        sim.log_row()
+        store.add_row(dt.datetime(2024, 1, 1) + dt.timedelta(minutes=5.0 * (k + 1)), sim.state_numpy()[7])
+    assert sim.export_trajectory(7, str(tmp_path / "ring.csv")) == 6
+    store.export_by_subcategory("secondary", "steam_generator_SG-1", str(tmp_path / "store.csv"))
+    assert open(tmp_path / "ring.csv").read() == open(tmp_path / "store.csv").read()

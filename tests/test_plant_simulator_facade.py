@@ -84,3 +84,24 @@ def test_maintenance_scenario_through_facade(tmp_path):
     assert levels[26] > 58.0 > levels[27] and levels[30] > 90.0
     hdr = next(csv.reader(open(sec)))
     assert len(hdr) > 600 and all(h == "time" or h.startswith("secondary.") for h in hdr)
+
+
+def test_ring_buffer_export_equals_row_store_export(tmp_path):
+    """export_ring_to_csv (the batched engine's ring buffer -> reference CSV) writes what TrajectoryStore writes for the
+    same states: same header, same values, same timestamps - on a synthetic ring built from fixture states."""
+    import datetime as dt
+    from nuclear_sim_b200.export import ColumnSchema, TrajectoryStore, export_ring_to_csv
+    g = U.load_golden("cfg1_oil_top_off")
+    states = [g["states"][c][0] for c in range(5)]
+    schema = ColumnSchema()
+    which = schema.select("secondary.feedwater_FWP-1.")
+    ids = schema.logged_fields(which)
+    ring = np.stack([np.stack([np.stack([s[f], s[f] * 0 - 1.0]) for f in ids]) for s in states])     # [rows, n_logged, 2 plants]
+    start = dt.datetime(2024, 1, 1)
+    n = export_ring_to_csv(str(tmp_path / "ring.csv"), ring, ids, 0, start, 5.0, first_row_step=1, schema=schema, which=which)
+    store = TrajectoryStore(start)
+    for k, s in enumerate(states):
+        store.add_row(start + dt.timedelta(minutes=5.0 * (k + 1)), s)
+    store.export_by_subcategory("secondary", "feedwater_FWP-1", str(tmp_path / "store.csv"))
+    assert n == 5
+    assert open(tmp_path / "ring.csv").read() == open(tmp_path / "store.csv").read()
