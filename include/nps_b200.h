@@ -27,7 +27,7 @@ extern "C" {
 
 typedef struct nps_handle nps_handle;
 
-#define NPS_ABI_VERSION 1
+#define NPS_ABI_VERSION 2
 #define NPS_OBS_DIM 22          /* get_observation(): 12 primary + 6 secondary + 4 feedwater (sim.py:290-333) */
 #define NPS_NOISE_PER_STEP 5    /* z_heat, z_ph, u_ph[3] (constant_heat_source.py:178; ph_control_system.py:278-420) */
 
@@ -62,6 +62,46 @@ int nps_step(nps_handle* h, double* d_state, const int8_t* d_action, const doubl
              const double* d_noise, const double* d_setpoint, int k_substeps, double* d_obs, double* d_reward,
              uint8_t* d_done, void* cuda_stream);
 
+/* --- per-step monitoring inside a fused launch ---------------------------------------------------------------
+ * The reference looks at the plant after EVERY step: `done` = scram_activated (sim.py:256), the NaN reset
+ * (thermal_hydraulics.py:257-269), threshold monitoring (state_manager.py:1307-1369).  nps_step_monitored does the same
+ * after every substep of a K-substep launch, so the step of every discrete event is the one K = 1 launches would report.
+ * All pointers are caller-owned device memory; any of them may be NULL (that output is skipped).
+ *   d_last_fired   [n_thresholds][n_plants] cooldown stamps (same array nps_check_thresholds uses).  Non-NULL switches on
+ *                  threshold evaluation after every substep (rows from nps_set_thresholds); violations are appended to
+ *                  d_events[*d_n_events ...] (one warp-aggregated atomic per row and warp), *d_n_events keeps counting
+ *                  past event_capacity so the caller can detect an overflow; the caller zeroes it.
+ *   skip_last_check  1: no threshold evaluation after the LAST substep (the caller applies maintenance first and then
+ *                  runs nps_check_thresholds for that step, as sim.py:209-223 orders it).
+ *   d_watch_fields [n_watch] (<= 32) PlantState field indices; d_watch_step [n_watch][n_plants] = step index at which the
+ *                  field first was non-zero, -1 = not yet (caller initialises to -1; persists across launches).
+ *   d_first_scram_step, d_first_nan_reset_step [n_plants] int32, -1 = never; d_status [n_plants] sticky NPS_STATUS_* bits.
+ *   d_reward_k [k_substeps][n_plants], d_done_k [k_substeps][n_plants] uint8: calculate_reward / done after every substep.
+ *   step0          step index of the first substep of this launch (event.step = step0 + substep). */
+#define NPS_STATUS_NAN_RESET 1u
+#define NPS_STATUS_SCRAM 2u
+typedef struct nps_event { int32_t plant; int32_t row; int32_t step; int32_t reserved; double value; double time_minutes; } nps_event;
+typedef struct nps_monitor {
+    double* d_last_fired;
+    nps_event* d_events;
+    uint32_t* d_n_events;
+    uint32_t event_capacity;
+    int32_t skip_last_check;
+    const int32_t* d_watch_fields;
+    int32_t* d_watch_step;
+    int32_t n_watch;
+    int32_t reserved;
+    int32_t* d_first_scram_step;
+    int32_t* d_first_nan_reset_step;
+    uint32_t* d_status;
+    double* d_reward_k;
+    uint8_t* d_done_k;
+    int64_t step0;
+} nps_monitor;
+int nps_step_monitored(nps_handle* h, double* d_state, const int8_t* d_action, const double* d_magnitude,
+                       const double* d_noise, const double* d_setpoint, int k_substeps, double* d_obs, double* d_reward,
+                       uint8_t* d_done, const nps_monitor* monitor, void* cuda_stream);
+
 /* Device-side noise.  The reference draws its per-step noise inside its Python objects (constant_heat_source.py:178,
  * ph_control_system.py:288,409-420); parity runs pass those very streams in d_noise.  A production batch that passes
  * d_noise == NULL can instead have every (plant, step) draw its five numbers on the device from Philox4x32-10 keyed by
@@ -75,6 +115,11 @@ int nps_device_rng_draws(uint64_t seed, uint64_t plant, uint64_t step, double* o
 /* Test hook: out[i] = x[i] ** y[i] through the step kernel's own power function (csrc/plant/hd.h py_pow: exact
  * specialisations, csrc/plant/fastpow.h for positive finite bases, libdevice pow otherwise), device arrays. */
 int nps_selftest_pow(const double* d_x, const double* d_y, double* d_out, int64_t n, void* cuda_stream);
+
+/* Measurement hook: achieved FP64 FMA throughput of `device` (8 independent DFMA chains per thread, 2 048 threads per
+ * SM, best of 4 timed launches of `iters` iterations; synchronous).  The FP64 side of the roofline in bench.py divides by
+ * this number instead of a datasheet figure. */
+int nps_measure_fp64_peak(int device, int iters, double* out_tflops, double* out_ms);
 
 /* Same step with HOST buffers for the per-step inputs and outputs (pinned or pageable): the
  * host->device copies of action/magnitude/noise and the device->host copies of obs/reward/done are
@@ -134,8 +179,10 @@ int nps_apply_maintenance(nps_handle* h, double* d_state, const int32_t* h_plant
                           const int32_t* h_action, const int32_t* h_arg, int n_requests, int32_t* h_status,
                           void* cuda_stream);
 
-/* gather selected fields of all plants to a host array out[n_fields][n_plants] (synchronous) */
-int nps_read_fields(nps_handle* h, const double* d_state, const int32_t* fields, int n_fields, double* out_host);
+/* gather selected fields of all plants to a host array out[n_fields][n_plants]; runs on `cuda_stream` (ordered after
+ * the launches queued there) and returns after synchronising that stream */
+int nps_read_fields(nps_handle* h, const double* d_state, const int32_t* fields, int n_fields, double* out_host,
+                    void* cuda_stream);
 
 #ifdef __cplusplus
 }

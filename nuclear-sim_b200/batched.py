@@ -53,6 +53,10 @@ class _StateView:
     def __getitem__(self, name: str) -> torch.Tensor:
         return self._sim.slab[field_index()[name]]
 
+    def __setitem__(self, name: str, value) -> None:
+        """``sim.state["sim.cooling_water_temp"] = x`` with a scalar or an [N] array / tensor."""
+        self._sim.slab[field_index()[name]] = torch.as_tensor(value, dtype=torch.float64, device=self._sim.device)
+
 
 class _HeatSourceView:
     """``sim.primary_physics.heat_source.set_power_setpoint`` (constant_heat_source.py:94-102), batched."""
@@ -66,6 +70,26 @@ class _HeatSourceView:
         ix = field_index()
         sim.slab[ix["pri.hs_setpoint_percent"]] = sp
         sim.slab[ix["pri.hs_current_power_mw"]] = (sp / 100.0) * float(sim.params[field_index("PlantParams")["rated_power_mw"]])
+
+
+class _Monitor(ctypes.Structure):
+    """struct nps_monitor of include/nps_b200.h"""
+    _fields_ = [("d_last_fired", ctypes.c_void_p), ("d_events", ctypes.c_void_p), ("d_n_events", ctypes.c_void_p),
+                ("event_capacity", ctypes.c_uint32), ("skip_last_check", ctypes.c_int32),
+                ("d_watch_fields", ctypes.c_void_p), ("d_watch_step", ctypes.c_void_p),
+                ("n_watch", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("d_first_scram_step", ctypes.c_void_p), ("d_first_nan_reset_step", ctypes.c_void_p),
+                ("d_status", ctypes.c_void_p), ("d_reward_k", ctypes.c_void_p), ("d_done_k", ctypes.c_void_p),
+                ("step0", ctypes.c_int64)]
+
+
+EVENT_DTYPE = np.dtype([("plant", np.int32), ("row", np.int32), ("step", np.int32), ("reserved", np.int32),
+                        ("value", np.float64), ("time_minutes", np.float64)])   # struct nps_event
+
+# flag fields whose first non-zero step is stamped by default (SURVEY 8 a-events e3-e12: the latched trips)
+DEFAULT_WATCH = ("fw.pump[0].trip_active", "fw.pump[1].trip_active", "fw.pump[2].trip_active", "fw.pump[3].trip_active",
+                 "fw.prot_system_trip_active", "fw.prot_npsh_low_low_trip_active", "fw.prot_npsh_critical_trip_active",
+                 "turb.prot_trip_active", "cond.vs_trip_high_pressure")
 
 
 class BatchedNuclearPlantSimulator:
@@ -103,6 +127,8 @@ class BatchedNuclearPlantSimulator:
         self.n_launches = 0
         self._thr = None
         self._logged = None
+        self._mon = None
+        self.step_index = 0      # steps taken since construction / reset(); the in-launch monitor stamps events with it
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -125,24 +151,124 @@ class BatchedNuclearPlantSimulator:
             t = t.expand(shape)
         return t.contiguous()
 
-    def step(self, actions=None, magnitudes=None, noise=None, power_setpoint=None, K: int = 1) -> Dict[str, torch.Tensor]:
+    def step(self, actions=None, magnitudes=None, noise=None, power_setpoint=None, K: int = 1,
+             skip_last_check: bool = False) -> Dict[str, torch.Tensor]:
         """K fused calls of NuclearPlantSimulator.step (sim.py:130-258) for every plant.
 
         actions [K,N] or [N] int8 (ControlAction values; None = NO_ACTION); magnitudes [K,N] f64;
         noise [K,5,N] f64 = (z_heat, z_ph, u0, u1, u2) host-supplied streams; power_setpoint [K,N] (NaN = keep).
-        Returns observation [N,22], reward [N], done [N] (bool) of the last substep.
+        Returns observation [N,22] and reward [N] of the last substep and done [N] (bool: a scram was activated in any
+        substep).  With enable_monitor() every substep is observed the way the reference observes every step: event
+        steps are exact whatever K is (first_scram_step, watch_steps(), drain_step_events()).
         """
         a = self._prep(actions, torch.int8, K)
         m = self._prep(magnitudes, torch.float64, K)
         z = self._prep(noise, torch.float64, K, NOISE_PER_STEP)
         sp = self._prep(power_setpoint, torch.float64, K)
-        stream = torch.cuda.current_stream(self.device).cuda_stream
-        _clib.check(self.L.nps_step(self._h, _ptr(self.slab), _ptr(a), _ptr(m), _ptr(z), _ptr(sp), int(K),
-                                    _ptr(self._obs), _ptr(self._reward), _ptr(self._done), ctypes.c_void_p(stream)))
+        mon = self._monitor_struct(int(K), skip_last_check)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _clib.check(self.L.nps_step_monitored(self._h, _ptr(self.slab), _ptr(a), _ptr(m), _ptr(z), _ptr(sp), int(K),
+                                                  _ptr(self._obs), _ptr(self._reward), _ptr(self._done),
+                                                  ctypes.byref(mon) if mon is not None else None, ctypes.c_void_p(stream)))
         self.n_launches += 1
+        self.step_index += int(K)
         if z is None and getattr(self, "_rng", None) is not None:
             self._rng[2] += int(K)
-        return {"observation": self._obs.t(), "reward": self._reward, "done": self._done.bool()}
+        out = {"observation": self._obs.t(), "reward": self._reward, "done": self._done.bool()}
+        if mon is not None and self._mon["per_substep"]:
+            out["reward_k"] = self._mon["reward_k"][:K]
+            out["done_k"] = self._mon["done_k"][:K].bool()
+        return out
+
+    # -- in-launch monitoring (nps_step_monitored) ------------------------------------------------------------------
+    def enable_monitor(self, watch: Optional[Sequence[str]] = DEFAULT_WATCH, event_capacity: Optional[int] = None,
+                       per_substep: bool = False, max_k: int = 128) -> None:
+        """Evaluate after EVERY substep of a fused launch what the reference evaluates after every step: first scram /
+        NaN-reset step and sticky status bits per plant, the first step each `watch` flag field became non-zero, the
+        threshold rows of set_thresholds() (events with their step, drained by drain_step_events()), and with
+        per_substep=True the reward and done of every substep (step() then also returns reward_k / done_k [K, N])."""
+        ix = field_index()
+        watch = list(watch or [])
+        if len(watch) > 32:
+            raise ValueError("at most 32 watched fields")
+        n = self.n_plants
+        dev = self.device
+        cap = int(event_capacity) if event_capacity else max(1 << 16, 4 * n)
+        self._mon = {
+            "watch": watch, "cap": cap, "per_substep": bool(per_substep), "max_k": int(max_k),
+            "watch_fields": torch.as_tensor([ix[w] for w in watch] or [0], dtype=torch.int32, device=dev),
+            "watch_step": torch.full((max(1, len(watch)), n), -1, dtype=torch.int32, device=dev),
+            "first_scram": torch.full((n,), -1, dtype=torch.int32, device=dev),
+            "first_nan_reset": torch.full((n,), -1, dtype=torch.int32, device=dev),
+            "status": torch.zeros((n,), dtype=torch.int32, device=dev),
+            "events": torch.zeros((cap, EVENT_DTYPE.itemsize), dtype=torch.uint8, device=dev),
+            "n_events": torch.zeros((1,), dtype=torch.int32, device=dev),
+            "reward_k": torch.empty((max_k, n), dtype=torch.float64, device=dev) if per_substep else None,
+            "done_k": torch.empty((max_k, n), dtype=torch.uint8, device=dev) if per_substep else None,
+        }
+
+    def disable_monitor(self) -> None:
+        self._mon = None
+
+    def _monitor_struct(self, K: int, skip_last_check: bool):
+        g = self._mon
+        if g is None:
+            return None
+        if g["per_substep"] and K > g["max_k"]:
+            raise ValueError(f"K={K} exceeds the monitor's max_k={g['max_k']}")
+        m = _Monitor()
+        thr = self._thr
+        if thr is not None:
+            m.d_last_fired = thr["last"].data_ptr()
+            m.d_events = g["events"].data_ptr()
+            m.d_n_events = g["n_events"].data_ptr()
+            m.event_capacity = g["cap"]
+        m.skip_last_check = 1 if skip_last_check else 0
+        m.n_watch = len(g["watch"])
+        m.d_watch_fields = g["watch_fields"].data_ptr()
+        m.d_watch_step = g["watch_step"].data_ptr()
+        m.d_first_scram_step = g["first_scram"].data_ptr()
+        m.d_first_nan_reset_step = g["first_nan_reset"].data_ptr()
+        m.d_status = g["status"].data_ptr()
+        if g["per_substep"]:
+            m.d_reward_k = g["reward_k"].data_ptr()
+            m.d_done_k = g["done_k"].data_ptr()
+        m.step0 = self.step_index
+        return m
+
+    def drain_step_events(self) -> np.ndarray:
+        """Threshold violations recorded inside the launches since the last drain, as a structured array
+        (plant, row, step, value, time_minutes) sorted by (step, plant, row); clears the device list."""
+        g = self._mon
+        if g is None:
+            raise _clib.NpsError("enable_monitor() first")
+        n = int(g["n_events"].item())
+        if n == 0:
+            return np.zeros(0, dtype=EVENT_DTYPE)
+        if n > g["cap"]:
+            raise _clib.NpsError(f"event list overflow: {n} violations, capacity {g['cap']} (enable_monitor(event_capacity=...))")
+        ev = g["events"][:n].cpu().numpy().view(EVENT_DTYPE).reshape(-1).copy()
+        g["n_events"].zero_()
+        return ev[np.lexsort((ev["row"], ev["plant"], ev["step"]))]
+
+    @property
+    def first_scram_step(self) -> torch.Tensor:
+        return self._mon["first_scram"]
+
+    @property
+    def first_nan_reset_step(self) -> torch.Tensor:
+        return self._mon["first_nan_reset"]
+
+    @property
+    def status(self) -> torch.Tensor:
+        """Sticky per-plant status word: bit 0 a NaN reset happened (thermal_hydraulics.py:257-269), bit 1 scram latched."""
+        return self._mon["status"]
+
+    def watch_steps(self) -> Dict[str, torch.Tensor]:
+        """{watched field: Tensor[N] int32 first step at which it was non-zero, -1 = never}."""
+        g = self._mon
+        return {w: g["watch_step"][i] for i, w in enumerate(g["watch"])}
 
     def set_device_rng(self, seed: Optional[int], plant_offset: int = 0, first_step: int = 0) -> None:
         """Device-side noise (nps_set_device_rng): with a seed, step(noise=None) draws every plant-step's five random
@@ -195,12 +321,26 @@ class BatchedNuclearPlantSimulator:
         return self._obs.t()
 
     def reset(self, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Back to the initial state (all plants, or the masked ones).  A reset plant starts a new episode: its clock
+        restarts, so its threshold cooldown stamps and monitor stamps are forgotten as well."""
         if mask is None:
             self.slab.copy_(self._initial)
+            m = slice(None)
         else:
             m = torch.as_tensor(mask, dtype=torch.bool, device=self.device)
             self.slab[:, m] = self._initial[:, m]
+        self._forget_episode(m)
         return self.get_observation()
+
+    def _forget_episode(self, m) -> None:
+        if self._thr is not None:
+            self._thr["last"][:, m] = -float("inf")
+        if self._mon is not None:
+            g = self._mon
+            g["watch_step"][:, m] = -1
+            g["first_scram"][m] = -1
+            g["first_nan_reset"][m] = -1
+            g["status"][m] = 0
 
     # -- single-plant conveniences used by the scalar NuclearPlantSimulator facade (plant_simulator.py) ----------
     def step_plant(self, plant: int, action: int, magnitude: float, z: np.ndarray):
@@ -222,12 +362,17 @@ class BatchedNuclearPlantSimulator:
 
     def reset_plant(self, plant: int) -> None:
         self.slab[:, plant] = self._initial[:, plant]
+        self._forget_episode(int(plant))
 
     def write_fields(self, plant: int, values: Dict[int, float]) -> None:
         for f, v in values.items():
             self.slab[int(f), int(plant)] = float(v)
 
     # -- state access -------------------------------------------------------------------------
+    def current_time_minutes(self) -> float:
+        """The batch clock (plants stepped in lockstep share it): sim.time_minutes of plant 0."""
+        return float(self.slab[field_index()["sim.time_minutes"], 0].item())
+
     def state_numpy(self) -> np.ndarray:
         """[n_plants, n_state] host copy in PlantState field order."""
         return self.slab.t().contiguous().cpu().numpy()
@@ -236,8 +381,9 @@ class BatchedNuclearPlantSimulator:
         ix = field_index()
         ids = np.array([ix[n] for n in names], dtype=np.int32)
         out = np.empty((len(ids), self.n_plants), dtype=np.float64)
+        stream = torch.cuda.current_stream(self.device).cuda_stream   # ordered after the launches queued on this stream
         _clib.check(self.L.nps_read_fields(self._h, _ptr(self.slab), ids.ctypes.data_as(ctypes.c_void_p), len(ids),
-                                           out.ctypes.data_as(ctypes.c_void_p)))
+                                           out.ctypes.data_as(ctypes.c_void_p), ctypes.c_void_p(stream)))
         return out
 
     # -- threshold monitoring (state_manager.py:1307-1369) --------------------------------------

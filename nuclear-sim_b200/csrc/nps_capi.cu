@@ -33,6 +33,15 @@ static int fail(const char* what, cudaError_t e = cudaSuccess) {
 }
 #define NPS_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail(#call, e__); } while (0)
 
+// every entry point that launches or copies runs on the handle's device and leaves the caller's current device alone
+struct DeviceGuard {
+    int prev = -1; bool switched = false;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != device) switched = (cudaSetDevice(device) == cudaSuccess);
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+
 constexpr int kNState = (int)(sizeof(PlantState) / sizeof(double));
 constexpr int kNParams = (int)(sizeof(PlantParams) / sizeof(double));
 static_assert(kNState == NPS_GEN_N_STATE, "state.h and fields_gen.inc disagree; rerun the build");
@@ -54,6 +63,10 @@ struct nps_handle {
     int32_t* d_word_start = nullptr;   // live rows are sorted by table row: [word w] = d_thresholds[d_word_start[w] .. d_word_start[w + 1])
     int32_t* d_logged = nullptr; int n_logged = 0;
     int32_t* d_gather_fields = nullptr; double* d_gather_out = nullptr; int gather_cap = 0;
+    // nps_apply_maintenance: request / group / status buffers grow geometrically and are reused (no cudaMalloc per call);
+    // the host mirrors are pinned so the copies are truly asynchronous on the caller's stream
+    struct MaintBuf { void* d_req = nullptr; int32_t* d_start = nullptr; int32_t* d_status = nullptr;
+                      void* h_req = nullptr; int32_t* h_start = nullptr; int32_t* h_status = nullptr; int cap = 0; } mb;
     // nps_step_host_async: NPS_PIPE_DEPTH staging sets, so the host->device copy of a launch is issued several
     // kernels ahead of its use (a sporadically slow PCIe transfer then costs nothing) and overlaps the running kernel
     struct Pipe {
@@ -84,46 +97,153 @@ struct nps_handle {
 #define NPS_PRAGMA_UNROLL(n) _Pragma(NPS_STR_(unroll n))
 constexpr int kLargeBatch = 148 * 448 / 2;
 
+// ------------------------------------------------------------------------------------------------
+// in-launch monitoring: what the reference does after the physics of EVERY step (sim.py:209-223,256) evaluated after
+// every fused substep, so a K-substep launch reports the same (event, step) pairs as K single-step launches:
+//   * threshold rows (StateManager._check_maintenance_thresholds: state_manager.py:1307-1369) with their cooldown
+//     stamps; violations are appended to a device event list (warp ballot -> one atomic per warp per row),
+//   * first step a watched flag field became non-zero (latched trips, FSM states: SURVEY 8 a-events e3-e12),
+//   * first scram step / first NaN-reset step / sticky status bits, per-substep reward and done.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxSharedRows = 128;
+struct MonitorArgs {
+    int enabled, n_live, skip_last_check, n_watch;
+    const Threshold* live; double* last_fired;
+    nps_event* events; uint32_t* n_events; uint32_t event_cap; uint32_t pad;
+    const int32_t* watch_fields; int32_t* watch_step;
+    int32_t* first_scram_step; int32_t* first_nan_reset_step; uint32_t* status;
+    double* reward_k; uint8_t* done_k;
+    int64_t step0;
+};
+struct StepArgs {
+    double* slab; const int8_t* action; const double* magnitude; const double* noise; const double* setpoint;
+    double* obs; double* reward; uint8_t* done;
+    int64_t n; int k_substeps; int pad;
+    RngConfig rng; MonitorArgs mon;
+};
+
+__device__ __forceinline__ double derived_from_state(const PlantState& st, int code) {
+    const int k = -code - 2, kind = k >> 2, unit = k & 3;
+    if (kind == 0) {   // sum_wear_level: feedwater/pump_lubrication.py:1585-1596
+        const double* w = st.fw.pump[unit].lub.component_wear;
+        return w[0] + py_max3(w[FWL_MOTOR_BRG], w[FWL_PUMP_BRG], w[FWL_THRUST_BRG]) + w[FWL_SEALS];
+    }
+    return NAN;
+}
+
+__device__ __forceinline__ bool threshold_compare(int cmp, double v, double x) {   // _check_threshold_condition: state_manager.py:1412-1442
+    switch (cmp) {
+        case 0: return v > x;
+        case 1: return v < x;
+        case 2: return v >= x;
+        case 3: return v <= x;
+        case 4: return fabs(v - x) < 1e-3;
+        case 5: return fabs(v - x) >= 1e-3;
+        default: return false;
+    }
+}
+
+__device__ __noinline__ void monitor_substep(const PlantState& st, const MonitorArgs& mon, const Threshold* rows,
+                                             int64_t n, int64_t p, int k, bool last, unsigned warp_mask, unsigned step_status,
+                                             unsigned& seen_watch) {
+    const double* sv = reinterpret_cast<const double*>(&st);
+    const int32_t step = (int32_t)(mon.step0 + k);
+    if (step_status) {
+        if (mon.status) mon.status[p] |= step_status;
+        if ((step_status & kStatusScram) && mon.first_scram_step && mon.first_scram_step[p] < 0) mon.first_scram_step[p] = step;
+        if ((step_status & kStatusNanReset) && mon.first_nan_reset_step && mon.first_nan_reset_step[p] < 0) mon.first_nan_reset_step[p] = step;
+    }
+    for (int w = 0; w < mon.n_watch; ++w) {
+        if (!((seen_watch >> w) & 1u) && sv[mon.watch_fields[w]] != 0.0) {
+            mon.watch_step[(int64_t)w * n + p] = step;
+            seen_watch |= 1u << w;
+        }
+    }
+    if (mon.last_fired && !(last && mon.skip_last_check)) {
+        const double now = st.sim.time_minutes;
+        const unsigned lane = threadIdx.x & 31u;
+        for (int j = 0; j < mon.n_live; ++j) {
+            const Threshold th = rows[j];
+            const double v = (th.field >= 0) ? sv[th.field] : derived_from_state(st, th.field);
+            bool fire = threshold_compare(th.cmp, v, th.value);
+            if (fire) {   // _is_threshold_in_cooldown (state_manager.py:1267-1305) only matters for rows that would fire
+                double* stamp = mon.last_fired + (int64_t)th.row * n + p;
+                if ((now - *stamp) < th.cooldown) fire = false;
+                else *stamp = now;      // _record_threshold_violation_time
+            }
+            const unsigned m = __ballot_sync(warp_mask, fire);
+            if (m) {
+                const int leader = __ffs(m) - 1;
+                uint32_t base = 0;
+                if ((int)lane == leader) base = atomicAdd(mon.n_events, (uint32_t)__popc(m));
+                base = __shfl_sync(warp_mask, base, leader);
+                if (fire) {
+                    const uint32_t slot = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+                    if (slot < mon.event_cap) mon.events[slot] = nps_event{(int32_t)p, th.row, step, 0, v, now};
+                }
+            }
+        }
+    }
+}
+
 template <int BLOCK, int MINBLOCKS>
 __global__ void __launch_bounds__(BLOCK, MINBLOCKS)
-nps_step_kernel(double* __restrict__ slab, const __grid_constant__ PlantParams prm, const int8_t* __restrict__ action,
-                const double* __restrict__ magnitude, const double* __restrict__ noise,
-                const double* __restrict__ setpoint, int k_substeps, int64_t n,
-                double* __restrict__ obs, double* __restrict__ reward, uint8_t* __restrict__ done, const RngConfig rng) {
+nps_step_kernel(const __grid_constant__ PlantParams prm, const __grid_constant__ StepArgs a) {
+    __shared__ Threshold s_rows[kMaxSharedRows];
+    const MonitorArgs& mon = a.mon;
+    const Threshold* rows = mon.live;
+    if (mon.enabled && mon.n_live > 0 && mon.n_live <= kMaxSharedRows) {
+        for (int j = threadIdx.x; j < mon.n_live; j += BLOCK) s_rows[j] = mon.live[j];
+        __syncthreads();
+        rows = s_rows;
+    }
+    const int64_t n = a.n;
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned warp_mask = __ballot_sync(0xffffffffu, p < n);
     if (p >= n) return;
+    double* __restrict__ slab = a.slab;
     PlantState st;
     double* sv = reinterpret_cast<double*>(&st);
 NPS_PRAGMA_UNROLL(NPS_COPY_UNROLL)
     for (int f = 0; f < kNState; ++f) sv[f] = slab[(int64_t)f * n + p];
     bool scrammed = false;
+    unsigned seen_watch = 0;
+    if (mon.enabled)
+        for (int w = 0; w < mon.n_watch; ++w) if (mon.watch_step[(int64_t)w * n + p] >= 0) seen_watch |= 1u << w;
+    const int k_substeps = a.k_substeps;
     for (int k = 0; k < k_substeps; ++k) {
         StepInput in;
-        in.action = action ? (int)action[(int64_t)k * n + p] : (int)ACT_NO_ACTION;
-        in.magnitude = magnitude ? magnitude[(int64_t)k * n + p] : 1.0;
-        if (noise) {
-            const double* z = noise + (int64_t)k * NPS_NOISE_PER_STEP * n + p;
+        in.action = a.action ? (int)a.action[(int64_t)k * n + p] : (int)ACT_NO_ACTION;
+        in.magnitude = a.magnitude ? a.magnitude[(int64_t)k * n + p] : 1.0;
+        if (a.noise) {
+            const double* z = a.noise + (int64_t)k * NPS_NOISE_PER_STEP * n + p;
             in.z_heat = z[0]; in.z_ph = z[n]; in.u_ph[0] = z[2 * n]; in.u_ph[1] = z[3 * n]; in.u_ph[2] = z[4 * n];
-        } else if (rng.enabled) {
-            const StepDraws d = plant_step_draws(rng.seed, rng.plant_offset + (uint64_t)p, rng.step0 + (uint64_t)k);
+        } else if (a.rng.enabled) {
+            const StepDraws d = plant_step_draws(a.rng.seed, a.rng.plant_offset + (uint64_t)p, a.rng.step0 + (uint64_t)k);
             in.z_heat = d.z_heat; in.z_ph = d.z_ph; in.u_ph[0] = d.u_ph[0]; in.u_ph[1] = d.u_ph[1]; in.u_ph[2] = d.u_ph[2];
         } else {
             in.z_heat = 0.0; in.z_ph = 0.0; in.u_ph[0] = 1.0; in.u_ph[1] = 1.0; in.u_ph[2] = 1.0;
         }
-        in.power_setpoint = setpoint ? setpoint[(int64_t)k * n + p] : NAN;
+        in.power_setpoint = a.setpoint ? a.setpoint[(int64_t)k * n + p] : NAN;
         in.emit_outputs = (k == k_substeps - 1);
         plant_step(st, prm, in);
-        scrammed |= is_true(st.pri.scram_activated);
+        const bool scram_now = is_true(st.pri.scram_activated);
+        scrammed |= scram_now;
+        if (mon.enabled) {
+            monitor_substep(st, mon, rows, n, p, k, k == k_substeps - 1, warp_mask, in.status, seen_watch);
+            if (mon.reward_k) mon.reward_k[(int64_t)k * n + p] = plant_reward(st, prm);
+            if (mon.done_k) mon.done_k[(int64_t)k * n + p] = scram_now ? 1 : 0;
+        }
     }
 NPS_PRAGMA_UNROLL(NPS_COPY_UNROLL)
     for (int f = 0; f < kNState; ++f) slab[(int64_t)f * n + p] = sv[f];
-    if (obs) {
+    if (a.obs) {
         struct ObsOut { double* o; int64_t n; int64_t p; struct Ref { double* a; NPS_HD void operator=(double v) { *a = v; } };
-                        __device__ Ref operator[](int i) { return Ref{o + (int64_t)i * n + p}; } } out{obs, n, p};
+                        __device__ Ref operator[](int i) { return Ref{o + (int64_t)i * n + p}; } } out{a.obs, n, p};
         plant_observe(st, prm, out);
     }
-    if (reward) reward[p] = plant_reward(st, prm);
-    if (done) done[p] = scrammed ? 1 : 0;
+    if (a.reward) a.reward[p] = plant_reward(st, prm);
+    if (a.done) a.done[p] = scrammed ? 1 : 0;
 }
 
 template <class T>
@@ -381,7 +501,7 @@ int nps_create(int64_t n_plants, int device, nps_handle** out) {
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count <= 0) return fail("nps_create: no CUDA device (this library has no CPU fallback)", e);
     if (device < 0 || device >= count) return fail("nps_create: device index out of range");
-    NPS_CUDA(cudaSetDevice(device));
+    DeviceGuard guard(device);
     nps_handle* h = new nps_handle();
     h->n = n_plants; h->device = device;
     std::memset(&h->params, 0, sizeof(PlantParams));
@@ -401,10 +521,12 @@ int nps_create(int64_t n_plants, int device, nps_handle** out) {
 
 void nps_destroy(nps_handle* h) {
     if (!h) return;
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     cudaFree(h->d_setpoint); cudaFree(h->d_action); cudaFree(h->d_mag); cudaFree(h->d_noise);
     cudaFree(h->d_obs); cudaFree(h->d_reward); cudaFree(h->d_done); cudaFree(h->d_thresholds); cudaFree(h->d_word_start);
     cudaFree(h->d_logged); cudaFree(h->d_gather_fields); cudaFree(h->d_gather_out);
+    cudaFree(h->mb.d_req); cudaFree(h->mb.d_start); cudaFree(h->mb.d_status);
+    cudaFreeHost(h->mb.h_req); cudaFreeHost(h->mb.h_start); cudaFreeHost(h->mb.h_status);
     for (auto& q : h->pipe) {
         cudaFree(q.d_action); cudaFree(q.d_mag); cudaFree(q.d_noise); cudaFree(q.d_setpoint);
         cudaFree(q.d_obs); cudaFree(q.d_reward); cudaFree(q.d_done);
@@ -426,27 +548,56 @@ int nps_set_params(nps_handle* h, const double* params_host, int n_params) {
     return 0;
 }
 
-int nps_step(nps_handle* h, double* d_state, const int8_t* d_action, const double* d_magnitude, const double* d_noise,
-             const double* d_setpoint, int k_substeps, double* d_obs, double* d_reward, uint8_t* d_done,
-             void* cuda_stream) {
-    if (!h || !d_state) return fail("nps_step: null argument");
-    if (k_substeps <= 0) return fail("nps_step: k_substeps must be positive");
-    cudaStream_t s = (cudaStream_t)cuda_stream;
-    RngConfig rng = h->rng;
-    if (rng.enabled && !d_noise) h->rng.step0 += (uint64_t)k_substeps;   // the next launch continues the stream
+static int launch_step(nps_handle* h, const StepArgs& a, cudaStream_t s) {
 #if defined(NPS_STEP_BLOCK)
-    nps_step_kernel<NPS_STEP_BLOCK, NPS_STEP_MINBLOCKS><<<(int)((h->n + NPS_STEP_BLOCK - 1) / NPS_STEP_BLOCK), NPS_STEP_BLOCK, 0, s>>>(
-        d_state, h->params, d_action, d_magnitude, d_noise, d_setpoint, k_substeps, h->n, d_obs, d_reward, d_done, rng);
+    nps_step_kernel<NPS_STEP_BLOCK, NPS_STEP_MINBLOCKS><<<(int)((h->n + NPS_STEP_BLOCK - 1) / NPS_STEP_BLOCK), NPS_STEP_BLOCK, 0, s>>>(h->params, a);
 #else
-    if (h->n >= kLargeBatch)
-        nps_step_kernel<448, 1><<<(int)((h->n + 447) / 448), 448, 0, s>>>(d_state, h->params, d_action, d_magnitude, d_noise,
-                                                                         d_setpoint, k_substeps, h->n, d_obs, d_reward, d_done, rng);
-    else
-        nps_step_kernel<64, 7><<<(int)((h->n + 63) / 64), 64, 0, s>>>(d_state, h->params, d_action, d_magnitude, d_noise,
-                                                                      d_setpoint, k_substeps, h->n, d_obs, d_reward, d_done, rng);
+    if (h->n >= kLargeBatch) nps_step_kernel<448, 1><<<(int)((h->n + 447) / 448), 448, 0, s>>>(h->params, a);
+    else nps_step_kernel<64, 7><<<(int)((h->n + 63) / 64), 64, 0, s>>>(h->params, a);
 #endif
     NPS_CUDA(cudaGetLastError());
     return 0;
+}
+
+int nps_step_monitored(nps_handle* h, double* d_state, const int8_t* d_action, const double* d_magnitude, const double* d_noise,
+                       const double* d_setpoint, int k_substeps, double* d_obs, double* d_reward, uint8_t* d_done,
+                       const nps_monitor* mon, void* cuda_stream) {
+    if (!h || !d_state) return fail("nps_step: null argument");
+    if (k_substeps <= 0) return fail("nps_step: k_substeps must be positive");
+    DeviceGuard guard(h->device);
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    StepArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.slab = d_state; a.action = d_action; a.magnitude = d_magnitude; a.noise = d_noise; a.setpoint = d_setpoint;
+    a.obs = d_obs; a.reward = d_reward; a.done = d_done; a.n = h->n; a.k_substeps = k_substeps;
+    a.rng = h->rng;
+    if (a.rng.enabled && !d_noise) h->rng.step0 += (uint64_t)k_substeps;   // the next launch continues the stream
+    if (mon) {
+        MonitorArgs& m = a.mon;
+        if (mon->d_last_fired) {
+            if (h->n_thresholds == 0) return fail("nps_step_monitored: d_last_fired given but no thresholds set");
+            if (!mon->d_events || !mon->d_n_events || mon->event_capacity == 0) return fail("nps_step_monitored: threshold evaluation needs an event list");
+        }
+        if (mon->n_watch < 0 || mon->n_watch > 32) return fail("nps_step_monitored: at most 32 watched fields");
+        if (mon->n_watch > 0 && (!mon->d_watch_fields || !mon->d_watch_step)) return fail("nps_step_monitored: null watch arrays");
+        m.enabled = 1;
+        m.n_live = mon->d_last_fired ? h->n_live_thresholds : 0;
+        m.skip_last_check = mon->skip_last_check;
+        m.n_watch = mon->n_watch;
+        m.live = h->d_thresholds; m.last_fired = mon->d_last_fired;
+        m.events = mon->d_events; m.n_events = mon->d_n_events; m.event_cap = mon->event_capacity;
+        m.watch_fields = mon->d_watch_fields; m.watch_step = mon->d_watch_step;
+        m.first_scram_step = mon->d_first_scram_step; m.first_nan_reset_step = mon->d_first_nan_reset_step; m.status = mon->d_status;
+        m.reward_k = mon->d_reward_k; m.done_k = mon->d_done_k; m.step0 = mon->step0;
+    }
+    return launch_step(h, a, s);
+}
+
+int nps_step(nps_handle* h, double* d_state, const int8_t* d_action, const double* d_magnitude, const double* d_noise,
+             const double* d_setpoint, int k_substeps, double* d_obs, double* d_reward, uint8_t* d_done,
+             void* cuda_stream) {
+    return nps_step_monitored(h, d_state, d_action, d_magnitude, d_noise, d_setpoint, k_substeps, d_obs, d_reward, d_done,
+                              nullptr, cuda_stream);
 }
 
 static int ensure_staging(nps_handle* h, int k) {
@@ -471,7 +622,7 @@ int nps_step_host(nps_handle* h, double* d_state, const int8_t* h_action, const 
                   uint8_t* h_done, void* cuda_stream) {
     if (!h || !d_state) return fail("nps_step_host: null argument");
     if (k_substeps <= 0) return fail("nps_step_host: k_substeps must be positive");
-    NPS_CUDA(cudaSetDevice(h->device));
+    DeviceGuard guard(h->device);
     if (ensure_staging(h, k_substeps)) return -1;
     cudaStream_t s = (cudaStream_t)cuda_stream;
     const size_t kn = (size_t)k_substeps * h->n;
@@ -521,7 +672,7 @@ int nps_step_host_async(nps_handle* h, double* d_state, const int8_t* h_action, 
                         uint8_t* h_done, void* cuda_stream) {
     if (!h || !d_state) return fail("nps_step_host_async: null argument");
     if (k_substeps <= 0) return fail("nps_step_host_async: k_substeps must be positive");
-    NPS_CUDA(cudaSetDevice(h->device));
+    DeviceGuard guard(h->device);
     if (ensure_pipe(h, k_substeps)) return -1;
     cudaStream_t s = (cudaStream_t)cuda_stream;
     const int slot = (int)(h->pipe_count++ % NPS_PIPE_DEPTH);
@@ -563,6 +714,50 @@ int nps_selftest_pow(const double* d_x, const double* d_y, double* d_out, int64_
     return 0;
 }
 
+// FP64 peak microbenchmark (SURVEY 6 / BASELINE.md 2): kChains independent DFMA chains per thread, full occupancy.
+// -fmad=false does not touch explicit __fma_rn, so every loop iteration is kChains DFMA instructions.
+constexpr int kFmaChains = 8;
+__global__ void __launch_bounds__(256) nps_fp64_fma_kernel(double* __restrict__ out, int iters, double a, double b) {
+    double x[kFmaChains];
+#pragma unroll
+    for (int c = 0; c < kFmaChains; ++c) x[c] = (double)(threadIdx.x + c) * 1e-3;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int c = 0; c < kFmaChains; ++c) x[c] = __fma_rn(x[c], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < kFmaChains; ++c) s += x[c];
+    if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;   // keeps the chains alive, never true in practice
+}
+
+int nps_measure_fp64_peak(int device, int iters, double* out_tflops, double* out_ms) {
+    if (!out_tflops || iters <= 0) return fail("nps_measure_fp64_peak: bad arguments");
+    DeviceGuard guard(device);
+    int sms = 0;
+    NPS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const int blocks = sms * 8, threads = 256;      // 2 048 threads per SM: every scheduler has 16 warps of DFMA work
+    double* d_out = nullptr;
+    NPS_CUDA(cudaMalloc(&d_out, sizeof(double) * blocks * threads));
+    cudaEvent_t e0, e1;
+    NPS_CUDA(cudaEventCreate(&e0)); NPS_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {   // rep 0 is the warm-up
+        NPS_CUDA(cudaEventRecord(e0, 0));
+        nps_fp64_fma_kernel<<<blocks, threads>>>(d_out, iters, 0.999999, 1e-9);
+        NPS_CUDA(cudaEventRecord(e1, 0));
+        NPS_CUDA(cudaEventSynchronize(e1));
+        float ms = 0; NPS_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    NPS_CUDA(cudaGetLastError());
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
+    const double flops = 2.0 * kFmaChains * (double)iters * blocks * threads;
+    *out_tflops = flops / (best * 1e-3) / 1e12;
+    if (out_ms) *out_ms = best;
+    return 0;
+}
+
 int nps_pipe_depth(void) { return NPS_PIPE_DEPTH; }
 
 int nps_set_device_rng(nps_handle* h, int enabled, uint64_t seed, uint64_t plant_offset, uint64_t first_step) {
@@ -581,6 +776,7 @@ int nps_device_rng_draws(uint64_t seed, uint64_t plant, uint64_t step, double* o
 
 int nps_wait(nps_handle* h, int ticket) {
     if (!h || ticket < 0 || ticket >= NPS_PIPE_DEPTH || !h->pipe[ticket].out_done) return fail("nps_wait: bad ticket");
+    DeviceGuard guard(h->device);
     NPS_CUDA(cudaEventSynchronize(h->pipe[ticket].out_done));
     if (h->pipe_trace) {   // where one pipelined step spent its time on the device
         nps_handle::Pipe& q = h->pipe[ticket];
@@ -596,6 +792,7 @@ int nps_wait(nps_handle* h, int ticket) {
 
 int nps_observe(nps_handle* h, const double* d_state, double* d_obs, double* d_reward, void* cuda_stream) {
     if (!h || !d_state) return fail("nps_observe: null argument");
+    DeviceGuard guard(h->device);
     const int block = 64;
     const int grid = (int)((h->n + block - 1) / block);
     nps_observe_kernel<<<grid, block, 0, (cudaStream_t)cuda_stream>>>(d_state, h->params, h->n, d_obs, d_reward);
@@ -606,7 +803,7 @@ int nps_observe(nps_handle* h, const double* d_state, double* d_obs, double* d_r
 int nps_set_thresholds(nps_handle* h, const int32_t* field, const int32_t* comparator, const double* value,
                        const double* cooldown_minutes, int n_thresholds) {
     if (!h || n_thresholds < 0) return fail("nps_set_thresholds: bad arguments");
-    NPS_CUDA(cudaSetDevice(h->device));
+    DeviceGuard guard(h->device);
     cudaFree(h->d_thresholds); h->d_thresholds = nullptr; h->n_thresholds = 0;
     cudaFree(h->d_word_start); h->d_word_start = nullptr;
     if (n_thresholds == 0) return 0;
@@ -634,6 +831,7 @@ int nps_check_thresholds(nps_handle* h, const double* d_state, double* d_last_fi
                          uint32_t* d_any_warp, void* cuda_stream) {
     if (!h || !d_state || !d_last_fired || !d_flags) return fail("nps_check_thresholds: null argument");
     if (h->n_thresholds == 0) return fail("nps_check_thresholds: no thresholds set");
+    DeviceGuard guard(h->device);
     cudaStream_t s = (cudaStream_t)cuda_stream;
     const int n_words = (h->n_thresholds + 31) / 32;
     if (d_any_warp) NPS_CUDA(cudaMemsetAsync(d_any_warp, 0, sizeof(uint32_t) * (size_t)((h->n + 31) / 32), s));
@@ -651,7 +849,7 @@ int nps_check_thresholds(nps_handle* h, const double* d_state, double* d_last_fi
 
 int nps_set_logged_fields(nps_handle* h, const int32_t* fields, int n_logged) {
     if (!h || n_logged < 0) return fail("nps_set_logged_fields: bad arguments");
-    NPS_CUDA(cudaSetDevice(h->device));
+    DeviceGuard guard(h->device);
     cudaFree(h->d_logged); h->d_logged = nullptr; h->n_logged = 0;
     if (n_logged == 0) return 0;
     for (int i = 0; i < n_logged; ++i) if (fields[i] < 0 || fields[i] >= kNState) return fail("nps_set_logged_fields: field index out of range");
@@ -665,6 +863,7 @@ int nps_log_row(nps_handle* h, const double* d_state, double* d_ring, int64_t ri
                 void* cuda_stream) {
     if (!h || !d_state || !d_ring || ring_rows <= 0) return fail("nps_log_row: bad arguments");
     if (h->n_logged == 0) return fail("nps_log_row: no logged fields set");
+    DeviceGuard guard(h->device);
     double* row = d_ring + (write_index % ring_rows) * (int64_t)h->n_logged * h->n;
     const bool aligned = (h->n % 2 == 0) && ((reinterpret_cast<uintptr_t>(d_state) | reinterpret_cast<uintptr_t>(d_ring)) % 16 == 0);
     if (aligned && !h->log_row_tile_only) {
@@ -702,7 +901,7 @@ int nps_apply_maintenance(nps_handle* h, double* d_state, const int32_t* h_plant
     if (!h || !d_state || n_requests < 0) return fail("nps_apply_maintenance: bad arguments");
     if (n_requests == 0) return 0;
     if (!h_plant || !h_target || !h_action || !h_status) return fail("nps_apply_maintenance: null request arrays");
-    NPS_CUDA(cudaSetDevice(h->device));
+    DeviceGuard guard(h->device);
     cudaStream_t s = (cudaStream_t)cuda_stream;
     // group requests by plant, keeping the caller's order inside each plant (stable)
     std::vector<int> order(n_requests);
@@ -722,38 +921,55 @@ int nps_apply_maintenance(nps_handle* h, double* d_state, const int32_t* h_plant
     }
     const int n_groups = (int)start.size();
     start.push_back(n_requests);
-    MaintRequest* d_req = nullptr; int32_t* d_start = nullptr; int32_t* d_status = nullptr;
-    NPS_CUDA(cudaMalloc(&d_req, sizeof(MaintRequest) * n_requests));
-    NPS_CUDA(cudaMalloc(&d_start, sizeof(int32_t) * start.size()));
-    NPS_CUDA(cudaMalloc(&d_status, sizeof(int32_t) * n_requests));
-    NPS_CUDA(cudaMemcpyAsync(d_req, req.data(), sizeof(MaintRequest) * n_requests, cudaMemcpyHostToDevice, s));
-    NPS_CUDA(cudaMemcpyAsync(d_start, start.data(), sizeof(int32_t) * start.size(), cudaMemcpyHostToDevice, s));
+    nps_handle::MaintBuf& mb = h->mb;
+    if (mb.cap < n_requests) {
+        int cap = mb.cap ? mb.cap : 1024;
+        while (cap < n_requests) cap *= 2;
+        cudaFree(mb.d_req); cudaFree(mb.d_start); cudaFree(mb.d_status);
+        cudaFreeHost(mb.h_req); cudaFreeHost(mb.h_start); cudaFreeHost(mb.h_status);
+        mb = nps_handle::MaintBuf();
+        NPS_CUDA(cudaMalloc(&mb.d_req, sizeof(MaintRequest) * cap));
+        NPS_CUDA(cudaMalloc(&mb.d_start, sizeof(int32_t) * (cap + 1)));
+        NPS_CUDA(cudaMalloc(&mb.d_status, sizeof(int32_t) * cap));
+        NPS_CUDA(cudaMallocHost(&mb.h_req, sizeof(MaintRequest) * cap));
+        NPS_CUDA(cudaMallocHost(&mb.h_start, sizeof(int32_t) * (cap + 1)));
+        NPS_CUDA(cudaMallocHost(&mb.h_status, sizeof(int32_t) * cap));
+        mb.cap = cap;
+    }
+    std::memcpy(mb.h_req, req.data(), sizeof(MaintRequest) * n_requests);
+    std::memcpy(mb.h_start, start.data(), sizeof(int32_t) * start.size());
+    NPS_CUDA(cudaMemcpyAsync(mb.d_req, mb.h_req, sizeof(MaintRequest) * n_requests, cudaMemcpyHostToDevice, s));
+    NPS_CUDA(cudaMemcpyAsync(mb.d_start, mb.h_start, sizeof(int32_t) * start.size(), cudaMemcpyHostToDevice, s));
     const int block = 32;
-    nps_maintenance_kernel<<<(n_groups + block - 1) / block, block, 0, s>>>(d_state, h->params, d_req, d_start, n_groups, d_status, h->n);
+    nps_maintenance_kernel<<<(n_groups + block - 1) / block, block, 0, s>>>(d_state, h->params, (const MaintRequest*)mb.d_req, mb.d_start,
+                                                                           n_groups, mb.d_status, h->n);
     NPS_CUDA(cudaGetLastError());
-    std::vector<int32_t> st(n_requests);
-    NPS_CUDA(cudaMemcpyAsync(st.data(), d_status, sizeof(int32_t) * n_requests, cudaMemcpyDeviceToHost, s));
+    NPS_CUDA(cudaMemcpyAsync(mb.h_status, mb.d_status, sizeof(int32_t) * n_requests, cudaMemcpyDeviceToHost, s));
     NPS_CUDA(cudaStreamSynchronize(s));
-    for (int j = 0; j < n_requests; ++j) h_status[order[j]] = st[j];
-    cudaFree(d_req); cudaFree(d_start); cudaFree(d_status);
+    for (int j = 0; j < n_requests; ++j) h_status[order[j]] = mb.h_status[j];
     return 0;
 }
 
-int nps_read_fields(nps_handle* h, const double* d_state, const int32_t* fields, int n_fields, double* out_host) {
+int nps_read_fields(nps_handle* h, const double* d_state, const int32_t* fields, int n_fields, double* out_host,
+                    void* cuda_stream) {
     if (!h || !d_state || !fields || !out_host || n_fields <= 0) return fail("nps_read_fields: bad arguments");
-    NPS_CUDA(cudaSetDevice(h->device));
+    DeviceGuard guard(h->device);
+    cudaStream_t s = (cudaStream_t)cuda_stream;
     for (int i = 0; i < n_fields; ++i) if (fields[i] < 0 || fields[i] >= kNState) return fail("nps_read_fields: field index out of range");
     if (h->gather_cap < n_fields) {
         cudaFree(h->d_gather_fields); cudaFree(h->d_gather_out);
+        h->d_gather_fields = nullptr; h->d_gather_out = nullptr; h->gather_cap = 0;
         NPS_CUDA(cudaMalloc(&h->d_gather_fields, sizeof(int32_t) * n_fields));
         NPS_CUDA(cudaMalloc(&h->d_gather_out, sizeof(double) * n_fields * h->n));
         h->gather_cap = n_fields;
     }
-    NPS_CUDA(cudaMemcpy(h->d_gather_fields, fields, sizeof(int32_t) * n_fields, cudaMemcpyHostToDevice));
+    // everything on the caller's stream: ordered after the launches already queued there, no legacy-default-stream work
+    NPS_CUDA(cudaMemcpyAsync(h->d_gather_fields, fields, sizeof(int32_t) * n_fields, cudaMemcpyHostToDevice, s));
     const int block = 128;
-    nps_gather_kernel<<<(int)((h->n + block - 1) / block), block>>>(d_state, h->d_gather_fields, n_fields, h->d_gather_out, h->n);
+    nps_gather_kernel<<<(int)((h->n + block - 1) / block), block, 0, s>>>(d_state, h->d_gather_fields, n_fields, h->d_gather_out, h->n);
     NPS_CUDA(cudaGetLastError());
-    NPS_CUDA(cudaMemcpy(out_host, h->d_gather_out, sizeof(double) * n_fields * h->n, cudaMemcpyDeviceToHost));
+    NPS_CUDA(cudaMemcpyAsync(out_host, h->d_gather_out, sizeof(double) * n_fields * h->n, cudaMemcpyDeviceToHost, s));
+    NPS_CUDA(cudaStreamSynchronize(s));
     return 0;
 }
 

@@ -28,7 +28,12 @@ struct StepInput {
     // controller's 100-sample deviation RMS, the stage inlet entropy) are pure functions of the state at the moment
     // they are observed, and nobody observes the state between fused substeps, so they are evaluated once, at the end.
     bool emit_outputs = true;
+    // NPS_STATUS_* bits raised by this step (the reference resets / latches silently; the batched engine surfaces them
+    // per plant: SURVEY 8b).  Written by the physics, read by the caller after plant_step.
+    mutable unsigned status = 0;
 };
+constexpr unsigned kStatusNanReset = 1u;   // thermal_hydraulics.py:257-269 reset five primary fields this step
+constexpr unsigned kStatusScram = 2u;          // scram latched this step (scram_logic.py:34-61)
 
 // _apply_control_actions: systems/primary/__init__.py:289-359 with the action routing of
 // NuclearPlantSimulator._convert_action_to_control_inputs (simulator/core/sim.py:260-288).
@@ -167,7 +172,7 @@ NPS_HD double primary_overall_ua(double coolant_flow_rate) {
 
 // calculate_thermal_hydraulics / calculate_steam_cycle / update_thermal_state /
 // update_steam_state / check_for_nan_values: physics/thermal_hydraulics.py:26-270
-NPS_HD void primary_thermal_hydraulics(PrimaryState& s, double thermal_power_w, double dt) {
+NPS_HD bool primary_thermal_hydraulics(PrimaryState& s, double thermal_power_w, double dt) {
     const double FUEL_MASS = 200000.0, FUEL_CP = 1500.0;
     double heat_removal = primary_overall_ua(s.coolant_flow_rate) * (s.fuel_temperature - s.coolant_temperature);
     double fuel_temp_dot = (thermal_power_w - heat_removal) / (FUEL_MASS * FUEL_CP);
@@ -206,7 +211,9 @@ NPS_HD void primary_thermal_hydraulics(PrimaryState& s, double thermal_power_w, 
         s.coolant_temperature = 280.0;
         s.coolant_pressure = 15.5;
         s.power_level = 100.0;
+        return true;
     }
+    return false;
 }
 
 // ScramSystem.check_safety_systems: reactor/safety/scram_logic.py:24-61
@@ -241,8 +248,10 @@ NPS_HD void primary_update(PrimaryState& s, const PlantParams& p, const StepInpu
         s.total_reactivity_pcm = rho_pcm;
         s.reactivity = rho_pcm / 100000.0;
     }
-    primary_thermal_hydraulics(s, s.thermal_power_mw * 1e6, dt);
-    s.scram_activated = as_flag(primary_check_scram(s));
+    if (primary_thermal_hydraulics(s, s.thermal_power_mw * 1e6, dt)) in.status |= kStatusNanReset;
+    const bool scram_now = primary_check_scram(s);
+    if (scram_now) in.status |= kStatusScram;
+    s.scram_activated = as_flag(scram_now);
 }
 
 }  // namespace nps

@@ -426,6 +426,13 @@ class BatchedAutoMaintenance:
         self._single = [single_violation_rules(r.component_id, r.parameter, r.action) for r in table.rows]
         sim.set_thresholds(table.device_rows())
 
+    def reset(self, plants) -> None:
+        """Forget the work-order books of plants that start a new episode (their clocks restart with the reset): pending
+        orders, dedupe stamps and counters.  The simulator's own reset() clears their threshold cooldown stamps."""
+        for p in (int(q) for q in plants):
+            self.books.pop(p, None)
+            self._pending.pop(p, None)
+
     # -- AutoMaintenanceSystem.update: auto_maintenance.py:200-236 ------------------------------------------------
     def update(self, t_minutes: float) -> List[WorkOrder]:
         """Call after the physics step and BEFORE check(): executes the work orders that are due (sim.py:209-213)."""
@@ -467,13 +474,66 @@ class BatchedAutoMaintenance:
         fired = self.sim.drain_events()
         if not fired:
             return []
+        try:
+            values = self.sim.read_threshold_values(sorted({p for p, _ in fired}), self.table, events=fired)
+        except TypeError:      # engines without the sparse form (tests' CPU stand-in)
+            values = self.sim.read_threshold_values(sorted({p for p, _ in fired}), self.table)
+        return self._process(t_minutes, fired, values)
+
+    def handle_step_events(self, events) -> List[WorkOrder]:
+        """Violations recorded INSIDE fused launches (sim.drain_step_events(): plant, row, step, value, time_minutes,
+        sorted by step): the same bookkeeping as check(), step by step, with each step's own time stamp."""
+        created: List[WorkOrder] = []
+        i, n = 0, len(events)
+        while i < n:
+            j = i
+            while j < n and events["step"][j] == events["step"][i]:
+                j += 1
+            fired = [(int(p), int(r)) for p, r in zip(events["plant"][i:j], events["row"][i:j])]
+            values = {f: float(v) for f, v in zip(fired, events["value"][i:j])}
+            created += self._process(float(events["time_minutes"][i]), fired, values)
+            i = j
+        return created
+
+    def gate_open(self, t_minutes: float) -> bool:
+        """Would update(t_minutes) pass its check-interval gate (auto_maintenance.py:213-217)?"""
+        return not (self.last_check_time > 0.0 and t_minutes - self.last_check_time < self.check_interval_hours * 60)
+
+    def advance(self, n_steps: int, actions=None, magnitudes=None, noise=None, power_setpoint=None,
+                t0_minutes: Optional[float] = None, max_k: int = 128) -> None:
+        """n_steps reference steps with monitoring and automatic maintenance, in as few launches as exactness allows.
+
+        Thresholds are evaluated on the device after every substep, so events carry their own step.  Work orders only
+        execute when update() passes its 15-minute gate, and the step at which that happens is known in advance; a
+        launch therefore runs up to and including the next gate step, skips the in-launch check of that last substep,
+        and the host then does what the reference does at that step, in its order (sim.py:209-223): update() - execute
+        due orders on the device - then the threshold check of the gate step (flag kernel)."""
+        sim = self.sim
+        if getattr(sim, "_mon", None) is None:
+            sim.enable_monitor()
+        dt = sim.dt
+        t0 = float(sim.current_time_minutes()) if t0_minutes is None else float(t0_minutes)
+        sl = lambda x, a, b: None if x is None else (x[a:b] if getattr(x, "ndim", 0) and x.shape[0] == n_steps and x.ndim >= 2 else x)  # noqa: E731
+        done = 0
+        while done < n_steps:
+            k = 1
+            while done + k < n_steps and k < max_k and not self.gate_open(t0 + (done + k) * dt):
+                k += 1
+            t_end = t0 + (done + k) * dt
+            on_gate = self.gate_open(t_end)
+            sim.step(actions=sl(actions, done, done + k), magnitudes=sl(magnitudes, done, done + k),
+                     noise=sl(noise, done, done + k), power_setpoint=sl(power_setpoint, done, done + k), K=k,
+                     skip_last_check=on_gate)
+            self.handle_step_events(sim.drain_step_events())
+            if on_gate:
+                self.update(t_end)
+                self.check(t_end)
+            done += k
+
+    def _process(self, t_minutes: float, fired, values) -> List[WorkOrder]:
         by_plant: Dict[int, Dict[str, List[int]]] = {}
         for plant, t in fired:
             by_plant.setdefault(plant, {}).setdefault(self.table.rows[t].component_id, []).append(t)
-        try:
-            values = self.sim.read_threshold_values(sorted(by_plant), self.table, events=fired)
-        except TypeError:      # engines without the sparse form (tests' CPU stand-in)
-            values = self.sim.read_threshold_values(sorted(by_plant), self.table)
         created = []
         for plant in sorted(by_plant):
             # component order = table order (dict order of maintenance_thresholds), parameters in config order

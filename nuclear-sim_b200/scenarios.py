@@ -67,10 +67,23 @@ def load_following_inputs(plant_ids: np.ndarray, t0: int, k: int):
     return act.astype(np.int8), np.broadcast_to(mag[None, :], (k, n)).copy()
 
 
+def _mix64(x: np.ndarray) -> np.ndarray:
+    x = x.copy()
+    x ^= x >> np.uint64(30); x *= np.uint64(0xBF58476D1CE4E5B9)
+    x ^= x >> np.uint64(27); x *= np.uint64(0x94D049BB133111EB)
+    x ^= x >> np.uint64(31)
+    return x
+
+
 def noise_inputs(plant_ids: np.ndarray, t0: int, k: int, seed: int = 1000) -> np.ndarray:
-    """[k, 5, n] host-supplied random streams (z_heat, z_ph, u0, u1, u2)."""
-    n = len(plant_ids)
-    rng = np.random.Generator(np.random.Philox(key=seed, counter=[0, 0, int(t0), int(plant_ids[0])]))
-    z = rng.standard_normal((k, 2, n))
-    u = rng.random((k, 3, n))
-    return np.concatenate([z, u], axis=1)
+    """[k, 5, n] host-supplied random streams (z_heat, z_ph, u0, u1, u2).  Counter-based: the five numbers of
+    (plant id, step) are a pure function of (seed, plant id, step), so a plant sees the same draws whatever the batch,
+    the launch grouping or the GPU it is sharded to."""
+    pid = np.asarray(plant_ids, dtype=np.uint64)[None, None, :]
+    t = np.arange(t0, t0 + k, dtype=np.uint64)[:, None, None]
+    c = np.arange(7, dtype=np.uint64)[None, :, None]
+    with np.errstate(over="ignore"):
+        x = _mix64(_mix64(pid * np.uint64(0x9E3779B97F4A7C15) + np.uint64(seed)) + t * np.uint64(0xD1B54A32D192ED03) + c)
+    u = ((x >> np.uint64(11)).astype(np.float64) + 0.5) / float(1 << 53)      # (0, 1)
+    z = np.sqrt(-2.0 * np.log(u[:, 0:4:2])) * np.cos(2.0 * np.pi * u[:, 1:4:2])   # Box-Muller: (u0,u1) -> z_heat, (u2,u3) -> z_ph
+    return np.concatenate([z, u[:, 4:7]], axis=1)

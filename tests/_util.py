@@ -41,6 +41,38 @@ def load_golden(name):
     return g
 
 
+def load_sized(name):
+    """64-plant BASELINE-size fixtures (oracle/make_golden_sized.py): the per-step inputs are regenerated from the plant
+    ids by the generator's own pure function (no reference needed), everything else comes from the live reference."""
+    from oracle import make_golden_sized as MG
+    g = load_golden(name)
+    T = int(g["n_steps"])
+    ins = [MG.plant_inputs(name, j, int(pid), T) for j, pid in enumerate(g["plant_ids"])]
+    g["actions"] = np.stack([i[0] for i in ins], axis=1)                      # [T, 64]
+    g["magnitudes"] = np.stack([i[1] for i in ins], axis=1)
+    g["noise"] = np.stack([i[2] for i in ins], axis=1)                        # [T, 64, 5]
+    g["setpoint"] = np.full((T, len(ins)), np.nan)
+    return g
+
+
+def oracle_run_sized(L, g, st, t0, t1):
+    """oracle_run for the sized fixtures: up to 4 injected (field, value) pairs per plant-step."""
+    st = np.ascontiguousarray(st, dtype=np.float64).copy()
+    inj = g["inject"]
+    steps = sorted(set(np.nonzero(~np.isnan(inj[t0:t1, :, 0, 0]))[0] + t0)) + [t1]
+    t = t0
+    for nxt in steps:
+        if nxt > t:
+            st = oracle_run(L, st, g["params"], g["actions"], g["magnitudes"], g["noise"], g["setpoint"], None, t, nxt)
+            t = nxt
+        if t < t1:
+            for p in np.nonzero(~np.isnan(inj[t, :, 0, 0]))[0]:
+                for f, v in inj[t, p]:
+                    if not np.isnan(f):
+                        st[p, int(f)] = v
+    return st
+
+
 def discrete_mask():
     """Fields that hold flags / enums / counters / latches: compared bit-exactly."""
     from nuclear_sim_b200 import field_names
@@ -148,8 +180,39 @@ class OracleSim:
         self.n_plants = self.st.shape[0]
         self.ix = field_index()
         self._thr = None
+        self._mon = None
+        self.step_index = 0
+        self.dt = float(self.params[field_index("PlantParams")["dt"]])
 
-    def step(self, actions=None, magnitudes=None, noise=None, power_setpoint=None):
+    # in-launch monitoring surface of BatchedNuclearPlantSimulator (enable_monitor / step(K=...) / drain_step_events)
+    def enable_monitor(self, *a, **k):
+        self._mon = True
+        self._step_events = []
+
+    def current_time_minutes(self):
+        return float(self.st[0, self.ix["sim.time_minutes"]])
+
+    def drain_step_events(self):
+        from nuclear_sim_b200.batched import EVENT_DTYPE
+        ev = np.array(sorted(self._step_events, key=lambda e: (e[2], e[0], e[1])), dtype=EVENT_DTYPE) if self._step_events \
+            else np.zeros(0, dtype=EVENT_DTYPE)
+        self._step_events = []
+        return ev
+
+    def step(self, actions=None, magnitudes=None, noise=None, power_setpoint=None, K=None, skip_last_check=False):
+        if K is not None:     # device-style call: [K, N] inputs, noise [K, 5, N]; thresholds checked after every substep
+            pick = lambda x, k: None if x is None else np.asarray(x)[k]   # noqa: E731
+            for k in range(K):
+                z = None if noise is None else np.ascontiguousarray(np.asarray(noise)[k].T)
+                self.step(pick(actions, k), pick(magnitudes, k), z, pick(power_setpoint, k))
+                if self._mon and getattr(self, "_rows", None) and not (skip_last_check and k == K - 1):
+                    self.check_thresholds()
+                    now = self.current_time_minutes()
+                    for p, t in self._fired:
+                        self._step_events.append((p, t, self.step_index - 1, 0, float(self._value(self._rows[t][0])[p]), now))
+                    self._fired = []
+            return
+        self.step_index += 1
         P = self.n_plants
         a = np.full(P, 8, dtype=np.int8) if actions is None else np.ascontiguousarray(actions, dtype=np.int8)
         m = np.ones(P) if magnitudes is None else np.ascontiguousarray(magnitudes, dtype=np.float64)

@@ -372,6 +372,52 @@ def test_vector_env_and_checkpoint_resume(tmp_path):
     assert len(torch.unique(live.state.power_level)) > 1        # the plants really drew different noise
 
 
+def test_env_cooling_water_reset_cooldowns_and_maintenance_checkpoint(tmp_path):
+    """Advisor findings of round 1: env.step(cooling_water_temp=...) (scalar and per plant) reaches the plants; a reset
+    plant forgets its threshold cooldown stamps; a checkpoint taken in the middle of a maintenance run resumes with the
+    same pending work orders and produces the same orders and state as the uninterrupted run."""
+    import json
+    import torch
+    from nuclear_sim_b200 import load_snapshot, maintenance as M
+    from nuclear_sim_b200.env import BatchedNuclearPlantEnv, load_checkpoint, save_checkpoint
+    s0, params = load_snapshot("pwr3000_reactor_dt1")
+    n = 40
+    env = BatchedNuclearPlantEnv(_sim(np.tile(s0, (n, 1)), params), auto_reset=False, seed=1)
+    env.step(torch.full((n,), 8), None, 31.5)                      # the reference's positional order: load_demand, cooling water
+    assert (env.sim.state["sim.cooling_water_temp"] == 31.5).all()
+    cw = torch.linspace(18.0, 30.0, n, dtype=torch.float64)
+    obs, *_ = env.step(torch.full((n,), 8), cooling_water_temp=cw, magnitude=torch.ones(n, dtype=torch.float64))
+    assert torch.equal(env.sim.state["sim.cooling_water_temp"].cpu(), cw)
+    assert torch.allclose(obs[:, 17].cpu(), cw / 35.0)             # observation 17 = cooling water temperature / 35
+    # cooldown stamps of a reset plant
+    g = np.load(os.path.join(U.GOLDEN, "maint_oil_top_off.npz"), allow_pickle=False)
+    log = json.loads(str(g["log"]))
+    table = M.ThresholdTable(log["maintenance_system"])
+    T = g["states"].shape[0]
+    mk = lambda s: M.BatchedAutoMaintenance(s, table, aggressive=True)   # noqa: E731
+    full = _sim(np.tile(g["state0"], (3, 1)), g["params"]); m_full = mk(full)
+    part = _sim(np.tile(g["state0"], (3, 1)), g["params"]); m_part = mk(part)
+    cut = int(log["created"][0]["step"]) + 1                       # a work order is pending at the cut
+    m_full.advance(T)
+    m_part.advance(cut)
+    assert m_part._pending
+    path = str(tmp_path / "maint.pt")
+    save_checkpoint(part, path, maintenance=m_part)
+    resumed, m_res = load_checkpoint(path, maintenance=mk)
+    m_res.advance(T - cut)
+    key = lambda w: (w.plant, w.work_order_id, w.component_id, w.action, w.created, w.executed_at, w.success)   # noqa: E731
+    assert [key(w) for w in m_res.created_log] == [key(w) for w in m_full.created_log]
+    assert [key(w) for w in m_res.executed_log] == [key(w) for w in m_full.executed_log] and m_res.executed_log
+    assert torch.equal(resumed.slab, full.slab)
+    with pytest.raises(ValueError):
+        load_checkpoint(path)                                      # stamps without their table would be dropped silently
+    fired = (full._thr["last"] > -float("inf")).any(dim=0)
+    assert bool(fired.all())
+    full.reset(torch.tensor([True, False, False]))
+    fired = (full._thr["last"] > -float("inf")).any(dim=0).cpu().numpy().tolist()
+    assert fired == [False, True, True]
+
+
 def test_cuda_batched_timing_sweep():
     """The batched TimingOptimizer replacement on the CUDA engine: 512 candidate oil levels in one batch; the committed
     initial level reproduces the reference's trigger time and the curve is monotone."""
@@ -499,3 +545,172 @@ def test_batched_export_trajectory_in_reference_schema(tmp_path):
     assert sim.export_trajectory(7, str(tmp_path / "ring.csv")) == 6
     store.export_by_subcategory("secondary", "steam_generator_SG-1", str(tmp_path / "store.csv"))
     assert open(tmp_path / "ring.csv").read() == open(tmp_path / "store.csv").read()
+
+
+# ---- in-launch monitoring: the step of every discrete event does not depend on how steps are fused into launches ---
+def _monitored_run(g, kmax, table_cfg=None):
+    """Replay a trajectory fixture with launches of up to kmax substeps and the in-launch monitor; returns the simulator,
+    the drained threshold events and the per-step done flags."""
+    import torch
+    from nuclear_sim_b200 import maintenance as M
+    sim = _sim(g["state0"], g["params"])
+    if table_cfg is not None:
+        sim.set_thresholds(M.ThresholdTable(table_cfg).device_rows())
+    sim.enable_monitor(per_substep=True, max_k=kmax)
+    T = g["actions"].shape[0]
+    inj = g["inject"]
+    done = np.zeros((T, sim.n_plants), dtype=bool)
+    rewards = np.zeros((T, sim.n_plants))
+    events = []
+    t = 0
+    while t < T:
+        for p in range(sim.n_plants):
+            if not np.isnan(inj[t, p, 0]):
+                sim.slab[int(inj[t, p, 0]), p] = float(inj[t, p, 1])
+        k = 1
+        while t + k < T and k < kmax and np.isnan(inj[t + k, :, 0]).all():
+            k += 1
+        out = sim.step(actions=torch.from_numpy(np.ascontiguousarray(g["actions"][t:t + k])),
+                       magnitudes=torch.from_numpy(np.ascontiguousarray(g["magnitudes"][t:t + k])),
+                       noise=torch.from_numpy(np.ascontiguousarray(g["noise"][t:t + k].transpose(0, 2, 1))),
+                       power_setpoint=torch.from_numpy(np.ascontiguousarray(g["setpoint"][t:t + k])), K=k)
+        done[t:t + k] = out["done_k"].cpu().numpy()
+        rewards[t:t + k] = out["reward_k"].cpu().numpy()
+        events.append(sim.drain_step_events())
+        t += k
+    return sim, np.concatenate(events), done, rewards
+
+
+@pytest.mark.parametrize("name", ["cfg4_scram", "cfg6_secondary_trips", "cfg7_turbine_trips_fouling"])
+def test_fused_launches_report_the_same_event_steps_as_single_steps(name):
+    """K = 64 against K = 1: first scram step, first step of every watched trip latch, threshold violations
+    (plant, row, step, value, time), per-step done and reward, status words and the final state — all identical;
+    scram steps also equal the live-reference fixture."""
+    import json
+    import torch
+    g = U.load_golden(name)
+    cfg = json.loads(str(np.load(os.path.join(U.GOLDEN, "maint_oil_top_off.npz"), allow_pickle=False)["log"]))["maintenance_system"]
+    a, ev_a, done_a, rew_a = _monitored_run(g, 1, cfg)
+    b, ev_b, done_b, rew_b = _monitored_run(g, 64, cfg)
+    assert a.n_launches > b.n_launches * 8
+    assert torch.equal(a.slab, b.slab)
+    assert torch.equal(a.first_scram_step, b.first_scram_step) and torch.equal(a.status, b.status)
+    assert torch.equal(a.first_nan_reset_step, b.first_nan_reset_step)
+    for (wa, sa), (wb, sb) in zip(a.watch_steps().items(), b.watch_steps().items()):
+        assert wa == wb and torch.equal(sa, sb), wa
+    assert ev_a.tolist() == ev_b.tolist()
+    assert np.array_equal(done_a, done_b) and np.array_equal(rew_a, rew_b)
+    first_done = np.where(done_a.any(0), done_a.argmax(0), -1)
+    assert first_done.tolist() == g["done_step"].tolist()
+    assert a.first_scram_step.cpu().numpy().tolist() == g["done_step"].tolist()
+    if name != "cfg4_scram":
+        assert len(ev_a) > 0                                        # degraded plants do cross maintenance thresholds
+        trips = torch.stack(list(a.watch_steps().values()))
+        assert int((trips >= 0).sum()) >= 2                         # and do latch trips, at known steps
+
+
+def test_status_word_reports_the_nan_reset():
+    """thermal_hydraulics.py:257-269 resets five primary fields when one of them is NaN — silently in the reference; the
+    batched engine reproduces the reset and raises bit 0 of the plant's status word, with the step it happened at."""
+    import torch
+    from nuclear_sim_b200 import field_index, load_snapshot
+    s0, params = load_snapshot("pwr3000_reactor_dt1")
+    n = 70
+    sim = _sim(np.tile(s0, (n, 1)), params)
+    sim.enable_monitor()
+    sim.step(K=3)
+    sim.state["pri.fuel_temperature"][5] = float("nan")
+    sim.state["pri.coolant_pressure"][64] = float("nan")
+    sim.step(K=4)
+    st = sim.status.cpu().numpy()
+    fr = sim.first_nan_reset_step.cpu().numpy()
+    assert [int(p) for p in np.nonzero(st & 1)[0]] == [5, 64]
+    assert fr[5] == 3 and fr[64] == 3 and (np.delete(fr, [5, 64]) == -1).all()
+    assert float(sim.state.power_level[5]) > 0 and not torch.isnan(sim.slab[:, 5]).any()
+    sim.reset()
+    assert int(sim.status.sum()) == 0 and int((sim.first_nan_reset_step >= 0).sum()) == 0
+
+
+@pytest.mark.parametrize("name", MAINT_SCENARIOS)
+def test_cuda_maintenance_advance_with_fused_launches(name):
+    """BatchedAutoMaintenance.advance on the device: in-launch threshold evaluation, launches cut at the 15-minute gate
+    steps — threshold events, work orders created / executed and the final state equal the live-reference fixture."""
+    import json
+    import torch
+    from nuclear_sim_b200 import maintenance as M
+    from tests.test_maintenance_host import compare_logs
+    g = np.load(os.path.join(U.GOLDEN, f"maint_{name}.npz"), allow_pickle=False)
+    log = json.loads(str(g["log"]))
+    T = g["states"].shape[0]
+    sim = _sim(g["state0"][None, :], g["params"])
+    maint = M.BatchedAutoMaintenance(sim, M.ThresholdTable(log["maintenance_system"]), aggressive=True)
+    noise = torch.from_numpy(np.ascontiguousarray((g["noise"][:, None, :] if g["noise"].ndim == 2 else g["noise"]).transpose(0, 2, 1)))
+    maint.advance(T, noise=noise, max_k=64)
+    assert sim.n_launches < 3 * T      # step + flag kernel per gate instead of per step (+ a few maintenance launches)
+    compare_logs(maint, log)
+    U.assert_states_close(sim.state_numpy(), g["states"][T - 1][None, :], U.TOL_STEP * T, f"{name} final state")
+
+
+# ---- BASELINE sizes against the live reference: 64 reference plants embedded in the full batch -----------------------
+def _run_sized_embedded(name, kmax):
+    import torch
+    from nuclear_sim_b200 import load_snapshot
+    from nuclear_sim_b200 import scenarios as sc
+    g = U.load_sized(name)
+    n = int(g["total"])
+    ids = g["plant_ids"].astype(np.int64)
+    s0, params = load_snapshot("pwr3000_reactor_dt1")
+    assert np.array_equal(params, g["params"])
+    pid = np.arange(n)
+    st = sc.randomized_states(s0, pid)          # the bench workload's plants ...
+    st[ids] = g["state0"]                       # ... with the reference-built plants at their scattered global ids
+    sim = _sim(st, g["params"])
+    sim.enable_monitor(per_substep=True, max_k=kmax)
+    T = int(g["n_steps"])
+    inj = g["inject"]
+    inj_steps = sorted(set(np.nonzero(~np.isnan(inj[:, :, 0, 0]))[0].tolist()))
+    cps = [int(c) for c in g["checkpoints"]]
+    stops = sorted(set(inj_steps + cps + [T]))
+    dev_ids = torch.as_tensor(ids, device="cuda:0")
+    done = np.zeros((T, len(ids)), dtype=bool)
+    t = 0
+    while t < T:
+        for j in np.nonzero(~np.isnan(inj[t, :, 0, 0]))[0]:
+            for f, v in inj[t, j]:
+                if not np.isnan(f):
+                    sim.slab[int(f), int(ids[j])] = float(v)
+        nxt = min(s for s in stops if s > t)
+        k = min(kmax, nxt - t)
+        acts, mags = sc.load_following_inputs(pid, t, k)
+        acts[:, ids] = g["actions"][t:t + k]
+        mags[:, ids] = g["magnitudes"][t:t + k]
+        noise = torch.zeros((k, 5, n), dtype=torch.float64, device="cuda:0")
+        noise[:, 2:, :] = 1.0
+        noise[:, :, dev_ids] = torch.from_numpy(np.ascontiguousarray(g["noise"][t:t + k].transpose(0, 2, 1))).to("cuda:0")
+        out = sim.step(actions=torch.from_numpy(acts), magnitudes=torch.from_numpy(mags), noise=noise, K=k)
+        done[t:t + k] = out["done_k"][:, dev_ids].cpu().numpy()
+        t += k
+        if t in cps:
+            got = sim.slab[:, dev_ids].t().contiguous().cpu().numpy()
+            tol = U.TOL_STEP * max(1, min(t, 1000)) if t < 3600 else U.TOL_LONG
+            U.assert_states_close(got, g["states"][cps.index(t)], tol, f"{name} step {t}")
+    return sim, g, done, dev_ids
+
+
+def test_cfg3_reference_plants_embedded_in_65536():
+    """BASELINE config #3 at full size: 65 536 plants, 3 600 steps, 64-substep launches; the 64 plants built by the
+    reference's randomised-IC generators and stepped by the reference must come out of the full batch as the fixture
+    recorded them (1e-9 per step, 1e-6 after 3 600 steps), whatever their neighbours do."""
+    sim, g, done, dev_ids = _run_sized_embedded("cfg3_rand64", 64)
+    assert not done.any() and (sim.first_scram_step[dev_ids] < 0).all()
+    assert float(sim.state.power_level.mean()) >= 0.0
+
+
+def test_cfg4_reference_transients_embedded_in_16384():
+    """BASELINE config #4 at full size: 16 384 plants, 900 steps; 64 plants get the reference's EquipmentFailureSimulator
+    / emergency transients at their own trigger steps.  done every step, first scram step, and the states at the
+    checkpoints equal the live reference's."""
+    sim, g, done, dev_ids = _run_sized_embedded("cfg4_fail64", 64)
+    assert np.array_equal(done, g["done"].astype(bool))
+    assert sim.first_scram_step[dev_ids].cpu().numpy().tolist() == g["first_scram_step"].tolist()
+    assert (g["first_scram_step"] >= 0).sum() >= 15

@@ -134,6 +134,26 @@ def test_scenario_host_logic_on_oracle(name):
     assert len(log["created"]) >= 1 and len(log["executed"]) >= 1
 
 
+@pytest.mark.parametrize("name", SCENARIOS)
+@pytest.mark.parametrize("max_k", [64, 2])
+def test_advance_with_fused_launches_equals_single_steps(name, max_k):
+    """BatchedAutoMaintenance.advance(): thresholds evaluated after every substep inside the launch, launches cut at the
+    15-minute gate steps.  Events, work orders (created / executed times) and the final state must equal the K = 1
+    replay and the live-reference log, whatever the launch length."""
+    M = _maint()
+    g = np.load(os.path.join(U.GOLDEN, f"maint_{name}.npz"), allow_pickle=False)
+    log = json.loads(str(g["log"]))
+    T = g["states"].shape[0]
+    sim = U.OracleSim(g["state0"], g["params"])
+    maint = M.BatchedAutoMaintenance(sim, M.ThresholdTable(log["maintenance_system"]), aggressive=True)
+    noise = np.ascontiguousarray((g["noise"][:, None, :] if g["noise"].ndim == 2 else g["noise"]).transpose(0, 2, 1))  # [T, 5, P]
+    half = T // 2
+    maint.advance(half, noise=noise[:half], max_k=max_k)
+    maint.advance(T - half, noise=noise[half:], max_k=max_k)
+    compare_logs(maint, log)
+    U.assert_states_close(sim.state_numpy(), g["states"][T - 1][None, :], U.TOL_STEP * T, f"{name} final state")
+
+
 def test_single_violation_fast_path_equals_orchestrate():
     """BatchedAutoMaintenance precomputes the decision for one-violation events; it must agree with orchestrate()
     for every threshold row of the reference configuration, below and above every rule threshold."""

@@ -54,3 +54,60 @@ def test_scram_steps_bit_exact(oracle_lib):
         np.testing.assert_allclose(st[:, ix["pri.power_level"]], g["power_level"][t], rtol=1e-9, atol=1e-12)
     assert first.tolist() == g["done_step"].tolist()
     assert (first >= 0).sum() >= 2   # the fixture really contains scrams
+
+
+# ---- 64-plant fixtures built by the reference's own generators (BASELINE configs #3 and #4) ----------------------
+def test_oracle_matches_reference_randomized_ics_cfg3(oracle_lib):
+    """64 plants with the reference's get_randomized_*_conditions ICs over the action catalog, load-following / ramp /
+    valve / boron policies, 3 600 steps: state at every checkpoint, power and electrical output every 10th step."""
+    from nuclear_sim_b200 import field_index
+    g = U.load_sized("cfg3_rand64")
+    ix = field_index()
+    tr = [ix[str(f)] for f in g["trace_fields"]]
+    stride = int(g["trace_stride"])
+    st = g["state0"].copy()
+    t = 0
+    cps = {int(c): i for i, c in enumerate(g["checkpoints"])}
+    for row in range(g["trace"].shape[0]):
+        t1 = (row + 1) * stride
+        for c in sorted(k for k in cps if t < k < t1):
+            st = U.oracle_run_sized(oracle_lib, g, st, t, c)
+            t = c
+            U.assert_states_close(st, g["states"][cps[c]], U.TOL_STEP * max(1, min(c, 1000)), f"cfg3_rand64 step {c}")
+        st = U.oracle_run_sized(oracle_lib, g, st, t, t1)
+        t = t1
+        got = st[:, tr]
+        assert np.array_equal(got[:, 0], g["trace"][row][:, 0])                 # scram_status
+        assert U.rel_err(got, g["trace"][row]).max() <= (U.TOL_STEP * min(t, 1000) if t < 3600 else U.TOL_LONG), f"step {t}"
+        if t in cps:
+            tol = U.TOL_STEP * max(1, min(t, 1000)) if t < 3600 else U.TOL_LONG
+            U.assert_states_close(st, g["states"][cps[t]], tol, f"cfg3_rand64 step {t}")
+    assert t == 3600 and g["ic_randomized"].all()
+
+
+def test_oracle_matches_reference_failure_injections_cfg4(oracle_lib):
+    """64 plants, each with one EquipmentFailureSimulator / emergency transient at its own trigger step: scram_status,
+    done, power, fuel temperature, flow, pressure EVERY step (event steps bit-exact), full state at the checkpoints."""
+    from nuclear_sim_b200 import field_index
+    g = U.load_sized("cfg4_fail64")
+    ix = field_index()
+    tr = [ix[str(f)] for f in g["trace_fields"]]
+    st = g["state0"].copy()
+    P = st.shape[0]
+    first_scram = np.full(P, -1)
+    first_done = np.full(P, -1)
+    cps = {int(c): i for i, c in enumerate(g["checkpoints"])}
+    for t in range(int(g["n_steps"])):
+        st = U.oracle_run_sized(oracle_lib, g, st, t, t + 1)
+        got = st[:, tr]
+        assert np.array_equal(got[:, 0], g["trace"][t][:, 0]), f"scram_status at step {t}"
+        done = st[:, ix["pri.scram_activated"]] != 0
+        assert np.array_equal(done, g["done"][t].astype(bool)), f"done at step {t}"
+        first_scram[(first_scram < 0) & (got[:, 0] != 0)] = t
+        first_done[(first_done < 0) & done] = t
+        assert U.rel_err(got, g["trace"][t]).max() <= U.TOL_STEP * (t + 1), f"step {t}"
+        if t + 1 in cps:
+            U.assert_states_close(st, g["states"][cps[t + 1]], U.TOL_STEP * (t + 1), f"cfg4_fail64 step {t + 1}")
+    assert first_scram.tolist() == g["first_scram_step"].tolist()
+    assert first_done.tolist() == g["first_done_step"].tolist()
+    assert (first_scram >= 0).sum() >= 15
