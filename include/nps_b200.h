@@ -157,6 +157,11 @@ int nps_set_thresholds(nps_handle* h, const int32_t* field, const int32_t* compa
 int nps_check_thresholds(nps_handle* h, const double* d_state, double* d_last_fired, uint32_t* d_flags,
                          uint32_t* d_any_warp, void* cuda_stream);
 
+/* The same check with the violations appended to an event list (struct nps_event, see nps_step_monitored; event.step =
+ * `step`): the form the work-order bookkeeping consumes, identical for checks inside a fused launch and between launches. */
+int nps_check_thresholds_events(nps_handle* h, const double* d_state, double* d_last_fired, nps_event* d_events,
+                                uint32_t* d_n_events, uint32_t event_capacity, int32_t step, void* cuda_stream);
+
 /* --- trajectory ring buffer (StateManager.collect_states/_add_row, state_manager.py:152-233) ---
  * Appends the selected fields of every plant as row (write_index % ring_rows) of
  * d_ring [ring_rows][n_logged][n_plants].  Each logged field is one contiguous row of the slab; the rows travel as

@@ -86,10 +86,15 @@ class _Monitor(ctypes.Structure):
 EVENT_DTYPE = np.dtype([("plant", np.int32), ("row", np.int32), ("step", np.int32), ("reserved", np.int32),
                         ("value", np.float64), ("time_minutes", np.float64)])   # struct nps_event
 
-# flag fields whose first non-zero step is stamped by default (SURVEY 8 a-events e3-e12: the latched trips)
+# flag fields whose first non-zero step is stamped by default (SURVEY 8 a-events e3-e12: latched trips, SG shutdown /
+# replacement flags)
 DEFAULT_WATCH = ("fw.pump[0].trip_active", "fw.pump[1].trip_active", "fw.pump[2].trip_active", "fw.pump[3].trip_active",
                  "fw.prot_system_trip_active", "fw.prot_npsh_low_low_trip_active", "fw.prot_npsh_critical_trip_active",
-                 "turb.prot_trip_active", "cond.vs_trip_high_pressure")
+                 "turb.prot_trip_active", "cond.vs_trip_high_pressure",
+                 "sgs.sg[0].tsp_shutdown_required", "sgs.sg[1].tsp_shutdown_required", "sgs.sg[2].tsp_shutdown_required",
+                 "sgs.sg[0].tsp_replacement_recommended", "sgs.sg[1].tsp_replacement_recommended",
+                 "sgs.sg[2].tsp_replacement_recommended", "sgs.sg[0].tif_replacement_recommended",
+                 "sgs.sg[1].tif_replacement_recommended", "sgs.sg[2].tif_replacement_recommended")
 
 
 class BatchedNuclearPlantSimulator:
@@ -409,6 +414,12 @@ class BatchedNuclearPlantSimulator:
             "any": torch.zeros(((self.n_plants + 31) // 32,), dtype=torch.int32, device=self.device),
         }
 
+    def clear_thresholds(self) -> None:
+        empty = np.zeros(0, dtype=np.int32)
+        _clib.check(self.L.nps_set_thresholds(self._h, empty.ctypes.data_as(ctypes.c_void_p), empty.ctypes.data_as(ctypes.c_void_p),
+                                              empty.ctypes.data_as(ctypes.c_void_p), empty.ctypes.data_as(ctypes.c_void_p), 0))
+        self._thr = None
+
     def check_thresholds(self):
         """Returns (flags [n_words, N] int32 bitmask tensor, any_warp [ceil(N/32)] int32 ballot words)."""
         t = self._thr
@@ -419,6 +430,17 @@ class BatchedNuclearPlantSimulator:
                                                 ctypes.c_void_p(stream)))
         self.n_launches += 1
         return t["flags"], t["any"]
+
+    def check_thresholds_events(self) -> None:
+        """The threshold check of the CURRENT state with the violations appended to the monitor's event list (stamped
+        with the last completed step), instead of the flag matrix: drain_step_events() returns them."""
+        t, g = self._thr, self._mon
+        if t is None or g is None:
+            raise _clib.NpsError("set_thresholds() and enable_monitor() first")
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _clib.check(self.L.nps_check_thresholds_events(self._h, _ptr(self.slab), _ptr(t["last"]), _ptr(g["events"]),
+                                                       _ptr(g["n_events"]), g["cap"], self.step_index - 1, ctypes.c_void_p(stream)))
+        self.n_launches += 1
 
     def drain_events(self):
         """Host drain: sorted list of (plant, threshold_index) that fired in the last check_thresholds().  The warp

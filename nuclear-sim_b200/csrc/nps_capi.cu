@@ -50,6 +50,17 @@ static_assert(kNParams == NPS_GEN_N_PARAMS, "state.h and fields_gen.inc disagree
 // device-side noise (csrc/plant/rng.h): used when the caller passes no noise array and nps_set_device_rng enabled it
 struct RngConfig { uint64_t seed; uint64_t plant_offset; uint64_t step0; int enabled; int pad; };
 struct Threshold { int field; int cmp; double value; double cooldown; int row; int pad; };
+__device__ __forceinline__ bool threshold_compare(int cmp, double v, double x) {   // _check_threshold_condition: state_manager.py:1412-1442
+    switch (cmp) {
+        case 0: return v > x;
+        case 1: return v < x;
+        case 2: return v >= x;
+        case 3: return v <= x;
+        case 4: return fabs(v - x) < 1e-3;
+        case 5: return fabs(v - x) >= 1e-3;
+        default: return false;
+    }
+}
 
 struct nps_handle {
     int64_t n = 0;
@@ -85,9 +96,12 @@ struct nps_handle {
 // ------------------------------------------------------------------------------------------------
 // step kernel: thread-per-plant, state register/local resident across k substeps
 // ------------------------------------------------------------------------------------------------
-// Launch shapes (both 128 registers, 448 resident threads per SM, so 65,536 plants are ONE wave on 148 SMs):
-//   large batches  448 threads x 1 block/SM  - measured 2 % faster than 64 x 7 at 65,536 plants (profiles/r01_tuning_variants.txt (7))
-//   small batches   64 threads x 7 blocks/SM - spreads a few thousand plants over all SMs instead of a handful
+// Launch shapes:
+//   large batches  448 threads x 1 block/SM, 128 registers: 65,536 plants are ONE wave on 148 SMs
+//                  (measured 2 % faster than 64 x 7 at 65,536 plants, profiles/r01_tuning_variants.txt (7))
+//   small batches  one warp per block, no register cap (ptxas takes what it needs up to 255): below ~33 K plants an SM
+//                  holds at most 7 warps, so registers are free and the time is one warp's own dependency chain - a
+//                  wider register file per thread means fewer spills on that chain (profiles/r01_tuning_variants.txt (21))
 // NPS_STEP_BLOCK / NPS_STEP_MINBLOCKS pin one shape for tuning builds.
 #ifndef NPS_COPY_UNROLL
 #define NPS_COPY_UNROLL 8   /* loads in flight per thread while the slab is copied in / out; 2, 4, 24 and 48 all
@@ -131,17 +145,6 @@ __device__ __forceinline__ double derived_from_state(const PlantState& st, int c
     return NAN;
 }
 
-__device__ __forceinline__ bool threshold_compare(int cmp, double v, double x) {   // _check_threshold_condition: state_manager.py:1412-1442
-    switch (cmp) {
-        case 0: return v > x;
-        case 1: return v < x;
-        case 2: return v >= x;
-        case 3: return v <= x;
-        case 4: return fabs(v - x) < 1e-3;
-        case 5: return fabs(v - x) >= 1e-3;
-        default: return false;
-    }
-}
 
 __device__ __noinline__ void monitor_substep(const PlantState& st, const MonitorArgs& mon, const Threshold* rows,
                                              int64_t n, int64_t p, int k, bool last, unsigned warp_mask, unsigned step_status,
@@ -162,24 +165,45 @@ __device__ __noinline__ void monitor_substep(const PlantState& st, const Monitor
     if (mon.last_fired && !(last && mon.skip_last_check)) {
         const double now = st.sim.time_minutes;
         const unsigned lane = threadIdx.x & 31u;
-        for (int j = 0; j < mon.n_live; ++j) {
-            const Threshold th = rows[j];
-            const double v = (th.field >= 0) ? sv[th.field] : derived_from_state(st, th.field);
-            bool fire = threshold_compare(th.cmp, v, th.value);
-            if (fire) {   // _is_threshold_in_cooldown (state_manager.py:1267-1305) only matters for rows that would fire
-                double* stamp = mon.last_fired + (int64_t)th.row * n + p;
-                if ((now - *stamp) < th.cooldown) fire = false;
-                else *stamp = now;      // _record_threshold_violation_time
+        // rows in groups of kMonChunk: the group's values are independent loads issued back to back (they are first
+        // touches of this substep's freshly written state, i.e. cache misses), then compared; the warp votes ONCE per
+        // group, and only a group in which some lane fired goes through the per-row ballots that build the event list
+        constexpr int kMonChunk = 8;
+        for (int j0 = 0; j0 < mon.n_live; j0 += kMonChunk) {
+            double v[kMonChunk];
+            unsigned hit = 0;
+#pragma unroll
+            for (int j = 0; j < kMonChunk; ++j) {
+                if (j0 + j < mon.n_live) {
+                    const int f = rows[j0 + j].field;
+                    v[j] = (f >= 0) ? sv[f] : derived_from_state(st, f);
+                }
             }
-            const unsigned m = __ballot_sync(warp_mask, fire);
-            if (m) {
-                const int leader = __ffs(m) - 1;
-                uint32_t base = 0;
-                if ((int)lane == leader) base = atomicAdd(mon.n_events, (uint32_t)__popc(m));
-                base = __shfl_sync(warp_mask, base, leader);
-                if (fire) {
-                    const uint32_t slot = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
-                    if (slot < mon.event_cap) mon.events[slot] = nps_event{(int32_t)p, th.row, step, 0, v, now};
+#pragma unroll
+            for (int j = 0; j < kMonChunk; ++j) {
+                if (j0 + j < mon.n_live && threshold_compare(rows[j0 + j].cmp, v[j], rows[j0 + j].value)) hit |= 1u << j;
+            }
+            if (!__ballot_sync(warp_mask, hit != 0)) continue;
+#pragma unroll
+            for (int j = 0; j < kMonChunk; ++j) {
+                if (j0 + j >= mon.n_live) break;
+                const Threshold th = rows[j0 + j];
+                bool fire = (hit >> j) & 1u;
+                if (fire) {   // _is_threshold_in_cooldown (state_manager.py:1267-1305) only matters for rows that would fire
+                    double* stamp = mon.last_fired + (int64_t)th.row * n + p;
+                    if ((now - *stamp) < th.cooldown) fire = false;
+                    else *stamp = now;      // _record_threshold_violation_time
+                }
+                const unsigned m = __ballot_sync(warp_mask, fire);
+                if (m) {
+                    const int leader = __ffs(m) - 1;
+                    uint32_t base = 0;
+                    if ((int)lane == leader) base = atomicAdd(mon.n_events, (uint32_t)__popc(m));
+                    base = __shfl_sync(warp_mask, base, leader);
+                    if (fire) {
+                        const uint32_t slot = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+                        if (slot < mon.event_cap) mon.events[slot] = nps_event{(int32_t)p, th.row, step, 0, v[j], now};
+                    }
                 }
             }
         }
@@ -292,6 +316,7 @@ __device__ __forceinline__ double threshold_derived(const double* __restrict__ s
     return NAN;
 }
 
+
 constexpr int kThrRowsPerThread = 8;
 __global__ void __launch_bounds__(128)
 nps_threshold_kernel(const double* __restrict__ slab, const Threshold* __restrict__ live, const int32_t* __restrict__ word_start,
@@ -348,6 +373,46 @@ nps_threshold_kernel(const double* __restrict__ slab, const Threshold* __restric
     if (p < n) flags[(int64_t)w * n + p] = bits;
     const unsigned ballot = __ballot_sync(0xffffffffu, bits != 0);
     if ((threadIdx.x & 31) == 0 && ballot && any_warp) atomicOr(&any_warp[p >> 5], ballot);
+}
+
+// Event-list form of the same check: thread per plant walks the live rows (staged in shared memory; every row's value
+// is one coalesced load across the warp) and appends violations to the event list exactly as the in-launch monitor does.
+__global__ void __launch_bounds__(128)
+nps_threshold_events_kernel(const double* __restrict__ slab, const Threshold* __restrict__ live, int n_live, int time_field,
+                            double* __restrict__ last_fired, nps_event* __restrict__ events, uint32_t* __restrict__ n_events,
+                            uint32_t event_cap, int32_t step, int64_t n) {
+    extern __shared__ Threshold s_live[];
+    for (int j = threadIdx.x; j < n_live; j += blockDim.x) s_live[j] = live[j];
+    __syncthreads();
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = p < n;
+    const unsigned lane = threadIdx.x & 31u;
+    const double now = valid ? slab[(int64_t)time_field * n + p] : 0.0;
+    for (int j = 0; j < n_live; ++j) {
+        const Threshold th = s_live[j];
+        bool fire = false;
+        double v = 0.0;
+        if (valid) {
+            v = (th.field >= 0) ? slab[(int64_t)th.field * n + p] : threshold_derived(slab, n, p, th.field);
+            fire = threshold_compare(th.cmp, v, th.value);
+            if (fire) {
+                double* stamp = last_fired + (int64_t)th.row * n + p;
+                if ((now - *stamp) < th.cooldown) fire = false;
+                else *stamp = now;
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, fire);
+        if (m) {
+            const int leader = __ffs(m) - 1;
+            uint32_t base = 0;
+            if ((int)lane == leader) base = atomicAdd(n_events, (uint32_t)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (fire) {
+                const uint32_t slot = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+                if (slot < event_cap) events[slot] = nps_event{(int32_t)p, th.row, step, 0, v, now};
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -513,7 +578,9 @@ int nps_create(int64_t n_plants, int device, nps_handle** out) {
     NPS_CUDA(cudaFuncSetCacheConfig(nps_step_kernel<NPS_STEP_BLOCK, NPS_STEP_MINBLOCKS>, cudaFuncCachePreferL1));
 #else
     NPS_CUDA(cudaFuncSetCacheConfig(nps_step_kernel<448, 1>, cudaFuncCachePreferL1));
-    NPS_CUDA(cudaFuncSetCacheConfig(nps_step_kernel<64, 7>, cudaFuncCachePreferL1));
+    // one-warp blocks: several of them share an SM, each with its 4 KB threshold-row stage; PreferL1 alone would leave
+    // shared memory for a single block per SM (measured: 8 192 plants ran as two waves)
+    NPS_CUDA(cudaFuncSetAttribute(nps_step_kernel<32, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 25));
 #endif
     *out = h;
     return 0;
@@ -553,7 +620,7 @@ static int launch_step(nps_handle* h, const StepArgs& a, cudaStream_t s) {
     nps_step_kernel<NPS_STEP_BLOCK, NPS_STEP_MINBLOCKS><<<(int)((h->n + NPS_STEP_BLOCK - 1) / NPS_STEP_BLOCK), NPS_STEP_BLOCK, 0, s>>>(h->params, a);
 #else
     if (h->n >= kLargeBatch) nps_step_kernel<448, 1><<<(int)((h->n + 447) / 448), 448, 0, s>>>(h->params, a);
-    else nps_step_kernel<64, 7><<<(int)((h->n + 63) / 64), 64, 0, s>>>(h->params, a);
+    else nps_step_kernel<32, 1><<<(int)((h->n + 31) / 32), 32, 0, s>>>(h->params, a);
 #endif
     NPS_CUDA(cudaGetLastError());
     return 0;
@@ -843,6 +910,22 @@ int nps_check_thresholds(nps_handle* h, const double* d_state, double* d_last_fi
     dim3 grid((unsigned)((h->n + block - 1) / block), (unsigned)n_words);   // every flag word is written by its owner
     nps_threshold_kernel<<<grid, block, 0, s>>>(d_state, h->d_thresholds, h->d_word_start, kTimeMinutesField, d_last_fired,
                                                d_flags, d_any_warp, h->n);
+    NPS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int nps_check_thresholds_events(nps_handle* h, const double* d_state, double* d_last_fired, nps_event* d_events,
+                                uint32_t* d_n_events, uint32_t event_capacity, int32_t step, void* cuda_stream) {
+    if (!h || !d_state || !d_last_fired || !d_events || !d_n_events || event_capacity == 0) return fail("nps_check_thresholds_events: null argument");
+    if (h->n_thresholds == 0) return fail("nps_check_thresholds_events: no thresholds set");
+    if (h->n_live_thresholds == 0) return 0;
+    DeviceGuard guard(h->device);
+    const int block = 128;
+    const size_t smem = sizeof(Threshold) * (size_t)h->n_live_thresholds;
+    if (smem > 48 * 1024) return fail("nps_check_thresholds_events: too many live threshold rows for one shared-memory stage");
+    nps_threshold_events_kernel<<<(unsigned)((h->n + block - 1) / block), block, smem, (cudaStream_t)cuda_stream>>>(
+        d_state, h->d_thresholds, h->n_live_thresholds, kTimeMinutesField, d_last_fired, d_events, d_n_events, event_capacity,
+        step, h->n);
     NPS_CUDA(cudaGetLastError());
     return 0;
 }

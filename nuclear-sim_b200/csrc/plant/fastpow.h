@@ -58,10 +58,11 @@ NPS_HD double nps_rcp_f32(double g) {     // 1/g to single precision, correctly 
 #endif
 }
 
-NPS_HD bool nps_pow_pos(double x, double y, double& out) {
+// log x as a double-double (Lh, Ll) for a positive normal x; false outside the guarded range.
+NPS_HD bool nps_pow_log(double x, double& Lh_out, double& Ll_out) {
     const long long ix = nps_bits(x);
     const int be = (int)((ix >> 52) & 0x7ff);
-    if (!(ix > 0) || (unsigned)(be - 23) >= 2000u || !(fabs(y) < 1024.0)) return false;
+    if (!(ix > 0) || (unsigned)(be - 23) >= 2000u) return false;
     int e = be - 1023;
     double m = nps_from_bits((ix & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
     if (m > 1.4142135623730951) { m *= 0.5; e += 1; }
@@ -80,12 +81,20 @@ NPS_HD bool nps_pow_pos(double x, double y, double& out) {
     const double p = fma(po, u2, pe);
     const double lh = 2.0 * u;
     const double ll = fma(u2 * u, p, 2.0 * u_lo);
-    const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10, LOG2E = 1.44269504088896338700e+00;
+    const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
     const double ed = (double)e;
     const double t_hi = ed * LN2_HI;                // exact: LN2_HI has 21 trailing zero bits
     const double Lh = t_hi + lh;
     double Ll = (t_hi - Lh) + lh;                   // fast two-sum (|t_hi| >= |lh| or t_hi == 0)
     Ll += fma(ed, LN2_LO, ll);
+    Lh_out = Lh; Ll_out = Ll;
+    return true;
+}
+
+// exp(y * (Lh + Ll)); false outside the guarded range (|y| >= 1024 or |y log x| >= 64).
+NPS_HD bool nps_pow_exp(double y, double Lh, double Ll, double& out) {
+    if (!(fabs(y) < 1024.0)) return false;
+    const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10, LOG2E = 1.44269504088896338700e+00;
     const double Ph = y * Lh;
     const double Pl = fma(y, Lh, -Ph) + y * Ll;
     if (!(fabs(Ph) < 64.0)) return false;           // results within 1e-28 .. 1e28: the error budget was verified there
@@ -102,6 +111,17 @@ NPS_HD bool nps_pow_pos(double x, double y, double& out) {
     out = nps_from_bits(nps_bits(ex) + ((long long)kd * (1LL << 52)));
     return true;
 }
+
+NPS_HD bool nps_pow_pos(double x, double y, double& out) {
+    double Lh, Ll;
+    if (!(fabs(y) < 1024.0) || !nps_pow_log(x, Lh, Ll)) return false;
+    return nps_pow_exp(y, Lh, Ll, out);
+}
+
+// One base raised to several exponents (the wear laws: load_factor ** e_k, speed_factor ** e_k for every component of a
+// unit): the logarithm of the base is computed once and kept with the base's exact bits; a different base recomputes.
+// Same arithmetic as nps_pow_pos, so results are bit-identical to the unmemoised call.
+struct PowMemo { long long xbits = 0; double Lh = 0.0, Ll = 0.0; int state = 0; };   // state: 0 empty, 1 log valid, 2 base outside the guarded range
 
 #undef nps_pow_tab
 #undef NPS_POW_TAB

@@ -14,7 +14,7 @@ ROOT = U.ROOT
 def _declared_symbols():
     text = open(os.path.join(ROOT, "include", "nps_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(nps_[a-z_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(nps_[a-z0-9_]+)\s*\(", text)))
 
 
 def test_header_symbols_exported():
