@@ -253,8 +253,13 @@ class BatchedNuclearPlantSimulator:
             return np.zeros(0, dtype=EVENT_DTYPE)
         if n > g["cap"]:
             raise _clib.NpsError(f"event list overflow: {n} violations, capacity {g['cap']} (enable_monitor(event_capacity=...))")
-        ev = g["events"][:n].cpu().numpy().view(EVENT_DTYPE).reshape(-1).copy()
+        if g.get("host") is None or g["host"].shape[0] < n:      # pinned landing buffer, grown geometrically
+            g["host"] = torch.empty((max(n, 2 * (g["host"].shape[0] if g.get("host") is not None else 4096)), EVENT_DTYPE.itemsize),
+                                    dtype=torch.uint8).pin_memory()
+        g["host"][:n].copy_(g["events"][:n], non_blocking=True)
         g["n_events"].zero_()
+        torch.cuda.current_stream(self.device).synchronize()
+        ev = g["host"][:n].numpy().view(EVENT_DTYPE).reshape(-1).copy()
         return ev[np.lexsort((ev["row"], ev["plant"], ev["step"]))]
 
     @property
@@ -372,6 +377,9 @@ class BatchedNuclearPlantSimulator:
     def write_fields(self, plant: int, values: Dict[int, float]) -> None:
         for f, v in values.items():
             self.slab[int(f), int(plant)] = float(v)
+
+    def synchronize(self) -> None:
+        torch.cuda.synchronize(self.device)
 
     # -- state access -------------------------------------------------------------------------
     def current_time_minutes(self) -> float:
@@ -493,7 +501,8 @@ class BatchedNuclearPlantSimulator:
     def apply_maintenance(self, requests) -> list:
         """requests: iterable of (plant, target code, action code, arg); returns the per-request status codes
         (0 failed, 1 success, 2 unsupported target), applied in order."""
-        req = np.array(list(requests), dtype=np.int32).reshape(-1, 4)
+        req = (np.ascontiguousarray(requests, dtype=np.int32) if isinstance(requests, np.ndarray)
+               else np.array(list(requests), dtype=np.int32)).reshape(-1, 4)
         if len(req) == 0:
             return []
         cols = [np.ascontiguousarray(req[:, j]) for j in range(4)]
@@ -502,7 +511,7 @@ class BatchedNuclearPlantSimulator:
         _clib.check(self.L.nps_apply_maintenance(self._h, _ptr(self.slab), *(c.ctypes.data_as(ctypes.c_void_p) for c in cols),
                                                  len(req), status.ctypes.data_as(ctypes.c_void_p), ctypes.c_void_p(stream)))
         self.n_launches += 1
-        return status.tolist()
+        return status if isinstance(requests, np.ndarray) else status.tolist()
 
     # -- trajectory ring buffer (state_manager.py:152-233) --------------------------------------
     def set_logged_fields(self, names: Sequence[str], ring_rows: int) -> None:

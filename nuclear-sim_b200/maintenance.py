@@ -500,7 +500,7 @@ class BatchedAutoMaintenance:
         return not (self.last_check_time > 0.0 and t_minutes - self.last_check_time < self.check_interval_hours * 60)
 
     def advance(self, n_steps: int, actions=None, magnitudes=None, noise=None, power_setpoint=None,
-                t0_minutes: Optional[float] = None, max_k: int = 128) -> None:
+                t0_minutes: Optional[float] = None, max_k: int = 128, timers: Optional[dict] = None) -> None:
         """n_steps reference steps with monitoring and automatic maintenance, in as few launches as exactness allows.
 
         Thresholds are evaluated on the device after every substep, so events carry their own step.  Work orders only
@@ -521,13 +521,25 @@ class BatchedAutoMaintenance:
                 k += 1
             t_end = t0 + (done + k) * dt
             on_gate = self.gate_open(t_end)
+            if timers is not None:
+                import time as _time
+                c0 = _time.perf_counter()
             sim.step(actions=sl(actions, done, done + k), magnitudes=sl(magnitudes, done, done + k),
                      noise=sl(noise, done, done + k), power_setpoint=sl(power_setpoint, done, done + k), K=k,
                      skip_last_check=on_gate)
+            if timers is not None:      # attribute the wall clock: step kernel (synchronised) vs everything after it
+                getattr(sim, "synchronize", lambda: None)()
+                c1 = _time.perf_counter()
             self.handle_step_events(sim.drain_step_events())
             if on_gate:
                 self.update(t_end)
                 self.check(t_end)
+            if timers is not None:
+                getattr(sim, "synchronize", lambda: None)()
+                c2 = _time.perf_counter()
+                timers["step_kernel"] = timers.get("step_kernel", 0.0) + (c1 - c0)
+                timers["bookkeeping"] = timers.get("bookkeeping", 0.0) + (c2 - c1)
+                timers["launches"] = timers.get("launches", 0) + 1
             done += k
 
     def _process(self, t_minutes: float, fired, values) -> List[WorkOrder]:
@@ -589,3 +601,297 @@ class BatchedAutoMaintenance:
         book.recent_triggers[key] = t_minutes
         self.created_log.append(wo)
         return wo
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the same bookkeeping, columnar: for batches where tens of thousands of plants can fire in one check
+# ---------------------------------------------------------------------------------------------------------------
+class ColumnarAutoMaintenance(BatchedAutoMaintenance):
+    """BatchedAutoMaintenance with array bookkeeping instead of per-order Python objects.
+
+    Same rules, same order, same results (tests/test_maintenance_host.py runs both on the same scenarios); the per-event
+    work is numpy on whole event batches: decisions for the common one-violation event are a table lookup
+    (single_violation_rules), dedupe stamps live in one sorted key array, pending orders and the logs are columns.
+    Events with several violations of one component in one step (rare) take the orchestrate() path one by one.
+    With it the host side of BASELINE config #5 (131 072 plants per GPU, every pump crossing a threshold) costs less
+    than the step kernel (profiles/r02_cfg5_*.json); the object form above needs ~14 us per work order."""
+
+    _PRIOS = ("LOW", "MEDIUM", "HIGH", "CRITICAL", "EMERGENCY")
+
+    def __init__(self, sim, table: ThresholdTable, aggressive: bool = True, head_quirks: bool = True):
+        super().__init__(sim, table, aggressive, head_quirks)
+        import numpy as np
+        self.np = np
+        rows = table.rows
+        self.comp_ids: List[str] = []
+        comp_of = {}
+        for r in rows:
+            if r.component_id not in comp_of:
+                comp_of[r.component_id] = len(self.comp_ids)
+                self.comp_ids.append(r.component_id)
+        self.actions: List[str] = []
+        act_of: Dict[str, int] = {}
+
+        def aid(name):
+            if name not in act_of:
+                act_of[name] = len(self.actions)
+                self.actions.append(name)
+            return act_of[name]
+        R = len(rows)
+        self.row_comp = np.array([comp_of[r.component_id] for r in rows], dtype=np.int64)
+        max_rules = max([len(s[0]) for s in self._single] + [1])
+        self.rule_thr = np.full((R, max_rules), np.inf)
+        self.rule_act = np.zeros((R, max_rules), dtype=np.int64)
+        self.fallback = np.zeros(R, dtype=np.int64)
+        self.row_action = np.zeros(R, dtype=np.int64)
+        for i, (rules, fb) in enumerate(self._single):
+            self.fallback[i] = aid(fb)
+            self.row_action[i] = aid(rows[i].action) if rows[i].action else -1
+            for j, (thr, act) in enumerate(rules):
+                self.rule_thr[i, j], self.rule_act[i, j] = thr, aid(act)
+        self._aid = aid
+        self.row_prio = np.array([self._PRIOS.index(r.priority.upper()) if r.priority.upper() in self.delays else 1 for r in rows],
+                                 dtype=np.int64)
+        self.subs: List[Optional[str]] = [None]          # sub-component selectors (threshold_config['component_id']) by index
+        for r in rows:
+            if r.sub_component and r.sub_component not in self.subs:
+                self.subs.append(r.sub_component)
+        self.row_sub = np.array([self.subs.index(r.sub_component) if r.sub_component else 0 for r in rows], dtype=np.int64)
+        self.sub_arg = np.array([BEARING_ARG.get(q, 0) for q in self.subs], dtype=np.int64)
+        self.prio_delay = np.array([self.delays[p] * 60.0 for p in self._PRIOS])
+        self._refresh_action_tables()
+        self.comp_target = np.array([target_code(c) for c in self.comp_ids], dtype=np.int64)
+        self.n_comp = len(self.comp_ids)
+        # dedupe stamps: sorted keys (plant, component, action) -> time of the last work order created
+        self.rk = np.zeros(0, dtype=np.int64)
+        self.rt = np.zeros(0)
+        self.n_created = np.zeros(sim.n_plants, dtype=np.int64)
+        z = lambda dt=np.int64: np.zeros(0, dtype=dt)   # noqa: E731
+        self.pend = {"plant": z(), "comp": z(), "act": z(), "prio": z(), "sub": z(), "seq": z(), "created": z(float), "planned": z(float)}
+        self.created_cols: List[dict] = []
+        self.executed_cols: List[dict] = []
+        self.event_cols: List[dict] = []
+        # rows whose cooldown a performed action re-arms (record_maintenance_result path, head_quirks=False)
+        self._reset_rows: Dict[tuple, List[int]] = {}
+
+    def _refresh_action_tables(self):
+        np = self.np
+        known = known_action_names()
+        self.act_known = np.array([a in known for a in self.actions], dtype=bool)
+        self.act_code = np.array([action_code(a) for a in self.actions], dtype=np.int64)
+        self.act_is_bearing = np.array([a == "bearing_replacement" for a in self.actions], dtype=bool)
+
+    def _key(self, plant, comp, act):
+        return (plant * self.n_comp + comp) * 4096 + act
+
+    def reset(self, plants) -> None:
+        np = self.np
+        plants = np.asarray(list(plants), dtype=np.int64)
+        keep = ~np.isin(self.pend["plant"], plants)
+        self.pend = {k: v[keep] for k, v in self.pend.items()}
+        kp = self.rk // (self.n_comp * 4096)
+        keep = ~np.isin(kp, plants)
+        self.rk, self.rt = self.rk[keep], self.rt[keep]
+        self.n_created[plants] = 0
+
+    # -- events -> work orders ---------------------------------------------------------------------------------------
+    def handle_step_events(self, events):
+        np = self.np
+        n = len(events)
+        if n == 0:
+            return 0
+        steps = events["step"]
+        cuts = np.flatnonzero(np.diff(steps)) + 1
+        made = 0
+        for a, b in zip(np.concatenate([[0], cuts]), np.concatenate([cuts, [n]])):
+            made += self._process_arrays(float(events["time_minutes"][a]), events["plant"][a:b].astype(np.int64),
+                                         events["row"][a:b].astype(np.int64), events["value"][a:b])
+        return made
+
+    def check(self, t_minutes: float):
+        if not hasattr(self.sim, "check_thresholds_events"):
+            return super().check(t_minutes)
+        if getattr(self.sim, "_mon", None) is None:
+            self.sim.enable_monitor()
+        self.sim.check_thresholds_events()
+        ev = self.sim.drain_step_events()
+        if len(ev) == 0:
+            return 0
+        return self._process_arrays(t_minutes, ev["plant"].astype(self.np.int64), ev["row"].astype(self.np.int64), ev["value"])
+
+    def _process(self, t_minutes, fired, values):      # object-form entry point of the base class
+        np = self.np
+        if not fired:
+            return []
+        pl = np.array([f[0] for f in fired], dtype=np.int64)
+        rw = np.array([f[1] for f in fired], dtype=np.int64)
+        return self._process_arrays(t_minutes, pl, rw, np.array([values[f] for f in fired]))
+
+    def _process_arrays(self, t, plant, row, value) -> int:
+        """One step's violations (sorted by (plant, row)) -> events, decisions, work orders."""
+        np = self.np
+        comp = self.row_comp[row]
+        gkey = plant * self.n_comp + comp
+        order = np.lexsort((row, comp, plant))          # components of a plant in table order, rows in config order
+        plant, row, value, comp, gkey = plant[order], row[order], value[order], comp[order], gkey[order]
+        first = np.concatenate([[True], gkey[1:] != gkey[:-1]])
+        starts = np.flatnonzero(first)
+        counts = np.diff(np.concatenate([starts, [len(gkey)]]))
+        g_plant, g_comp, g_row, g_val = plant[starts], comp[starts], row[starts], value[starts]
+        # one-violation events: table lookup (first matching rule wins)
+        act = self.fallback[g_row].copy()
+        for j in range(self.rule_thr.shape[1] - 1, -1, -1):
+            m = g_val > self.rule_thr[g_row, j]
+            act[m] = self.rule_act[g_row[m], j]
+        prio = self.row_prio[g_row].copy()
+        sub = np.where(self.row_action[g_row] == act, self.row_sub[g_row], 0)
+        multi = np.flatnonzero(counts > 1)
+        for gi in multi:                                 # several violations of one component in one step: orchestrate()
+            lo, hi = starts[gi], starts[gi] + counts[gi]
+            viol = []
+            for t_row, v in zip(row[lo:hi], value[lo:hi]):
+                r = self.table.rows[int(t_row)]
+                viol.append({"parameter": r.parameter, "value": float(v), "threshold": r.threshold, "comparison": r.comparison,
+                             "action": r.action, "priority": r.priority, "component_id": r.sub_component})
+            name = orchestrate(self.comp_ids[int(g_comp[gi])], viol, viol[0]["action"])
+            if name not in self.actions:
+                self._aid(name)
+                self._refresh_action_tables()
+            act[gi] = self.actions.index(name)
+            pr = max((v["priority"] for v in viol), key=lambda q: _PRIORITY_RANK.get(q, 2))
+            prio[gi] = self._PRIOS.index(pr.upper()) if pr.upper() in self.delays else 1
+            sub[gi] = 0
+            for v in viol:
+                if v.get("action") == name and v.get("component_id"):
+                    sub[gi] = self.subs.index(v["component_id"])
+                    break
+        self.event_cols.append({"t": t, "plant": g_plant, "comp": g_comp, "act": act.copy(), "starts": starts, "n": counts,
+                                "row_all": row, "value_all": value})
+        # _create_automatic_work_order: known action, dedupe stamp (minutes vs hours, sic), no active order for (component, action)
+        ok = self.act_known[act] & (act >= 0)
+        key = self._key(g_plant, g_comp, act)
+        if len(self.rk):
+            # a stamp only ever blocks while t - stamp < 24 (minutes against the hours constant, sic) and the clock only
+            # moves forward, so older stamps are dropped instead of carried: the key array stays a few checks long
+            live = (t - self.rt) < self.work_order_cooldown_hours
+            if not live.all():
+                self.rk, self.rt = self.rk[live], self.rt[live]
+        if len(self.rk):
+            pos = np.minimum(np.searchsorted(self.rk, key), len(self.rk) - 1)
+            ok &= ~(self.rk[pos] == key)
+        if len(self.pend["plant"]):
+            ok &= ~np.isin(key, self._key(self.pend["plant"], self.pend["comp"], self.pend["act"]))
+        idx = np.flatnonzero(ok)
+        if len(idx) == 0:
+            return 0
+        c_plant, c_comp, c_act, c_prio, c_sub, c_key = g_plant[idx], g_comp[idx], act[idx], prio[idx], sub[idx], key[idx]
+        # WO-%06d numbering per plant, in creation order (plants ascending, components in table order)
+        firstp = np.concatenate([[True], c_plant[1:] != c_plant[:-1]])
+        run_start = np.maximum.accumulate(np.where(firstp, np.arange(len(c_plant)), 0))
+        rank = np.arange(len(c_plant)) - run_start
+        seq = self.n_created[c_plant] + rank + 1
+        up, cnt = np.unique(c_plant, return_counts=True)
+        self.n_created[up] += cnt
+        created = np.full(len(idx), t)
+        planned = t + self.prio_delay[c_prio]
+        new = {"plant": c_plant, "comp": c_comp, "act": c_act, "prio": c_prio, "sub": c_sub, "seq": seq, "created": created, "planned": planned}
+        self.pend = {k: np.concatenate([self.pend[k], new[k]]) for k in self.pend}
+        self.created_cols.append(new)
+        # dedupe stamps of the new orders (their keys are not in the array: a live stamp would have blocked them)
+        allk = np.concatenate([self.rk, c_key])
+        allt = np.concatenate([self.rt, created])
+        o = np.argsort(allk, kind="stable")
+        self.rk, self.rt = allk[o], allt[o]
+        return len(idx)
+
+    # -- due work orders -> device -------------------------------------------------------------------------------------
+    def update(self, t_minutes: float):
+        np = self.np
+        if not self.gate_open(t_minutes):
+            return 0
+        self.last_check_time = t_minutes
+        P = self.pend
+        if len(P["plant"]) == 0:
+            return 0
+        due = np.flatnonzero(t_minutes >= P["planned"])
+        if len(due) == 0:
+            return 0
+        if self.head_quirks:      # at most one order per plant per update: the first due one in creation order
+            o = np.lexsort((due, P["plant"][due]))      # pending rows are in creation order; group by plant
+            pl = P["plant"][due][o]
+            firstp = np.concatenate([[True], pl[1:] != pl[:-1]])
+            due = np.sort(due[o][firstp])
+        else:
+            due = due[np.lexsort((due, P["plant"][due]))]
+        d_act = P["act"][due]
+        req = np.stack([P["plant"][due], self.comp_target[P["comp"][due]], self.act_code[d_act],
+                        np.where(self.act_is_bearing[d_act], self.sub_arg[P["sub"][due]], 0)], axis=1).astype(np.int32)
+        status = np.asarray(self.sim.apply_maintenance(req))
+        if (status == 2).any():
+            bad = int(np.flatnonzero(status == 2)[0])
+            raise NotImplementedError(f"perform_maintenance on {self.comp_ids[int(P['comp'][due][bad])]} is not restated on the device")
+        done = {k: v[due] for k, v in P.items()}
+        done["executed_at"] = np.full(len(due), t_minutes)
+        done["success"] = status == 1
+        self.executed_cols.append(done)
+        keep = np.ones(len(P["plant"]), dtype=bool)
+        keep[due] = False
+        self.pend = {k: v[keep] for k, v in P.items()}
+        if not self.head_quirks:
+            for i in np.flatnonzero(done["success"]):
+                name, cid = self.actions[int(done["act"][i])], self.comp_ids[int(done["comp"][i])]
+                rows = self._reset_rows.get((cid, name))
+                if rows is None:
+                    addressed = _COOLDOWN_RESET.get(name, [])
+                    rows = [r for r in self._rows_by_component.get(cid, []) if self.table.rows[r].parameter in addressed]
+                    self._reset_rows[(cid, name)] = rows
+                if rows:
+                    self.sim.reset_cooldowns(int(done["plant"][i]), rows)
+        return len(due)
+
+    # -- object views of the logs (tests, exports) -------------------------------------------------------------------
+    def _orders(self, cols, executed=False) -> List[WorkOrder]:
+        out = []
+        for c in cols:
+            for i in range(len(c["plant"])):
+                wo = WorkOrder(f"WO-{int(c['seq'][i]):06d}", int(c["plant"][i]), self.comp_ids[int(c["comp"][i])],
+                               self.actions[int(c["act"][i])], self._PRIOS[int(c["prio"][i])], float(c["created"][i]),
+                               float(c["planned"][i]), self.subs[int(c["sub"][i])])
+                if executed:
+                    wo.status, wo.executed_at, wo.success = "COMPLETED", float(c["executed_at"][i]), bool(c["success"][i])
+                out.append(wo)
+        return out
+
+    @property
+    def n_work_orders_created(self) -> int:
+        return int(sum(len(c["plant"]) for c in self.created_cols))
+
+    @property
+    def n_work_orders_executed(self) -> int:
+        return int(sum(len(c["plant"]) for c in self.executed_cols))
+
+    def counts_by_action(self) -> Dict[str, int]:
+        np = self.np
+        out: Dict[str, int] = {}
+        for c in self.created_cols:
+            ids, cnt = np.unique(c["act"], return_counts=True)
+            for a, k in zip(ids, cnt):
+                out[self.actions[int(a)]] = out.get(self.actions[int(a)], 0) + int(k)
+        return out
+
+    def materialize_logs(self) -> None:
+        """Fill created_log / executed_log / event_log (lists of objects, as BatchedAutoMaintenance keeps them)."""
+        ex = {(w.plant, w.work_order_id): w for w in self._orders(self.executed_cols, executed=True)}
+        self.created_log = [ex.get((w.plant, w.work_order_id), w) for w in self._orders(self.created_cols)]
+        self.executed_log = list(ex.values())
+        self.event_log = []
+        for c in self.event_cols:
+            for i in range(len(c["plant"])):
+                lo, hi = int(c["starts"][i]), int(c["starts"][i]) + int(c["n"][i])
+                viol = []
+                for t_row, v in zip(c["row_all"][lo:hi], c["value_all"][lo:hi]):
+                    r = self.table.rows[int(t_row)]
+                    viol.append({"parameter": r.parameter, "value": float(v), "threshold": r.threshold, "comparison": r.comparison,
+                                 "action": r.action, "priority": r.priority, "component_id": r.sub_component})
+                self.event_log.append({"t": c["t"], "plant": int(c["plant"][i]), "component": self.comp_ids[int(c["comp"][i])],
+                                       "action": self.actions[int(c["act"][i])], "violations": viol})

@@ -1,8 +1,14 @@
 #!/usr/bin/env python
-"""BASELINE config #5 on one GPU: long-horizon maintenance degradation with the full loop
-(step kernel -> due work orders applied on the device -> flag kernel -> host drain -> work orders).
-dt = 5 min, one launch = 3 fused substeps = the 15-minute maintenance gate (auto_maintenance.py:74,213-217), 24 h.
-Prints one JSON line: plant-steps/s for the whole loop, time split device / host, event counts."""
+"""BASELINE config #5: long-horizon maintenance degradation with the FULL loop, sharded over the GPUs of one node.
+
+    python profiles/run_cfg5_maintenance.py [--plants-per-gpu 131072] [--hours 24]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 profiles/run_cfg5_maintenance.py
+
+dt = 5 min; every rank owns a contiguous plant range (ShardedBatchedSimulator) and runs its own work-order
+bookkeeping (ColumnarAutoMaintenance.advance): thresholds are evaluated after every substep inside the launch, a
+launch ends on each 15-minute gate step, due work orders are applied on the device, the gate step is checked by the
+event-list flag kernel.  No collective on the path; per-action counts are all-gathered at the end.
+Prints one JSON line: whole-job plant-steps/s, per-rank wall-clock split (step kernel vs bookkeeping), work orders."""
 import argparse
 import json
 import os
@@ -11,59 +17,76 @@ import time
 
 import numpy as np
 import torch
+import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from nuclear_sim_b200 import BatchedNuclearPlantSimulator, load_snapshot, field_index  # noqa: E402
+from nuclear_sim_b200 import load_snapshot, field_index  # noqa: E402
 from nuclear_sim_b200 import scenarios as sc  # noqa: E402
-from nuclear_sim_b200.maintenance import BatchedAutoMaintenance, ThresholdTable  # noqa: E402
+from nuclear_sim_b200.maintenance import ColumnarAutoMaintenance, ThresholdTable  # noqa: E402
+from nuclear_sim_b200.sharded import ShardedBatchedSimulator  # noqa: E402
 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--plants", type=int, default=131072)
+    ap.add_argument("--plants-per-gpu", type=int, default=131072)
     ap.add_argument("--hours", type=float, default=24.0)
     args = ap.parse_args()
-    n, k, dt = args.plants, 3, 5.0
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n, dt = args.plants_per_gpu, 5.0
     s0, params = load_snapshot("pwr3000_oil_top_off_dt5")
     ix = field_index()
-    pid = np.arange(n)
-    st = sc.randomized_states(s0, pid)
-    rng = np.random.RandomState(7)
-    # initial conditions positioned near maintenance thresholds: oil levels just above 58 %,
-    # TSP fouling / tube scale near their triggers, contamination near 15.2 ppm
-    for p in range(4):
-        st[:, ix[f"fw.pump[{p}].lub.oil_level"]] = 58.0 + rng.uniform(0.0, 6.0, n)
-        st[:, ix[f"fw.pump[{p}].lub.oil_contamination_level"]] = 15.2 - rng.uniform(0.0, 0.6, n)
-    g = np.load(os.path.join(ROOT, "tests", "golden", "maint_oil_top_off.npz"), allow_pickle=False)
-    cfg = json.loads(str(g["log"]))["maintenance_system"]
-    sim = BatchedNuclearPlantSimulator(n, st, params)
-    maint = BatchedAutoMaintenance(sim, ThresholdTable(cfg), aggressive=True)
-    launches = int(args.hours * 60 / (k * dt))
+
+    def states(pid):
+        """Initial conditions positioned near maintenance thresholds: oil levels just above 58 %,
+        contamination near 15.2 ppm — a pure function of the global plant id."""
+        st = sc.randomized_states(s0, pid)
+        u = sc.noise_inputs(pid, 0, 2, seed=7)[:, 2:, :]          # [2, 3, n] uniforms keyed by plant id
+        for p in range(4):
+            st[:, ix[f"fw.pump[{p}].lub.oil_level"]] = 58.0 + 6.0 * u[p // 3, p % 3]
+            st[:, ix[f"fw.pump[{p}].lub.oil_contamination_level"]] = 15.2 - 0.6 * u[(p + 1) // 3 % 2, (p + 1) % 3]
+        return st
+    shard = ShardedBatchedSimulator(world * n, s0, params, rank=rank, world=world, device=f"cuda:{local}", states=states)
+    cfg = json.load(open(os.path.join(ROOT, "nuclear-sim_b200", "data", "maintenance_system_template.json")))
+    maint = ColumnarAutoMaintenance(shard.sim, ThresholdTable(cfg), aggressive=True)
+    shard.sim.enable_monitor(event_capacity=8 * n)
+    steps = int(args.hours * 60 / dt)
+    maint.advance(3)                                    # warm-up: first launches, allocations
     torch.cuda.synchronize()
-    t_dev = t_host = 0.0
+    if world > 1:
+        dist.barrier()
+    timers = {}
     t0 = time.perf_counter()
-    for i in range(launches):
-        a = time.perf_counter()
-        sim.step(K=k)
-        torch.cuda.synchronize()
-        b = time.perf_counter()
-        now = (i + 1) * k * dt
-        maint.update(now)
-        maint.check(now)
-        c = time.perf_counter()
-        t_dev += b - a
-        t_host += c - b
+    maint.advance(steps, timers=timers)
+    torch.cuda.synchronize()
     total = time.perf_counter() - t0
-    by_action = {}
-    for wo in maint.created_log:
-        by_action[wo.action] = by_action.get(wo.action, 0) + 1
-    print(json.dumps({"workload": "cfg5: long-horizon maintenance degradation, dt=5 min, 3 substeps per launch (15-min gate)",
-                      "plants": n, "simulated_hours": args.hours, "launches": launches, "plant_steps": n * k * launches,
-                      "plant_steps_per_s_whole_loop": n * k * launches / total, "seconds_total": total,
-                      "seconds_step_kernel": t_dev, "seconds_flag_kernel_drain_workorders_effects": t_host,
-                      "events": len(maint.event_log), "work_orders_created": len(maint.created_log),
-                      "work_orders_executed": len(maint.executed_log), "by_action": by_action}))
+    t = torch.tensor([total, timers["step_kernel"], timers["bookkeeping"]], dtype=torch.float64, device=f"cuda:{local}")
+    counts = torch.tensor([maint.n_work_orders_created, maint.n_work_orders_executed, sum(len(c["plant"]) for c in maint.event_cols)],
+                          dtype=torch.int64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    summary = shard.gather_summaries(["fw.pump[0].lub.oil_level", "pri.power_level"])
+    if rank == 0:
+        total, t_dev, t_host = (float(x) for x in t)
+        print(json.dumps({
+            "workload": "cfg5: long-horizon maintenance degradation, dt=5 min, launches cut at the 15-min gate, full loop",
+            "n_gpus": world, "plants": world * n, "plants_per_gpu": n, "simulated_hours": args.hours, "steps": steps,
+            "launches_per_rank": timers["launches"], "plant_steps": world * n * steps,
+            "plant_steps_per_s_whole_loop": world * n * steps / total, "seconds_total_max_over_ranks": total,
+            "seconds_step_kernel_max_over_ranks": t_dev, "seconds_bookkeeping_max_over_ranks": t_host,
+            "bookkeeping_over_kernel": t_host / t_dev,
+            "threshold_events": int(counts[2]), "work_orders_created": int(counts[0]), "work_orders_executed": int(counts[1]),
+            "by_action_rank0": maint.counts_by_action(), "mean_oil_level_pump0": float(summary[:, 0].mean()),
+            "bookkeeping": "ColumnarAutoMaintenance (numpy columns; in-launch threshold events + event-list flag kernel at gate steps)"}))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

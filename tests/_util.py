@@ -192,6 +192,13 @@ class OracleSim:
     def current_time_minutes(self):
         return float(self.st[0, self.ix["sim.time_minutes"]])
 
+    def check_thresholds_events(self):
+        self.check_thresholds()
+        now = self.current_time_minutes()
+        for p, t in self._fired:
+            self._step_events.append((p, t, self.step_index - 1, 0, float(self._value(self._rows[t][0])[p]), now))
+        self._fired = []
+
     def drain_step_events(self):
         from nuclear_sim_b200.batched import EVENT_DTYPE
         ev = np.array(sorted(self._step_events, key=lambda e: (e[2], e[0], e[1])), dtype=EVENT_DTYPE) if self._step_events \

@@ -262,6 +262,35 @@ def test_cuda_maintenance_batched_equals_oracle_host_logic():
     U.assert_states_close(sims[0].state_numpy(), sims[1].state_numpy(), U.TOL_STEP * 30, "batched maintenance")
 
 
+def test_cuda_columnar_maintenance_equals_object_bookkeeping():
+    """The large-batch path end to end on the device: in-launch threshold events, event-list flag kernel at the gate
+    steps, ColumnarAutoMaintenance, effects applied by the maintenance kernel — against the object bookkeeping on the
+    host oracle stand-in, 512 plants staggered around several thresholds, 36 steps."""
+    import json
+    from nuclear_sim_b200 import maintenance as M, field_index
+    g = np.load(os.path.join(U.GOLDEN, "maint_oil_top_off.npz"), allow_pickle=False)
+    cfg = json.loads(str(g["log"]))["maintenance_system"]
+    ix = field_index()
+    n = 512
+    st = np.tile(g["state0"], (n, 1))
+    rng = np.random.RandomState(21)
+    st[:, ix["fw.pump[0].lub.oil_level"]] = 58.0 + rng.uniform(-0.3, 1.5, n)
+    st[:, ix["fw.pump[2].lub.oil_level"]] = 58.0 + rng.uniform(0.0, 3.0, n)
+    st[:, ix["fw.pump[1].lub.oil_contamination_level"]] = 15.2 - rng.uniform(-0.01, 0.03, n)
+    st[::3, ix["fw.pump[3].lub.component_wear[1]"]] = 8.6
+    st[::5, ix["fw.pump[3].lub.component_wear[4]"]] = 16.5
+    dev, host = _sim(st, g["params"]), U.OracleSim(st, g["params"])
+    md = M.ColumnarAutoMaintenance(dev, M.ThresholdTable(cfg), aggressive=True)
+    mh = M.BatchedAutoMaintenance(host, M.ThresholdTable(cfg), aggressive=True)
+    md.advance(36)
+    mh.advance(36)
+    md.materialize_logs()
+    key = lambda w: (w.created, w.plant, w.component_id, w.action, w.work_order_id, w.priority, w.sub_component, w.executed_at, w.success)   # noqa: E731
+    assert sorted(key(w) for w in md.created_log) == sorted(key(w) for w in mh.created_log)
+    assert md.n_work_orders_created > 600 and md.n_work_orders_executed > 400
+    U.assert_states_close(dev.state_numpy(), host.state_numpy(), U.TOL_STEP * 36, "columnar maintenance on the device")
+
+
 def test_cuda_scalar_facade_runs_maintenance_scenario(tmp_path):
     """The reference-API facade (plant_simulator.NuclearPlantSimulator) on a 1-plant CUDA engine: step() dicts, work
     orders through the runner-facing members, CSV export in the reference schema."""

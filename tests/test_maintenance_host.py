@@ -154,6 +154,59 @@ def test_advance_with_fused_launches_equals_single_steps(name, max_k):
     U.assert_states_close(sim.state_numpy(), g["states"][T - 1][None, :], U.TOL_STEP * T, f"{name} final state")
 
 
+@pytest.mark.parametrize("name", SCENARIOS)
+def test_columnar_bookkeeping_on_reference_scenarios(name):
+    """ColumnarAutoMaintenance (array bookkeeping) through advance(): same events, orders and state as the live reference."""
+    M = _maint()
+    g = np.load(os.path.join(U.GOLDEN, f"maint_{name}.npz"), allow_pickle=False)
+    log = json.loads(str(g["log"]))
+    T = g["states"].shape[0]
+    sim = U.OracleSim(g["state0"], g["params"])
+    maint = M.ColumnarAutoMaintenance(sim, M.ThresholdTable(log["maintenance_system"]), aggressive=True)
+    noise = np.ascontiguousarray((g["noise"][:, None, :] if g["noise"].ndim == 2 else g["noise"]).transpose(0, 2, 1))
+    maint.advance(T, noise=noise)
+    maint.materialize_logs()
+    compare_logs(maint, log)
+    U.assert_states_close(sim.state_numpy(), g["states"][T - 1][None, :], U.TOL_STEP * T, f"{name} final state")
+
+
+@pytest.mark.parametrize("head_quirks", [True, False])
+def test_columnar_equals_object_bookkeeping_on_a_busy_batch(head_quirks):
+    """192 plants with oil levels, contamination and bearing wear staggered around their thresholds (several components
+    and several violations per component fire in the same check): the columnar and the object implementation create and
+    execute the same work orders at the same times and leave the same state."""
+    M = _maint()
+    from nuclear_sim_b200 import field_index
+    g = np.load(os.path.join(U.GOLDEN, "maint_oil_top_off.npz"), allow_pickle=False)
+    cfg = json.loads(str(g["log"]))["maintenance_system"]
+    ix = field_index()
+    n = 192
+    st = np.tile(g["state0"], (n, 1))
+    rng = np.random.RandomState(11)
+    st[:, ix["fw.pump[0].lub.oil_level"]] = 58.0 + rng.uniform(-0.3, 1.0, n)
+    st[:, ix["fw.pump[2].lub.oil_level"]] = 58.0 + rng.uniform(0.0, 2.0, n)
+    st[:, ix["fw.pump[1].lub.oil_contamination_level"]] = 15.2 - rng.uniform(-0.01, 0.02, n)
+    st[:, ix["fw.pump[0].lub.oil_contamination_level"]] = 15.2 - rng.uniform(-0.05, 0.02, n)
+    st[::3, ix["fw.pump[3].lub.component_wear[1]"]] = 8.6          # motor bearing wear above 8.5: bearing_replacement
+    st[::5, ix["fw.pump[3].lub.component_wear[4]"]] = 16.5         # seal wear above 16: seal_replacement (-> overhaul with the above)
+    sims = [U.OracleSim(st, g["params"]), U.OracleSim(st, g["params"])]
+    maints = [M.BatchedAutoMaintenance(sims[0], M.ThresholdTable(cfg), aggressive=True, head_quirks=head_quirks),
+              M.ColumnarAutoMaintenance(sims[1], M.ThresholdTable(cfg), aggressive=True, head_quirks=head_quirks)]
+    for m in maints:
+        m.advance(24)
+    maints[1].materialize_logs()
+    key = lambda w: (w.created, w.plant, w.component_id, w.action, w.work_order_id, w.priority, w.planned_start, w.sub_component,  # noqa: E731
+                     w.executed_at, w.success)
+    a, b = sorted(key(w) for w in maints[0].created_log), sorted(key(w) for w in maints[1].created_log)
+    assert a == b and len(a) > 200
+    assert len({k[3] for k in a}) >= 4                     # several distinct actions, promotions included
+    ex = lambda m: sorted((w.executed_at, w.plant, w.work_order_id, w.action, w.success) for w in m.executed_log)   # noqa: E731
+    assert ex(maints[0]) == ex(maints[1]) and len(maints[1].executed_log) > 100
+    assert [(e["t"], e["plant"], e["component"], e["action"]) for e in maints[0].event_log] == \
+           [(e["t"], e["plant"], e["component"], e["action"]) for e in maints[1].event_log]
+    np.testing.assert_array_equal(sims[0].state_numpy(), sims[1].state_numpy())
+
+
 def test_single_violation_fast_path_equals_orchestrate():
     """BatchedAutoMaintenance precomputes the decision for one-violation events; it must agree with orchestrate()
     for every threshold row of the reference configuration, below and above every rule threshold."""

@@ -56,3 +56,33 @@ def test_live_reference_step_equals_restatement(oracle_lib):
         assert oracle_lib.nps_oracle_step(U.ptr(c), U.ptr(params), U.ptr(np.array([8], dtype=np.int8)), U.ptr(np.array([1.0])),
                                           U.ptr(z), ctypes.c_int64(1), 1) == 0
         U.assert_states_close(c, s1[None, :], 1e-12, f"live step {k}")
+
+
+def test_long_format_export_equals_reference_plant_data_logger(tmp_path):
+    """the long-format trajectory CSV.  The reference's own PlantDataLogger
+    (data/plant_data_logger.py:82-157) logs a live plant for 12 steps; export_long_format writes the same steps from the
+    extracted PlantState vectors.  Every row — parameter name, value text, unit, quality, and their order — must be equal
+    (the timestamp column is datetime.now() in the reference, so it is copied over)."""
+    import csv
+    import os
+    import sys
+    from nuclear_sim_b200 import export as E
+    rp = R.make_reference_plant(R.compose_config("oil_top_off"), dt=1.0, heat_source="reactor")
+    sys.path.insert(0, os.path.join(R.REF_ROOT, "data"))
+    with R.quiet():
+        from plant_data_logger import PlantDataLogger
+    logger = PlantDataLogger(str(tmp_path / "run"))
+    states, times = [], []
+    rng = np.random.RandomState(3)
+    for t in range(12):
+        rp.step(int(rng.choice([0, 1, 8, 9, 10])), 0.7, (0.0, 0.0, 1.0, 1.0, 1.0))
+        logger.log_timestep(rp.sim)
+        states.append(R.extract_state(rp.sim))
+        times.append(float(rp.sim.time))
+    ref_rows = list(csv.reader(open(logger.csv_path, newline="")))
+    stamps = [ref_rows[1 + 22 * i][0] for i in range(12)]
+    out = tmp_path / "ours.csv"
+    n = E.export_long_format(str(out), stamps, states, times)
+    got_rows = list(csv.reader(open(out, newline="")))
+    assert n == 12 * 22 and len(got_rows) == len(ref_rows) == 1 + 12 * 22
+    assert got_rows == ref_rows
