@@ -971,7 +971,9 @@ static const char* const kMaintActionNames[MA_N_ACTIONS] = {
     "moisture_separator_maintenance", "scale_removal", "eddy_current_testing", "secondary_side_cleaning",
     "routine_maintenance", "tube_interior_scale_cleaning", "primary_scale_cleaning", "cleaning", "blade_replacement",
     "overhaul", "condenser_tube_cleaning", "condenser_tube_plugging", "condenser_chemical_cleaning", "vacuum_system_test",
-    "vacuum_leak_detection", "other"};
+    "vacuum_leak_detection", "turbine_performance_test", "turbine_system_optimization", "turbine_protection_test",
+    "thermal_stress_analysis", "system_coordination_maintenance", "system_steam_quality_maintenance",
+    "load_balancing_maintenance", "other"};
 
 int nps_n_maintenance_actions(void) { return MA_N_ACTIONS; }
 const char* nps_maintenance_action_name(int action) {

@@ -45,6 +45,8 @@ enum MaintAction : int {
     MA_STAGE_CLEANING, MA_BLADE_REPLACEMENT, MA_STAGE_OVERHAUL,
     MA_CONDENSER_TUBE_CLEANING, MA_CONDENSER_TUBE_PLUGGING, MA_CONDENSER_CHEMICAL_CLEANING, MA_VACUUM_SYSTEM_TEST,
     MA_VACUUM_LEAK_DETECTION,
+    MA_TURBINE_PERFORMANCE_TEST, MA_TURBINE_SYSTEM_OPTIMIZATION, MA_TURBINE_PROTECTION_TEST, MA_THERMAL_STRESS_ANALYSIS,
+    MA_SYSTEM_COORDINATION_MAINTENANCE, MA_SYSTEM_STEAM_QUALITY_MAINTENANCE, MA_LOAD_BALANCING_MAINTENANCE,
     MA_OTHER,              // any action name without a handler on the target: no state change
     MA_N_ACTIONS
 };
@@ -314,6 +316,75 @@ NPS_HD int maintain_condenser(CondenserState& C, const PlantParams& p, int actio
     }
 }
 
+// EnhancedTurbinePhysics.perform_maintenance: turbine/enhanced_physics.py:1055-1267 (Python min/max argument order kept)
+NPS_HD int maintain_turbine(TurbineState& T, int action) {
+    switch (action) {
+        case MA_TURBINE_PERFORMANCE_TEST:        // :1066-1101
+            T.overall_efficiency = py_min(0.34, T.overall_efficiency + 0.02);
+            T.performance_factor = py_min(1.0, T.performance_factor + 0.05);
+            return MS_SUCCESS;
+        case MA_TURBINE_SYSTEM_OPTIMIZATION:     // :1103-1135
+            T.performance_factor = py_min(1.0, T.performance_factor + 0.08);
+            T.ss_system_efficiency = py_min(1.0, T.ss_system_efficiency + 0.03);
+            for (int b = 0; b < 4; ++b) T.bearing[b].efficiency_factor = py_min(1.0, T.bearing[b].efficiency_factor + 0.02);
+            T.lub.lubrication_effectiveness = py_min(1.0, T.lub.lubrication_effectiveness + 0.05);
+            return MS_SUCCESS;
+        case MA_TURBINE_PROTECTION_TEST:         // :1137-1167; reset_protection_system :473-479
+            if (is_true(T.prot_trip_active)) {
+                T.prot_trip_active = 0.0; T.prot_trip_reasons = 0.0;
+                T.prot_timer_overspeed = 0.0; T.prot_timer_vibration = 0.0; T.prot_timer_bearing_temp = 0.0;
+            }
+            T.availability_factor = py_min(1.0, T.availability_factor + 0.03);
+            return MS_SUCCESS;
+        case MA_THERMAL_STRESS_ANALYSIS: {       // :1169-1199
+            const double original = T.th_max_thermal_stress;
+            const double reduction = py_min(100e6, original * 0.1);
+            T.th_max_thermal_stress -= reduction;
+            T.th_thermal_shock_risk *= 0.8;
+            return MS_SUCCESS;
+        }
+        case MA_VIBRATION_ANALYSIS: {            // :1201-1236; last_update_results['vibration_displacement'] = total displacement
+            const double current = T.vib_displacement_x;
+            const double reduction = py_min(5.0, current * 0.3);
+            for (int b = 0; b < 4; ++b) T.bearing[b].vibration_displacement = py_max(0.0, T.bearing[b].vibration_displacement - reduction);
+            T.thermal_bow *= 0.7;                // bearing.vibration_velocity (*= 0.8) is not read by the step path
+            return MS_SUCCESS;
+        }
+        case MA_ROUTINE_MAINTENANCE:             // :1238-1257
+            T.performance_factor = py_min(1.0, T.performance_factor + 0.01);
+            T.overall_efficiency = py_min(0.34, T.overall_efficiency + 0.002);
+            for (int b = 0; b < 4; ++b) {
+                T.bearing[b].efficiency_factor = py_min(1.0, T.bearing[b].efficiency_factor + 0.005);
+                T.bearing[b].metal_temperature = py_max(80.0, T.bearing[b].metal_temperature - 0.5);
+            }
+            return MS_SUCCESS;
+        default: return MS_FAILED;               // :1259-1266 (unknown maintenance type)
+    }
+}
+
+// EnhancedSteamGeneratorPhysics.perform_maintenance: steam_generator/enhanced_physics.py:1062-1190.  Its own
+// performance_factor / load_balance_factor start at 1.0 and are only ever raised towards 1.0 on the step path
+// (the chemistry update that lowers them, :905-917, is never called: SURVEY a16), so they are not carried.
+NPS_HD int maintain_sg_system(SGSystemState& S, int action) {
+    switch (action) {
+        case MA_SYSTEM_COORDINATION_MAINTENANCE: S.system_availability = 1.0; return MS_SUCCESS;   // :1073-1088
+        case MA_SYSTEM_STEAM_QUALITY_MAINTENANCE:                                                    // :1090-1116
+            for (int i = 0; i < 3; ++i)
+                if (S.sg[i].steam_quality < 0.99) maintain_sg(S.sg[i], MA_MOISTURE_SEPARATOR_MAINTENANCE);
+            return MS_SUCCESS;
+        case MA_LOAD_BALANCING_MAINTENANCE: {    // :1118-1154: TSP chemical cleaning on the first two degraded SGs
+            int done = 0;
+            for (int i = 0; i < 3 && done < 2; ++i)
+                if (S.sg[i].tsp_heat_transfer_degradation > 0.05) { maintain_sg(S.sg[i], MA_TSP_CHEMICAL_CLEANING); ++done; }
+            return MS_SUCCESS;
+        }
+        case MA_ROUTINE_MAINTENANCE:             // :1156-1174
+            for (int i = 0; i < 3; ++i) maintain_sg(S.sg[i], MA_ROUTINE_MAINTENANCE);
+            return MS_SUCCESS;
+        default: return MS_FAILED;               // :1176-1190: delegation needs an sg_index keyword nobody passes
+    }
+}
+
 // One request: (target, action, arg).  Targets without a perform_maintenance restatement report
 // MS_UNSUPPORTED_TARGET so the host can refuse instead of silently diverging.
 NPS_HD int maintenance_apply_target(PlantState& st, const PlantParams& p, int target, int action, int arg) {
@@ -321,7 +392,11 @@ NPS_HD int maintenance_apply_target(PlantState& st, const PlantParams& p, int ta
     if (target >= MT_SG0 && target < MT_SG0 + 3) return maintain_sg(st.sgs.sg[target - MT_SG0], action);
     if (target >= MT_STAGE0 && target < MT_STAGE0 + 14) return maintain_stage(st.turb.stage[target - MT_STAGE0], p, target - MT_STAGE0, action);
     if (target == MT_CONDENSER) return maintain_condenser(st.cond, p, action);
-    if (target == MT_TURBINE && action == MA_OTHER) return MS_FAILED;   // enhanced_physics.py:1259-1266 (unknown type)
+    if (target == MT_TURBINE) return maintain_turbine(st.turb, action);
+    if (target == MT_SG_SYSTEM) return maintain_sg_system(st.sgs, action);
+    // FEE-001: FeedwaterPumpSystem has no perform_maintenance method (the one in pump_system.py:750 belongs to
+    // FeedwaterPump), so _perform_maintenance_action reports "does not support maintenance": success False, no change
+    if (target == MT_FW_SYSTEM) return MS_FAILED;
     return MS_UNSUPPORTED_TARGET;
 }
 

@@ -45,6 +45,14 @@ EFFECT_CASES = [
     ("SECONDARY-COMP-001-COND", "condenser_tube_cleaning", None), ("SECONDARY-COMP-001-COND", "condenser_tube_plugging", None),
     ("SECONDARY-COMP-001-COND", "condenser_chemical_cleaning", None), ("SECONDARY-COMP-001-COND", "vacuum_system_test", None),
     ("SECONDARY-COMP-001-COND", "vacuum_leak_detection", None), ("SECONDARY-COMP-001-COND", "condenser_performance_test", None),
+    # system-level targets: EnhancedTurbinePhysics, EnhancedSteamGeneratorPhysics, FeedwaterPumpSystem (no method at all)
+    ("SECONDARY-COMP-001-TURB", "turbine_performance_test", None), ("SECONDARY-COMP-001-TURB", "turbine_system_optimization", None),
+    ("SECONDARY-COMP-001-TURB", "turbine_protection_test", None), ("SECONDARY-COMP-001-TURB", "thermal_stress_analysis", None),
+    ("SECONDARY-COMP-001-TURB", "vibration_analysis", None), ("SECONDARY-COMP-001-TURB", "routine_maintenance", None),
+    ("SECONDARY-COMP-001-SG", "system_coordination_maintenance", None), ("SECONDARY-COMP-001-SG", "system_steam_quality_maintenance", None),
+    ("SECONDARY-COMP-001-SG", "load_balancing_maintenance", None), ("SECONDARY-COMP-001-SG", "routine_maintenance", None),
+    ("SECONDARY-COMP-001-SG", "tsp_chemical_cleaning", None),
+    ("FEE-001", "oil_change", None), ("FEE-001", "routine_maintenance", None),
 ]
 
 
@@ -69,7 +77,7 @@ def effects():
         plants[ic] = runner_style_plant(ic)[0]
     rng = np.random.RandomState(11)
     for i, (cid, action, sub) in enumerate(EFFECT_CASES):
-        rp = plants["oil_change"] if (cid.startswith("FWP") or "COND" in cid or cid[:2] in ("HP", "LP") or "TURB" in cid) \
+        rp = plants["oil_change"] if (cid.startswith("FWP") or "COND" in cid or cid[:2] in ("HP", "LP") or "TURB" in cid or cid == "FEE-001") \
             else plants["tsp_chemical_cleaning"]
         sim = rp.sim
         for _ in range(2):
@@ -78,6 +86,10 @@ def effects():
         ms = sim.maintenance_system
         inst = sim.state_manager.get_registered_instance_info()[cid]["instance"]
         wo = types.SimpleNamespace(metadata={"extracted_component_id": sub} if sub else {})
+        if (cid, action) == ("SECONDARY-COMP-001-TURB", "turbine_protection_test"):     # a latched trip for the test to reset
+            pr = sim.secondary_physics.turbine.protection_system
+            pr.trip_active, pr.trip_reasons = True, ["Low Vacuum"]
+            pr.trip_timers["vibration"] = 1.5
         b = R.extract_state(sim)
         with R.quiet():
             res = ms._perform_maintenance_action(inst, action, wo)
