@@ -254,6 +254,7 @@ def main():
     ap.add_argument("--substeps", type=int, default=SUBSTEPS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="value + full_step only (tuning runs)")
+    ap.add_argument("--no-small", action="store_true", help="skip the small-batch / strong-scaling arm")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -419,19 +420,27 @@ def main():
         torch.cuda.empty_cache()
 
     # -------------------------------------------------------------- strong scaling / small batches
-    def sub_batch(n_sub, count):
+    def sub_batch(n_sub, count, shape=0):
         sub = ShardedBatchedSimulator(world * n_sub, s0, params, rank=rank, world=world, device=str(dev)).sim
+        sub.set_small_batch_shape(shape)
         sets = (acts_d[:, :, :n_sub].contiguous(), mags_d[:, :, :n_sub].contiguous(), noise_d[:, :, :, :n_sub].contiguous())
         ms, _ = timed_launches(sub, count, sets=sets, warm=3)
         return world * n_sub * ksub * count / (ms * 1e-3)
-    if world > 1:
+    if args.no_small:
+        pass
+    elif world > 1:
         extra["strong_65536"] = {"value": sub_batch(PLANTS_PER_GPU // world, max(3, K // 2)), "unit": UNIT,
+                                 "one_thread_per_plant": sub_batch(PLANTS_PER_GPU // world, max(3, K // 2), 1) if PLANTS_PER_GPU // world < 33152 else None,
                                  "plants_per_gpu": PLANTS_PER_GPU // world,
                                  "note": "the 65,536-plant batch of the north star split over the GPUs (strong scaling)"}
     else:
         extra["small_batch"] = {"unit": UNIT, "plants_4096": sub_batch(4096, 3), "plants_8192": sub_batch(8192, 3),
                                 "plants_16384": sub_batch(16384, 3),
-                                "note": "config #2 / strong-scaled config #3 share per GPU / config #4 sizes on one GPU"}
+                                "one_thread_per_plant": {"plants_4096": sub_batch(4096, 3, 1), "plants_8192": sub_batch(8192, 3, 1),
+                                                         "plants_16384": sub_batch(16384, 3, 1)},
+                                "note": "config #2 / strong-scaled config #3 share per GPU / config #4 sizes on one GPU; default "
+                                        "launch shape below 33 K plants = two threads per plant (source / sink halves pipelined "
+                                        "by one substep), bit-identical to one thread per plant"}
 
 
     # ------------------------------------------------------------------ trajectory summaries: the only collective

@@ -116,6 +116,14 @@ int nps_device_rng_draws(uint64_t seed, uint64_t plant, uint64_t step, double* o
  * specialisations, csrc/plant/fastpow.h for positive finite bases, libdevice pow otherwise), device arrays. */
 int nps_selftest_pow(const double* d_x, const double* d_y, double* d_out, int64_t n, void* cuda_stream);
 
+/* Launch shape of nps_step for batches below ~33 K plants (above, one thread per plant fills the GPU):
+ *   0 (default)  two threads per plant — one advances primary side / feedwater / steam generators / chemistry, the other
+ *                the turbine and condenser one substep behind it (they are pure sinks of the step's dataflow), so the
+ *                dependency chain per substep is the longer half instead of the sum;
+ *   1            one thread per plant.
+ * Both produce bit-identical state; the environment variable NPS_SMALL_SHAPE=1 selects shape 1 at nps_create. */
+int nps_set_small_batch_shape(nps_handle* h, int shape);
+
 /* Measurement hook: achieved FP64 FMA throughput of `device` (8 independent DFMA chains per thread, 2 048 threads per
  * SM, best of 4 timed launches of `iters` iterations; synchronous).  The FP64 side of the roofline in bench.py divides by
  * this number instead of a datasheet figure. */

@@ -51,6 +51,7 @@ def lib() -> ctypes.CDLL:
     L.nps_device_rng_draws.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, c_void_p]
     L.nps_selftest_pow.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]
     L.nps_measure_fp64_peak.argtypes = [c_int, c_int, c_void_p, c_void_p]
+    L.nps_set_small_batch_shape.argtypes = [c_void_p, c_int]
     L.nps_pipe_depth.argtypes = []
     L.nps_pipe_depth.restype = c_int
     L.nps_observe.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
@@ -78,7 +79,7 @@ def check(rc: int) -> None:
 EXPORTED_SYMBOLS = [
     "nps_abi_version", "nps_last_error", "nps_n_state", "nps_n_params", "nps_field_name", "nps_param_name",
     "nps_create", "nps_destroy", "nps_n_plants", "nps_set_params", "nps_step", "nps_step_monitored", "nps_step_host", "nps_step_host_async",
-    "nps_wait", "nps_pipe_depth", "nps_measure_fp64_peak", "nps_set_device_rng", "nps_device_rng_draws", "nps_selftest_pow", "nps_observe",
+    "nps_wait", "nps_pipe_depth", "nps_set_small_batch_shape", "nps_measure_fp64_peak", "nps_set_device_rng", "nps_device_rng_draws", "nps_selftest_pow", "nps_observe",
     "nps_set_thresholds", "nps_check_thresholds", "nps_check_thresholds_events", "nps_set_logged_fields", "nps_log_row", "nps_read_fields",
     "nps_n_maintenance_actions", "nps_maintenance_action_name", "nps_apply_maintenance",
 ]

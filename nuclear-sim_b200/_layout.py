@@ -19,6 +19,9 @@ _STRUCT = re.compile(r"^\s*struct\s+(\w+)\s*\{")
 _CONST = re.compile(r"^\s*(?:static\s+)?constexpr\s+int\s+(\w+)\s*=\s*(\d+)\s*;")
 
 
+_DISCRETE: Dict[Tuple[str, str], bool] = {}    # (struct, member) carries the `// @discrete` annotation
+
+
 def _parse(path: str) -> Tuple[Dict[str, list], Dict[str, int]]:
     structs: Dict[str, list] = {}
     consts: Dict[str, int] = {}
@@ -45,6 +48,7 @@ def _parse(path: str) -> Tuple[Dict[str, list], Dict[str, int]]:
                 typ, name, dims = m.groups()
                 shape = [consts[d] if d in consts else int(d) for d in re.findall(r"\[(\w+)\]", dims)]
                 structs[cur].append((typ, name, shape))
+                _DISCRETE[(cur, name)] = "@discrete" in raw.split("//", 1)[1] if "//" in raw else False
     return structs, consts
 
 
@@ -72,6 +76,29 @@ def field_names(struct: str = "PlantState") -> Tuple[str, ...]:
 @lru_cache(maxsize=None)
 def field_index(struct: str = "PlantState") -> Dict[str, int]:
     return {n: i for i, n in enumerate(field_names(struct))}
+
+
+@lru_cache(maxsize=None)
+def discrete_field_names(struct: str = "PlantState") -> Tuple[str, ...]:
+    """Fields that hold flags / enums / counters / latches (exact small integers stored as doubles): the members
+    annotated `// @discrete` in state.h.  The parity tests compare these bit for bit, everything else to tolerance."""
+    structs, _ = _parse(STATE_H)
+    out: List[str] = []
+
+    def walk(typ: str, prefix: str) -> None:
+        for mtyp, name, shape in structs[typ]:
+            idxs = [""]
+            for d in shape:
+                idxs = [f"{p}[{i}]" for p in idxs for i in range(d)]
+            for ix in idxs:
+                full = f"{prefix}{name}{ix}"
+                if mtyp == "double":
+                    if _DISCRETE.get((typ, name), False):
+                        out.append(full)
+                else:
+                    walk(mtyp, full + ".")
+    walk(struct, "")
+    return tuple(out)
 
 
 def struct_range(member_path: str, struct: str = "PlantState") -> Tuple[int, int]:

@@ -280,6 +280,11 @@ class BatchedNuclearPlantSimulator:
         g = self._mon
         return {w: g["watch_step"][i] for i, w in enumerate(g["watch"])}
 
+    def set_small_batch_shape(self, shape: int) -> None:
+        """Launch shape below ~33 K plants: 0 two threads per plant (source / sink halves pipelined by one substep,
+        default), 1 one thread per plant.  Bit-identical results (tests/test_gpu_parity.py)."""
+        _clib.check(self.L.nps_set_small_batch_shape(self._h, int(shape)))
+
     def set_device_rng(self, seed: Optional[int], plant_offset: int = 0, first_step: int = 0) -> None:
         """Device-side noise (nps_set_device_rng): with a seed, step(noise=None) draws every plant-step's five random
         numbers on the GPU (Philox4x32-10, counter = (plant_offset + plant, step)); None switches it off again.

@@ -90,7 +90,8 @@ struct nps_handle {
     cudaStream_t copy_stream = nullptr, out_stream = nullptr;   // host->device and device->host on separate streams
     int pipe_k = 0; int64_t pipe_count = 0;
     RngConfig rng = {0, 0, 0, 0, 0};
-    int n_sms = 148; bool log_row_tile_only = false;   // NPS_LOG_ROW_TILE=1 forces the shared-memory tile kernel
+    int n_sms = 148; bool log_row_tile_only = false;
+    int small_shape = 0;   // batches below kLargeBatch: 0 split kernel (two threads per plant), 1 one thread per plant (NPS_SMALL_SHAPE=1)   // NPS_LOG_ROW_TILE=1 forces the shared-memory tile kernel
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -146,9 +147,26 @@ __device__ __forceinline__ double derived_from_state(const PlantState& st, int c
 }
 
 
+// Which half of a split step (plant_step_source / plant_step_sink, csrc/plant/plant_step.h) owns state field f: the sink
+// half owns the turbine and condenser records, the six SecondaryState fields, sim.last_load_factor and the heat-flow
+// report fields it writes; the source half owns everything else.  A half's frame holds valid values for its own fields only.
+#define NPS_FIELD_OF(member) ((int)(offsetof(PlantState, member) / sizeof(double)))
+__device__ __forceinline__ bool sink_owns(int f) {
+    constexpr int lo = NPS_FIELD_OF(turb), hi = NPS_FIELD_OF(ph);     // [turb, cond] are adjacent, ph follows
+    static_assert(NPS_FIELD_OF(cond) > NPS_FIELD_OF(turb) && NPS_FIELD_OF(ph) > NPS_FIELD_OF(cond), "PlantState order changed");
+    if (f >= lo && f < hi) return true;
+    return f == NPS_FIELD_OF(sec.total_system_heat_rejection) || f == NPS_FIELD_OF(sec.power_reduction_factor) ||
+           f == NPS_FIELD_OF(sec.electrical_power_output) || f == NPS_FIELD_OF(sec.thermal_efficiency) ||
+           f == NPS_FIELD_OF(sec.heat_rate_kj_kwh) || f == NPS_FIELD_OF(sec.condenser_pressure) ||
+           f == NPS_FIELD_OF(sim.last_load_factor) ||
+           (f >= NPS_FIELD_OF(rep.hf_steam_enthalpy_flow) && f <= NPS_FIELD_OF(rep.hf_energy_balance_percent));
+}
+
+// role: -1 whole plant (one thread per plant), 0 source half, 1 sink half (evaluates only the rows / watched fields it owns;
+// `now` is the plant clock after the step, which a sink half gets from its source half)
 __device__ __noinline__ void monitor_substep(const PlantState& st, const MonitorArgs& mon, const Threshold* rows,
                                              int64_t n, int64_t p, int k, bool last, unsigned warp_mask, unsigned step_status,
-                                             unsigned& seen_watch) {
+                                             unsigned& seen_watch, int role = -1, double now_in = 0.0) {
     const double* sv = reinterpret_cast<const double*>(&st);
     const int32_t step = (int32_t)(mon.step0 + k);
     if (step_status) {
@@ -157,13 +175,14 @@ __device__ __noinline__ void monitor_substep(const PlantState& st, const Monitor
         if ((step_status & kStatusNanReset) && mon.first_nan_reset_step && mon.first_nan_reset_step[p] < 0) mon.first_nan_reset_step[p] = step;
     }
     for (int w = 0; w < mon.n_watch; ++w) {
+        if (role >= 0 && sink_owns(mon.watch_fields[w]) != (role == 1)) continue;
         if (!((seen_watch >> w) & 1u) && sv[mon.watch_fields[w]] != 0.0) {
             mon.watch_step[(int64_t)w * n + p] = step;
             seen_watch |= 1u << w;
         }
     }
     if (mon.last_fired && !(last && mon.skip_last_check)) {
-        const double now = st.sim.time_minutes;
+        const double now = (role == 1) ? now_in : st.sim.time_minutes;
         const unsigned lane = threadIdx.x & 31u;
         // rows in groups of kMonChunk: the group's values are independent loads issued back to back (they are first
         // touches of this substep's freshly written state, i.e. cache misses), then compared; the warp votes ONCE per
@@ -174,14 +193,15 @@ __device__ __noinline__ void monitor_substep(const PlantState& st, const Monitor
             unsigned hit = 0;
 #pragma unroll
             for (int j = 0; j < kMonChunk; ++j) {
+                v[j] = 0.0;
                 if (j0 + j < mon.n_live) {
                     const int f = rows[j0 + j].field;
-                    v[j] = (f >= 0) ? sv[f] : derived_from_state(st, f);
+                    const bool mine = role < 0 || ((f >= 0 && sink_owns(f)) == (role == 1));   // derived rows: source half
+                    if (mine) {
+                        v[j] = (f >= 0) ? sv[f] : derived_from_state(st, f);
+                        if (threshold_compare(rows[j0 + j].cmp, v[j], rows[j0 + j].value)) hit |= 1u << j;
+                    }
                 }
-            }
-#pragma unroll
-            for (int j = 0; j < kMonChunk; ++j) {
-                if (j0 + j < mon.n_live && threshold_compare(rows[j0 + j].cmp, v[j], rows[j0 + j].value)) hit |= 1u << j;
             }
             if (!__ballot_sync(warp_mask, hit != 0)) continue;
 #pragma unroll
@@ -268,6 +288,123 @@ NPS_PRAGMA_UNROLL(NPS_COPY_UNROLL)
     }
     if (a.reward) a.reward[p] = plant_reward(st, prm);
     if (a.done) a.done[p] = scrammed ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// split launch shape for small batches: TWO threads per plant, pipelined by one substep
+// ------------------------------------------------------------------------------------------------
+// Below ~33 K plants a B200 has fewer than 8 warps per SM and the time of a launch is ONE warp's dependency chain
+// (DESIGN.md 5).  The turbine + condenser are pure sinks of a step's dataflow (csrc/plant/secondary.h SecHandoff), so a
+// plant is advanced by a source thread (primary, feedwater, steam generators, chemistry, clock) and a sink thread
+// (turbine, condenser, energy bookkeeping): while the source half computes substep k, the sink half computes substep
+// k - 1 from the handoff the source left in shared memory.  Same functions, same arithmetic, same order inside each
+// half -> bit-identical state; the chain per substep drops from source + sink to max(source, sink).
+// Block = 64 threads = 32 plants: warp 0 source halves, warp 1 sink halves, one __syncthreads per substep.
+constexpr int kSplitPlants = 32;
+struct SplitShared {
+    SecHandoff hand[2][kSplitPlants];
+    double now[2][kSplitPlants];            // plant clock after the substep (the sink half stamps its events with it)
+    double a2b[2][6][kSplitPlants];         // power level, fuel temperature, coolant pressure, scram status, load demand, SG pressure: reward
+    double b2a[3][kSplitPlants];            // electrical output, thermal efficiency, condenser pressure: final observation / reward
+};
+
+__global__ void __launch_bounds__(2 * kSplitPlants, 1)
+nps_step_split_kernel(const __grid_constant__ PlantParams prm, const __grid_constant__ StepArgs a) {
+    __shared__ Threshold s_rows[kMaxSharedRows];
+    __shared__ SplitShared sh;
+    const MonitorArgs& mon = a.mon;
+    const Threshold* rows = mon.live;
+    if (mon.enabled && mon.n_live > 0 && mon.n_live <= kMaxSharedRows) {
+        for (int j = threadIdx.x; j < mon.n_live; j += 2 * kSplitPlants) s_rows[j] = mon.live[j];
+        rows = s_rows;
+    }
+    __syncthreads();
+    const int role = threadIdx.x >> 5;                 // 0 source half, 1 sink half
+    const int lane = threadIdx.x & 31;
+    const int64_t n = a.n;
+    const int64_t p = (int64_t)blockIdx.x * kSplitPlants + lane;
+    const bool valid = p < n;
+    const unsigned warp_mask = __ballot_sync(0xffffffffu, valid);
+    double* __restrict__ slab = a.slab;
+    PlantState st;
+    double* sv = reinterpret_cast<double*>(&st);
+    if (valid) {
+NPS_PRAGMA_UNROLL(NPS_COPY_UNROLL)
+        for (int f = 0; f < kNState; ++f) if (sink_owns(f) == (role == 1)) sv[f] = slab[(int64_t)f * n + p];
+    }
+    bool scrammed = false;
+    unsigned seen_watch = 0;
+    if (mon.enabled && valid)
+        for (int w = 0; w < mon.n_watch; ++w) if (mon.watch_step[(int64_t)w * n + p] >= 0) seen_watch |= 1u << w;
+    const int K = a.k_substeps;
+    for (int k = 0; k <= K; ++k) {
+        if (role == 0 && k < K && valid) {
+            StepInput in;
+            in.action = a.action ? (int)a.action[(int64_t)k * n + p] : (int)ACT_NO_ACTION;
+            in.magnitude = a.magnitude ? a.magnitude[(int64_t)k * n + p] : 1.0;
+            if (a.noise) {
+                const double* z = a.noise + (int64_t)k * NPS_NOISE_PER_STEP * n + p;
+                in.z_heat = z[0]; in.z_ph = z[n]; in.u_ph[0] = z[2 * n]; in.u_ph[1] = z[3 * n]; in.u_ph[2] = z[4 * n];
+            } else if (a.rng.enabled) {
+                const StepDraws d = plant_step_draws(a.rng.seed, a.rng.plant_offset + (uint64_t)p, a.rng.step0 + (uint64_t)k);
+                in.z_heat = d.z_heat; in.z_ph = d.z_ph; in.u_ph[0] = d.u_ph[0]; in.u_ph[1] = d.u_ph[1]; in.u_ph[2] = d.u_ph[2];
+            } else {
+                in.z_heat = 0.0; in.z_ph = 0.0; in.u_ph[0] = 1.0; in.u_ph[1] = 1.0; in.u_ph[2] = 1.0;
+            }
+            in.power_setpoint = a.setpoint ? a.setpoint[(int64_t)k * n + p] : NAN;
+            in.emit_outputs = (k == K - 1);
+            SecHandoff h;
+            h.emit_outputs = in.emit_outputs;
+            plant_step_source(st, prm, in, h);
+            sh.hand[k & 1][lane] = h;
+            sh.now[k & 1][lane] = st.sim.time_minutes;
+            const bool scram_now = is_true(st.pri.scram_activated);
+            scrammed |= scram_now;
+            if (mon.enabled) {
+                monitor_substep(st, mon, rows, n, p, k, k == K - 1, warp_mask, in.status, seen_watch, 0);
+                if (mon.done_k) mon.done_k[(int64_t)k * n + p] = scram_now ? 1 : 0;
+                if (mon.reward_k) {
+                    sh.a2b[k & 1][0][lane] = st.pri.power_level; sh.a2b[k & 1][1][lane] = st.pri.fuel_temperature;
+                    sh.a2b[k & 1][2][lane] = st.pri.coolant_pressure; sh.a2b[k & 1][3][lane] = st.pri.scram_status;
+                    sh.a2b[k & 1][4][lane] = st.sim.load_demand; sh.a2b[k & 1][5][lane] = st.sec.sg_avg_pressure;
+                }
+            }
+        } else if (role == 1 && k >= 1 && valid) {
+            const int j = k - 1, b = j & 1;
+            const SecHandoff h = sh.hand[b][lane];
+            plant_step_sink(st, prm, h);
+            if (mon.enabled) {
+                monitor_substep(st, mon, rows, n, p, j, j == K - 1, warp_mask, 0u, seen_watch, 1, sh.now[b][lane]);
+                if (mon.reward_k) {   // calculate_reward needs both halves: the six source-side values travel with the handoff
+                    st.pri.power_level = sh.a2b[b][0][lane]; st.pri.fuel_temperature = sh.a2b[b][1][lane];
+                    st.pri.coolant_pressure = sh.a2b[b][2][lane]; st.pri.scram_status = sh.a2b[b][3][lane];
+                    st.sim.load_demand = sh.a2b[b][4][lane]; st.sec.sg_avg_pressure = sh.a2b[b][5][lane];
+                    mon.reward_k[(int64_t)j * n + p] = plant_reward(st, prm);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (valid) {
+NPS_PRAGMA_UNROLL(NPS_COPY_UNROLL)
+        for (int f = 0; f < kNState; ++f) if (sink_owns(f) == (role == 1)) slab[(int64_t)f * n + p] = sv[f];
+    }
+    if (role == 1 && valid) {
+        sh.b2a[0][lane] = st.sec.electrical_power_output; sh.b2a[1][lane] = st.sec.thermal_efficiency;
+        sh.b2a[2][lane] = st.sec.condenser_pressure;
+    }
+    __syncthreads();
+    if (role == 0 && valid) {
+        st.sec.electrical_power_output = sh.b2a[0][lane]; st.sec.thermal_efficiency = sh.b2a[1][lane];
+        st.sec.condenser_pressure = sh.b2a[2][lane];
+        if (a.obs) {
+            struct ObsOut { double* o; int64_t n; int64_t p; struct Ref { double* a; NPS_HD void operator=(double v) { *a = v; } };
+                            __device__ Ref operator[](int i) { return Ref{o + (int64_t)i * n + p}; } } out{a.obs, n, p};
+            plant_observe(st, prm, out);
+        }
+        if (a.reward) a.reward[p] = plant_reward(st, prm);
+        if (a.done) a.done[p] = scrammed ? 1 : 0;
+    }
 }
 
 template <class T>
@@ -572,6 +709,7 @@ int nps_create(int64_t n_plants, int device, nps_handle** out) {
     std::memset(&h->params, 0, sizeof(PlantParams));
     cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, device);
     { const char* e = getenv("NPS_LOG_ROW_TILE"); h->log_row_tile_only = e && e[0] == '1'; }
+    { const char* e = getenv("NPS_SMALL_SHAPE"); h->small_shape = (e && e[0] == '1') ? 1 : 0; }
     NPS_CUDA(cudaFuncSetAttribute(nps_log_row_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLogStages * kLogStageBytes));
     // the step kernel keeps one PlantState per thread in local memory
 #if defined(NPS_STEP_BLOCK)
@@ -581,6 +719,7 @@ int nps_create(int64_t n_plants, int device, nps_handle** out) {
     // one-warp blocks: several of them share an SM, each with its 4 KB threshold-row stage; PreferL1 alone would leave
     // shared memory for a single block per SM (measured: 8 192 plants ran as two waves)
     NPS_CUDA(cudaFuncSetAttribute(nps_step_kernel<32, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 25));
+    NPS_CUDA(cudaFuncSetAttribute(nps_step_split_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 40));
 #endif
     *out = h;
     return 0;
@@ -620,7 +759,8 @@ static int launch_step(nps_handle* h, const StepArgs& a, cudaStream_t s) {
     nps_step_kernel<NPS_STEP_BLOCK, NPS_STEP_MINBLOCKS><<<(int)((h->n + NPS_STEP_BLOCK - 1) / NPS_STEP_BLOCK), NPS_STEP_BLOCK, 0, s>>>(h->params, a);
 #else
     if (h->n >= kLargeBatch) nps_step_kernel<448, 1><<<(int)((h->n + 447) / 448), 448, 0, s>>>(h->params, a);
-    else nps_step_kernel<32, 1><<<(int)((h->n + 31) / 32), 32, 0, s>>>(h->params, a);
+    else if (h->small_shape == 1) nps_step_kernel<32, 1><<<(int)((h->n + 31) / 32), 32, 0, s>>>(h->params, a);
+    else nps_step_split_kernel<<<(int)((h->n + kSplitPlants - 1) / kSplitPlants), 2 * kSplitPlants, 0, s>>>(h->params, a);
 #endif
     NPS_CUDA(cudaGetLastError());
     return 0;
@@ -822,6 +962,12 @@ int nps_measure_fp64_peak(int device, int iters, double* out_tflops, double* out
     const double flops = 2.0 * kFmaChains * (double)iters * blocks * threads;
     *out_tflops = flops / (best * 1e-3) / 1e12;
     if (out_ms) *out_ms = best;
+    return 0;
+}
+
+int nps_set_small_batch_shape(nps_handle* h, int shape) {
+    if (!h || (shape != 0 && shape != 1)) return fail("nps_set_small_batch_shape: shape is 0 (two threads per plant) or 1 (one thread per plant)");
+    h->small_shape = shape;
     return 0;
 }
 

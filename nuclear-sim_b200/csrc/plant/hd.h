@@ -164,7 +164,10 @@ NPS_HD double nps_pow_general_memo(double x, double y, PowMemo& m) {
     return pow(x, y);
 }
 NPS_HD double py_pow_memo(double x, double y, PowMemo& m) {
-#if defined(__CUDA_ARCH__) && !defined(NPS_GENERIC_POW)
+#if defined(NPS_NO_POW_MEMO)
+    (void)m;
+    return py_pow(x, y);
+#elif defined(__CUDA_ARCH__) && !defined(NPS_GENERIC_POW)
     if (y == 2.0) return x * x;
     if (y == 1.0) return x;
     if (x == 1.0) return 1.0;

@@ -47,10 +47,10 @@ NPS_HD void plant_primary_to_secondary(const PlantState& st, PrimaryConditions& 
 }
 
 // _apply_secondary_to_primary_feedback: sim.py:429-498
+// (the load-factor line, :446/:492, needs the turbine's electrical output: secondary_update_sink writes it)
 NPS_HD void plant_secondary_to_primary(PlantState& st) {
     double steam_demand = st.sec.total_steam_flow;
     double hrf = steam_demand / 1665.0;
-    double load_factor = st.sec.electrical_power_output / 1100.0;
     bool fw_avail = is_true(st.fw.system_availability);
     double fw_flow = st.fw.total_flow_rate;
     double n_pumps = st.fw.n_running_prev;
@@ -63,9 +63,27 @@ NPS_HD void plant_secondary_to_primary(PlantState& st) {
     st.pri.feedwater_num_running_pumps = n_pumps;
     st.sim.has_last_heat_removal_factor = 1.0;
     st.sim.last_heat_removal_factor = hrf;
-    st.sim.last_load_factor = load_factor;
     st.sim.last_feedwater_flow_factor = fw_flow / 1665.0;
     st.sim.last_pump_reliability_factor = py_min(1.0, n_pumps / 3.0);
+}
+
+// The half of a step that owns primary side, feedwater, steam generators, chemistry and the clock; hands the turbine /
+// condenser half what it needs in `h` (secondary disabled: h is left untouched and there is no other half).
+NPS_HD void plant_step_source(PlantState& st, const PlantParams& p, const StepInput& in, SecHandoff& h) {
+    const double dt = p.dt;
+    primary_update(st.pri, p, in, dt);
+    if (is_true(p.enable_secondary)) {
+        PrimaryConditions pc;
+        plant_primary_to_secondary(st, pc);
+        st.sim.load_demand = st.pri.power_level;   // sim.py:161 (percent; overrides the caller)
+        secondary_update_source(st, p, pc, st.sim.load_demand, st.sim.cooling_water_temp, dt, in, h);
+        plant_secondary_to_primary(st);
+        if (in.emit_outputs) plant_report_state(st, p);
+    }
+    st.sim.time_minutes += dt;   // state_manager.advance_time(dt) / self.time += dt : sim.py:183-194 (minutes)
+}
+NPS_HD void plant_step_sink(PlantState& st, const PlantParams& p, const SecHandoff& h) {
+    if (is_true(p.enable_secondary)) secondary_update_sink(st, p, h, p.dt);
 }
 
 NPS_HD void plant_step(PlantState& st, const PlantParams& p, const StepInput& in) {
@@ -83,7 +101,12 @@ NPS_HD void plant_step(PlantState& st, const PlantParams& p, const StepInput& in
         PrimaryConditions pc;
         plant_primary_to_secondary(st, pc);
         st.sim.load_demand = st.pri.power_level;   // sim.py:161 (percent; overrides the caller)
-        secondary_update(st, p, pc, st.sim.load_demand, st.sim.cooling_water_temp, dt, in);
+        SecHandoff h;
+        secondary_update_source(st, p, pc, st.sim.load_demand, st.sim.cooling_water_temp, dt, in, h);
+        secondary_update_sink(st, p, h, dt);
+#if defined(NPS_CHEM_LAST)
+        secondary_update_chemistry(st, dt, in);     // tuning variant: the reference's textual order (monolithic shape only)
+#endif
         plant_secondary_to_primary(st);
         if (in.emit_outputs) plant_report_state(st, p);
     }

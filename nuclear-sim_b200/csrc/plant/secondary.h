@@ -34,15 +34,38 @@ NPS_HD_SHARED double secondary_sat_temp(double p_mpa) {
     return np_clip(t, 10.0, 374.0);
 }
 
-NPS_HD void secondary_update(PlantState& st, const PlantParams& p, const PrimaryConditions& pc, double load_demand,
-                             double cooling_water_temp, double dt, const StepInput& in) {
+// What the turbine / condenser / energy-bookkeeping half of a step (secondary_update_sink) needs from the half that
+// advances primary side, feedwater, steam generators and chemistry (secondary_update_source).  Nothing flows the other
+// way: turbine and condenser are pure sinks of the step's dataflow — their outputs reach only the report columns,
+// observation and reward (electrical power, efficiency, condenser pressure, heat rejection, `_last_load_factor`,
+// none of which the dynamics read back: sim.py:429-498, systems/secondary/__init__.py:565-932).
+struct SecHandoff {
+    TurbineInlet inlet;
+    double load_demand, cooling_water_temperature;
+    double primary_thermal, total_heat_transfer, total_steam_flow, avg_p;
+    double fw_total_flow, fw_total_power;
+    bool emit_outputs;
+};
+
+// chemistry: systems/secondary/__init__.py:634-665 (reads neither turbine nor condenser)
+NPS_HD void secondary_update_chemistry(PlantState& st, double dt, const StepInput& in) {
+    const MakeupWater mk = {7.2, 100.0, 300.0, 30.0, 8.0};
+    NPS_PREFETCH_SELF(st.ph);
+    wc_update(st.wc_main, true, mk, 0.02, dt);
+    ph_control_update(st.ph, st.wc_main.ph, dt, in.z_ph, in.u_ph, in.emit_outputs);
+    wc_queue_effects(st.wc_main, st.ph.ph_setpoint, st.ph.ammonia_dose_rate, st.ph.morpholine_dose_rate);
+}
+
+// systems/secondary/__init__.py:340-563 and :629-665 — everything of update_system that does not involve the turbine or
+// the condenser.  The chemistry block (:634-665) reads neither, so running it before them is the same arithmetic.
+NPS_HD void secondary_update_source(PlantState& st, const PlantParams& p, const PrimaryConditions& pc, double load_demand,
+                                    double cooling_water_temp, double dt, const StepInput& in, SecHandoff& h) {
     SecondaryState& S = st.sec;
     NPS_TOUCH(S.has_previous_feedwater_temp); NPS_TOUCH(S.previous_feedwater_temp); NPS_TOUCH(S.has_previous_sg_conditions); NPS_TOUCH(S.operating_hours);
     for (int i = 0; i < 3; ++i) { NPS_TOUCH(S.prev_sg_levels[i]); NPS_TOUCH(S.prev_sg_steam_flows[i]); NPS_TOUCH(S.prev_sg_steam_qualities[i]); }
     S.load_demand = load_demand;
     S.feedwater_temperature = 227.0;
     S.cooling_water_temperature = cooling_water_temp;
-    const double cooling_water_flow = 45000.0;
 
     // feedwater-temperature smoothing: :384-398
     if (!is_true(S.has_previous_feedwater_temp)) { S.has_previous_feedwater_temp = 1.0; S.previous_feedwater_temp = S.feedwater_temperature; }
@@ -80,7 +103,7 @@ NPS_HD void secondary_update(PlantState& st, const PlantParams& p, const Primary
     double fw_flows[3];
     for (int i = 0; i < 3; ++i) fw_flows[i] = fwr.total_flow_rate / 3;
     sg_system_update(st.sgs, p, pc.inlet_temp, pc.outlet_temp, pc.flow, load_fraction, S.load_demand / 100.0,
-                     actual_fw_temp, fw_flows, dt * 60, &st.turb);
+                     actual_fw_temp, fw_flows, dt * 60, nullptr);
     for (int i = 0; i < 3; ++i) {
         S.prev_sg_levels[i] = st.sgs.sg[i].water_level;
         S.prev_sg_pressures[i] = st.sgs.sg[i].secondary_pressure;
@@ -94,9 +117,42 @@ NPS_HD void secondary_update(PlantState& st, const PlantParams& p, const Primary
     double total_steam_flow = 0.0 + st.sgs.sg[0].steam_flow_rate; total_steam_flow += st.sgs.sg[1].steam_flow_rate;
     total_steam_flow += st.sgs.sg[2].steam_flow_rate;
 
+    S.total_feedwater_flow = fwr.total_flow_rate;
+    S.operating_hours += dt / 3600.0;
+
+#if !defined(NPS_CHEM_LAST)
+    secondary_update_chemistry(st, dt, in);
+#endif
+
+    S.total_steam_flow = total_steam_flow;
+    S.total_heat_transfer = total_heat_transfer;
+    S.sg_avg_pressure = avg_p;
+    S.sg_avg_temperature = avg_t;
+
+    double primary_thermal = 0.0;
+    for (int i = 0; i < 3; ++i) primary_thermal += pc.thermal_power[i];
+    h.inlet = turbine_inlet_from(st.sgs);
+    h.load_demand = S.load_demand;
+    h.cooling_water_temperature = S.cooling_water_temperature;
+    h.primary_thermal = primary_thermal;
+    h.total_heat_transfer = total_heat_transfer;
+    h.total_steam_flow = total_steam_flow;
+    h.avg_p = avg_p;
+    h.fw_total_flow = fwr.total_flow_rate;
+    h.fw_total_power = fwr.total_power_consumption;
+    h.emit_outputs = in.emit_outputs;
+}
+
+// systems/secondary/__init__.py:565-627 and :759-932 — turbine, LP-6 exhaust quality, condenser, energy bookkeeping and
+// electrical-power gating, heat-flow report; plus the one line of _apply_secondary_to_primary_feedback (sim.py:492)
+// that needs the electrical output.  Touches st.turb, st.cond, six fields of st.sec, st.sim.last_load_factor and the
+// hf_* report fields — nothing the source half reads.
+NPS_HD void secondary_update_sink(PlantState& st, const PlantParams& p, const SecHandoff& h, double dt) {
+    SecondaryState& S = st.sec;
+    const double cooling_water_flow = 45000.0;
     // STEP 5 turbine: :565-570
     TurbineResult tr;
-    turbine_update(st.turb, p, st.sgs, S.load_demand, 0.007, dt / 60.0, tr, &st.cond, in.emit_outputs);
+    turbine_update(st.turb, p, h.inlet, h.load_demand, 0.007, dt / 60.0, tr, &st.cond, h.emit_outputs);
 
     // LP-6 exhaust quality: :591-607
     double lp_quality = 0.90;
@@ -111,37 +167,22 @@ NPS_HD void secondary_update(PlantState& st, const PlantParams& p, const Primary
     NPS_PREFETCH_SELF(st.cond);
     NPS_PREFETCH_SELF(st.cond.ejector[0]);
     NPS_PREFETCH_SELF(st.cond.ejector[1]);
-    NPS_PREFETCH_FAR(st.ph);       // consumers after the condenser: shared water chemistry (2nd update) and pH control
-    NPS_PREFETCH_FAR(st.wc_main);
     CondenserResult cr;
     condenser_update(st.cond, p, tr.condenser_pressure, tr.condenser_temperature, tr.effective_steam_flow, lp_quality,
-                     cooling_water_flow, S.cooling_water_temperature, 1.2, 185.0, dt / 60.0, cr);
-
-    S.total_feedwater_flow = fwr.total_flow_rate;
-    S.operating_hours += dt / 3600.0;
-
-    // chemistry: :634-665
-    const MakeupWater mk = {7.2, 100.0, 300.0, 30.0, 8.0};
-    NPS_PREFETCH_SELF(st.ph);
-    wc_update(st.wc_main, true, mk, 0.02, dt);
-    ph_control_update(st.ph, st.wc_main.ph, dt, in.z_ph, in.u_ph, in.emit_outputs);
-    wc_queue_effects(st.wc_main, st.ph.ph_setpoint, st.ph.ammonia_dose_rate, st.ph.morpholine_dose_rate);
-
-    S.total_steam_flow = total_steam_flow;
-    S.total_heat_transfer = total_heat_transfer;
+                     cooling_water_flow, h.cooling_water_temperature, 1.2, 185.0, dt / 60.0, cr);
 
     // energy bookkeeping and electrical-power gating: :759-932
-    double primary_thermal = 0.0;
-    for (int i = 0; i < 3; ++i) primary_thermal += pc.thermal_power[i];
+    const double primary_thermal = h.primary_thermal;
     const double thermal_power_mw = primary_thermal;
+    const double total_heat_transfer = h.total_heat_transfer;
     const double turbine_electrical = tr.electrical_power_net;
     S.total_system_heat_rejection = (primary_thermal - turbine_electrical) * 1e6;
-    const double actual_fw_flow = fwr.total_flow_rate;
+    const double actual_fw_flow = h.fw_total_flow;
     double factor = 1.0;
     if (actual_fw_flow < 300.0) factor = 0.0;
     if (factor > 0.0) {
-        if (total_steam_flow < (300.0 * 0.5)) factor *= 0.1;
-        if (avg_p < (1.0 * 0.5)) factor *= 0.1;
+        if (h.total_steam_flow < (300.0 * 0.5)) factor *= 0.1;
+        if (h.avg_p < (1.0 * 0.5)) factor *= 0.1;
         if (thermal_power_mw > (primary_thermal * 1.1)) factor = 0.0;
     }
     S.power_reduction_factor = factor;
@@ -149,19 +190,18 @@ NPS_HD void secondary_update(PlantState& st, const PlantParams& p, const Primary
     S.thermal_efficiency = (primary_thermal > 0) ? S.electrical_power_output / primary_thermal : 0.0;
     S.heat_rate_kj_kwh = (S.electrical_power_output > 0)
                              ? (total_heat_transfer / 1000.0) / (S.electrical_power_output * 1000.0) * 3600.0 : 0.0;
-    S.sg_avg_pressure = avg_p;
-    S.sg_avg_temperature = avg_t;
     S.condenser_pressure = cr.condenser_pressure;
+    st.sim.last_load_factor = S.electrical_power_output / 1100.0;   // sim.py:446,492
 
-    if (in.emit_outputs) {   // HeatFlowTracker: :680-744 and heat_flow_tracker.py:248-327 (all MW)
+    if (h.emit_outputs) {   // HeatFlowTracker: :680-744 and heat_flow_tracker.py:248-327 (all MW)
         ReportState& R = st.rep;
         const double sg_in = total_heat_transfer / 1e6;
         const double steam_out = total_heat_transfer * 0.98 / 1e6;
         const double sg_losses = total_heat_transfer * 0.02 / 1e6;
         const double mech = tr.mechanical_power;
         const double turb_losses = mech * 0.05;
-        const double pump_work = fwr.total_power_consumption;
-        const double fw_losses = fwr.total_power_consumption * 0.1;
+        const double pump_work = h.fw_total_power;
+        const double fw_losses = h.fw_total_power * 0.1;
         const double total_losses = (sg_losses + turb_losses + fw_losses);
         const double rejection = sg_in - mech - total_losses;
         const double cond_losses = rejection * 0.01;

@@ -29,22 +29,22 @@ struct PrimaryState {
     double control_rod_position;
     double steam_valve_position;
     double boron_concentration;
-    double feedwater_pump_status;
+    double feedwater_pump_status;   // @discrete
     double feedwater_pump_speed;
-    double feedwater_system_available;
+    double feedwater_system_available;   // @discrete
     double feedwater_pump_power;
-    double feedwater_num_running_pumps;
+    double feedwater_num_running_pumps;   // @discrete
     double xenon_concentration;
     double iodine_concentration;
     double samarium_concentration;
     double burnable_poison_worth;
     double fuel_burnup;
     double power_level;
-    double scram_status;
+    double scram_status;   // @discrete
     // PrimaryReactorPhysics members: systems/primary/__init__.py:168-171
     double thermal_power_mw;
     double total_reactivity_pcm;
-    double scram_activated;
+    double scram_activated;   // @discrete
     // ConstantHeatSource members: heat_sources/constant_heat_source.py:44-65
     double hs_setpoint_percent;
     double hs_current_power_mw;
@@ -59,7 +59,7 @@ struct SimState {
     double time_minutes;
     double load_demand;
     double cooling_water_temp;
-    double has_last_heat_removal_factor;
+    double has_last_heat_removal_factor;   // @discrete
     double last_heat_removal_factor;
     double last_load_factor;
     double last_feedwater_flow_factor;
@@ -92,7 +92,7 @@ struct WaterChemState {
     double operating_hours;
     double last_treatment_time;
     double chemistry_stability_factor;
-    double pending_effects;
+    double pending_effects;   // @discrete
     double pend_ph_setpoint;
     double pend_ammonia_dose_rate;
     double pend_morpholine_dose_rate;
@@ -128,12 +128,12 @@ struct LubCore {
 struct FWPumpState {
     double speed_percent;
     double flow_rate;
-    double status;
+    double status;   // @discrete
     double speed_setpoint;
     double power_consumption;
-    double available;
-    double trip_active;
-    double trip_reason;
+    double available;   // @discrete
+    double trip_active;   // @discrete
+    double trip_reason;   // @discrete
     double suction_pressure;
     double discharge_pressure;
     double npsh_available;
@@ -147,7 +147,7 @@ struct FWPumpState {
     double cavitation_time;
     double cavitation_noise_level;
     double flow_demand;
-    double ic_applied;
+    double ic_applied;   // @discrete
     LubCore lub;
     double pump_load_factor;
     double cavitation_lubrication_effect;
@@ -172,8 +172,8 @@ struct FeedwaterState {
     double maintenance_factor;
     double operating_hours;
     double load_demand;
-    double n_running_prev;
-    double pump_system_available;
+    double n_running_prev;   // @discrete
+    double pump_system_available;   // @discrete
     double total_flow_demand;
     double lc_level_errors[3];
     double lc_level_integral_errors[3];
@@ -182,7 +182,7 @@ struct FeedwaterState {
     double lc_control_performance;
     double cav_current_intensity;
     double cav_accumulated_damage;
-    double cav_n_events;
+    double cav_n_events;   // @discrete
     double cav_time_in_cavitation;
     double cav_acoustic_signature;
     double cav_noise_increase;
@@ -190,16 +190,16 @@ struct FeedwaterState {
     double cav_risk_score;
     double cav_predicted_damage_rate;
     double diag_health_score;
-    double prot_npsh_low_alarm_active;
-    double prot_npsh_low_low_trip_active;
-    double prot_npsh_critical_trip_active;
+    double prot_npsh_low_alarm_active;   // @discrete
+    double prot_npsh_low_low_trip_active;   // @discrete
+    double prot_npsh_critical_trip_active;   // @discrete
     double prot_npsh_low_low_timer;
     double prot_timer_low_flow;
     double prot_timer_high_flow;
     double prot_timer_bearing_temp;
     double prot_timer_motor_temp;
     double prot_timer_vibration;
-    double prot_system_trip_active;
+    double prot_system_trip_active;   // @discrete
 };
 
 // ---- steam generators ------------------------------------------------------------------------
@@ -226,17 +226,17 @@ struct SGState {
     double thermal_efficiency;
     double tsp_operating_years;
     double tsp_last_cleaning_time;
-    double tsp_total_cleaning_cycles;
+    double tsp_total_cleaning_cycles;   // @discrete
     double tsp_fouling_fraction;
     double tsp_thickness[7][4];
-    double tsp_fouling_stage;
+    double tsp_fouling_stage;   // @discrete
     double tsp_heat_transfer_degradation;
     double tsp_pressure_drop_ratio;
     double tsp_flow_maldistribution;
     double tsp_cumulative_power_loss;
-    double tsp_shutdown_required;
-    double tsp_shutdown_reasons;
-    double tsp_replacement_recommended;
+    double tsp_shutdown_required;   // @discrete
+    double tsp_shutdown_reasons;   // @discrete
+    double tsp_replacement_recommended;   // @discrete
     double tif_operating_years;
     double tif_last_cleaning_time;
     double tif_scale_thickness;
@@ -245,7 +245,7 @@ struct SGState {
     double tif_comp[3];
     double tif_fouling_fraction;
     double tif_cumulative_performance_loss;
-    double tif_replacement_recommended;
+    double tif_replacement_recommended;   // @discrete
 };
 
 // EnhancedSteamGeneratorPhysics members: steam_generator/enhanced_physics.py:133-150
@@ -300,7 +300,7 @@ struct TurbineBearingState {
     double oil_temperature;
     double oil_flow_rate;
     double oil_contamination_level;
-    double external_oil_temp;
+    double external_oil_temp;   // @discrete
 };
 
 // EnhancedTurbinePhysics (turbine/enhanced_physics.py:520-541) with its TurbineStageSystem
@@ -325,7 +325,7 @@ struct TurbineState {
     double thermal_expansion;
     double thermal_bow;
     double rotor_operating_hours;
-    double overspeed_events;
+    double overspeed_events;   // @discrete
     double vib_displacement_x;
     double vib_displacement_y;
     double vib_velocity_x;
@@ -333,10 +333,10 @@ struct TurbineState {
     double vib_acceleration_x;
     double vib_acceleration_y;
     double vib_harmonic[3];
-    double vib_displacement_alarm;
-    double vib_velocity_alarm;
-    double vib_acceleration_alarm;
-    double vib_critical_speed_alarm;
+    double vib_displacement_alarm;   // @discrete
+    double vib_velocity_alarm;   // @discrete
+    double vib_acceleration_alarm;   // @discrete
+    double vib_critical_speed_alarm;   // @discrete
     double th_rotor_temperatures[8];
     double th_casing_temperatures[6];
     double th_blade_temperatures[14];
@@ -349,8 +349,8 @@ struct TurbineState {
     double prot_timer_overspeed;
     double prot_timer_vibration;
     double prot_timer_bearing_temp;
-    double prot_trip_active;
-    double prot_trip_reasons;
+    double prot_trip_active;   // @discrete
+    double prot_trip_reasons;   // @discrete
     LubCore lub;
     double lub_turbine_efficiency_degradation;
     double lub_vibration_increase;
@@ -369,7 +369,7 @@ struct TurbineState {
 // ---- condenser ---------------------------------------------------------------------------------
 // SteamJetEjector members: condenser/vacuum_pump.py:56-95
 struct EjectorState {
-    double is_operating;
+    double is_operating;   // @discrete
     double operating_hours;
     double current_capacity;
     double suction_pressure;
@@ -431,16 +431,16 @@ struct CondenserState {
     double vs_air_mass_in_condenser;
     double vs_motive_steam_pressure;
     double vs_motive_steam_temperature;
-    double vs_motive_steam_available;
+    double vs_motive_steam_available;   // @discrete
     double vs_system_efficiency;
     double vs_operating_hours;
-    double vs_alarm_high_pressure;
-    double vs_alarm_low_motive_pressure;
-    double vs_alarm_ejector_failure;
-    double vs_alarm_excessive_air_leakage;
-    double vs_trip_high_pressure;
-    double vc_lead_ejector;
-    double vc_lag_ejector;
+    double vs_alarm_high_pressure;   // @discrete
+    double vs_alarm_low_motive_pressure;   // @discrete
+    double vs_alarm_ejector_failure;   // @discrete
+    double vs_alarm_excessive_air_leakage;   // @discrete
+    double vs_trip_high_pressure;   // @discrete
+    double vc_lead_ejector;   // @discrete
+    double vc_lag_ejector;   // @discrete
     double vc_rotation_timer;
 };
 
@@ -449,8 +449,8 @@ struct CondenserState {
 // 199-217, 521-532.  control_mode: 0 AUTO 1 MANUAL 2 FAILED 3 MAINTENANCE.
 // dev_hist is the sliding window of the last 100 |pH error| values (oldest at dev_head).
 struct PHControlState {
-    double control_mode;
-    double controller_enabled;
+    double control_mode;   // @discrete
+    double controller_enabled;   // @discrete
     double manual_output;
     double measured_ph;
     double ph_setpoint;
@@ -465,26 +465,26 @@ struct PHControlState {
     double integral_sum;
     double ammonia_tank_level;
     double morpholine_tank_level;
-    double ammonia_supply_available;
-    double morpholine_supply_available;
-    double ammonia_pump_status;
-    double morpholine_pump_status;
-    double ph_sensor_status;
-    double ph_low_alarm;
-    double ph_high_alarm;
-    double low_chemical_alarm;
-    double equipment_failure_alarm;
+    double ammonia_supply_available;   // @discrete
+    double morpholine_supply_available;   // @discrete
+    double ammonia_pump_status;   // @discrete
+    double morpholine_pump_status;   // @discrete
+    double ph_sensor_status;   // @discrete
+    double ph_low_alarm;   // @discrete
+    double ph_high_alarm;   // @discrete
+    double low_chemical_alarm;   // @discrete
+    double equipment_failure_alarm;   // @discrete
     double control_deviation_rms;
     double chemical_consumption_rate;
     double time_in_control;
     double operating_hours;
-    double tic_initialized;
+    double tic_initialized;   // @discrete
     double tic_sum;
     double tic_total_time;
     double total_chemical_consumed;
-    double control_actions_count;
-    double dev_count;
-    double dev_head;
+    double control_actions_count;   // @discrete
+    double dev_count;   // @discrete
+    double dev_head;   // @discrete
     double dev_hist[100];
 };
 
@@ -501,9 +501,9 @@ struct SecondaryState {
     double cooling_water_temperature;
     double operating_hours;
     double total_system_heat_rejection;
-    double has_previous_feedwater_temp;
+    double has_previous_feedwater_temp;   // @discrete
     double previous_feedwater_temp;
-    double has_previous_sg_conditions;
+    double has_previous_sg_conditions;   // @discrete
     double prev_sg_levels[3];
     double prev_sg_pressures[3];
     double prev_sg_steam_flows[3];
@@ -548,7 +548,7 @@ struct ReportState {
     double fw_avg_steam_quality;
     double fw_diag_maintenance_urgency;
     double fw_diag_total_wear;
-    double fw_prot_active_alarms_count;
+    double fw_prot_active_alarms_count;   // @discrete
     double hf_steam_enthalpy_flow;
     double hf_turbine_work_output;
     double hf_condenser_heat_rejection;

@@ -301,8 +301,24 @@ struct TurbineResult {
     double hp_power, lp_power, condenser_pressure, condenser_temperature, effective_steam_flow, lp6_outlet_enthalpy;
 };
 
+// What the turbine reads from the steam-generator system (EnhancedTurbinePhysics.update_state arguments assembled in
+// systems/secondary/__init__.py:537-570): the aggregates, the three SG pressures and the SG-system availability.  A
+// plain value record, so the turbine / condenser half of a step can run on a different thread than the half that
+// produced it (nps_capi.cu: split launch shape for small batches).
+struct TurbineInlet {
+    double average_steam_pressure, average_steam_temperature, total_steam_flow, system_availability;
+    double sg_pressure[3];
+};
+NPS_HD TurbineInlet turbine_inlet_from(const SGSystemState& S) {
+    TurbineInlet t;
+    t.average_steam_pressure = S.average_steam_pressure; t.average_steam_temperature = S.average_steam_temperature;
+    t.total_steam_flow = S.total_steam_flow; t.system_availability = S.system_availability;
+    for (int i = 0; i < 3; ++i) t.sg_pressure[i] = S.sg[i].secondary_pressure;
+    return t;
+}
+
 // Wrapped EnhancedTurbinePhysics.update_state (dt in hours; load_demand as passed = percent)
-NPS_HD void turbine_update(TurbineState& T, const PlantParams& p, const SGSystemState& S, double load_demand,
+NPS_HD void turbine_update(TurbineState& T, const PlantParams& p, const TurbineInlet& S, double load_demand,
                            double condenser_pressure, double dt, TurbineResult& out,
                            const CondenserState* prefetch_next = nullptr, bool emit_outputs = true) {
     NPS_PREFETCH(T.stage[0]);
@@ -316,9 +332,9 @@ NPS_HD void turbine_update(TurbineState& T, const PlantParams& p, const SGSystem
     // _calculate_pressure_variation_effects: enhanced_physics.py:1312-1350
     double psf;
     {
-        double avg = (0.0 + S.sg[0].secondary_pressure + S.sg[1].secondary_pressure + S.sg[2].secondary_pressure) / 3;
-        double md = py_max3(fabs(S.sg[0].secondary_pressure - avg), fabs(S.sg[1].secondary_pressure - avg),
-                            fabs(S.sg[2].secondary_pressure - avg));
+        double avg = (0.0 + S.sg_pressure[0] + S.sg_pressure[1] + S.sg_pressure[2]) / 3;
+        double md = py_max3(fabs(S.sg_pressure[0] - avg), fabs(S.sg_pressure[1] - avg),
+                            fabs(S.sg_pressure[2] - avg));
         double vf = md / 0.1;
         if (md < 0.02) psf = 1.0;
         else if (md < 0.05) psf = 1.0 - (md - 0.02) / 0.03 * 0.05;

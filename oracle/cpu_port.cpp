@@ -119,7 +119,7 @@ extern "C" int nps_oracle_turbine(double* state, const double* params, double lo
     PlantParams p; std::memcpy(&p, params, sizeof(p));
     PlantState st; std::memcpy(&st, state, sizeof(st));
     TurbineResult r;
-    turbine_update(st.turb, p, st.sgs, load_demand, cond_p, dt, r);
+    turbine_update(st.turb, p, turbine_inlet_from(st.sgs), load_demand, cond_p, dt, r);
     std::memcpy(state, &st, sizeof(st));
     std::memcpy(out11, &r, sizeof(r));
     return 0;

@@ -74,15 +74,12 @@ def oracle_run_sized(L, g, st, t0, t1):
 
 
 def discrete_mask():
-    """Fields that hold flags / enums / counters / latches: compared bit-exactly."""
+    """Fields that hold flags / enums / counters / latches: compared bit-exactly.  The list is explicit: the members
+    annotated `// @discrete` in csrc/plant/state.h (nuclear_sim_b200._layout.discrete_field_names)."""
     from nuclear_sim_b200 import field_names
-    keys = ("status", "scram", "available", "trip", "alarm", "_active", "is_operating", "ic_applied", "fouling_stage",
-            "shutdown", "replacement", "recommended", "mode", "enabled", "events", "cycles", "n_running", "n_events",
-            "lead_ejector", "lag_ejector", "dev_count", "dev_head", "external_oil_temp", "has_", "pending_effects",
-            "initialized", "control_actions_count", "feedwater_pump_status", "num_running")
-    names = field_names("PlantState")
-    not_discrete = ("npsh_available", "td_active_tube_count", "prot_timer", "feedwater_pump_speed", "feedwater_pump_power")
-    return np.array([any(k in n for k in keys) and not any(x in n for x in not_discrete) for n in names])
+    from nuclear_sim_b200._layout import discrete_field_names
+    d = set(discrete_field_names())
+    return np.array([n in d for n in field_names("PlantState")])
 
 
 def canonicalize(v):

@@ -84,3 +84,29 @@ def test_plain_c_example_compiles_and_links(tmp_path):
                            os.path.join(root, "examples", "step_from_c.c"), "-o", exe, "-L", lib_dir, "-lnps_b200",
                            "-L", "/usr/local/cuda/lib64", "-lcudart", f"-Wl,-rpath,{lib_dir}"])
     assert os.path.getsize(exe) > 0
+
+
+def test_discrete_fields_are_an_explicit_list_and_hold_integers():
+    """The bit-exact class of fields is declared in state.h (`// @discrete`), not guessed from names: 92 flat fields;
+    in every state the live reference produced for the fixtures they hold exact integers, and every field whose name
+    says flag / status / trip / alarm is on the list."""
+    import glob
+    import numpy as np
+    from nuclear_sim_b200 import field_index, field_names
+    from nuclear_sim_b200._layout import discrete_field_names
+    disc = discrete_field_names()
+    assert len(disc) == 92 and len(set(disc)) == 92
+    ix = field_index()
+    cols = np.array([ix[n] for n in disc])
+    n_checked = 0
+    for path in sorted(glob.glob(os.path.join(U.GOLDEN, "*.npz"))):
+        z = np.load(path, allow_pickle=False)
+        for key in ("states", "state0", "before", "after"):
+            if key in z.files:
+                v = z[key].reshape(-1, z[key].shape[-1])[:, cols]
+                assert np.array_equal(v, np.round(v)), f"{os.path.basename(path)}:{key} has a non-integer discrete field"
+                n_checked += v.shape[0]
+    assert n_checked > 1000
+    for n in field_names("PlantState"):
+        if any(k in n for k in ("trip_active", "scram", "_alarm", "is_operating", "shutdown_required")):
+            assert n in disc, n

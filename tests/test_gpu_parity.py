@@ -512,8 +512,14 @@ def test_error_conventions_through_the_abi():
     bad = np.array([10 ** 6], dtype=np.int32)
     assert L.nps_set_logged_fields(sim._h, bad.ctypes.data_as(ctypes.c_void_p), 1) < 0 and b"out of range" in L.nps_last_error()
     assert L.nps_wait(sim._h, 17) < 0 and b"bad ticket" in L.nps_last_error()
-    # a maintenance target without a restatement is refused, not ignored (status 2 -> the host raises)
-    assert sim.apply_maintenance([(0, 8, 0, 0)]) == [2]
+    # every target has a restatement now; an action a target does not know fails the way the reference's does
+    # (success False, no state change): oil_change on the SG system object
+    import torch
+    from nuclear_sim_b200 import struct_range
+    before = sim.slab.clone()
+    assert sim.apply_maintenance([(0, 8, 0, 0)]) == [0]
+    lo, _ = struct_range("rep")             # the report columns are refreshed after every maintenance call
+    assert torch.equal(before[:lo], sim.slab[:lo])
 
 
 def test_device_pow_against_libm():
@@ -743,3 +749,69 @@ def test_cfg4_reference_transients_embedded_in_16384():
     assert np.array_equal(done, g["done"].astype(bool))
     assert sim.first_scram_step[dev_ids].cpu().numpy().tolist() == g["first_scram_step"].tolist()
     assert (g["first_scram_step"] >= 0).sum() >= 15
+
+
+@pytest.mark.parametrize("name", ["cfg3_loadfollow", "cfg6_secondary_trips", "cfg7_turbine_trips_fouling", "cfg1_oil_top_off"])
+def test_split_launch_shape_is_bit_identical_to_one_thread_per_plant(name):
+    """Small batches run two threads per plant (source half / sink half, pipelined by one substep).  State, observation,
+    reward, done, per-substep reward / done, threshold events, watch stamps must equal the one-thread-per-plant shape
+    bit for bit, with and without monitoring, for K = 1 and fused launches."""
+    import json
+    import torch
+    from nuclear_sim_b200 import maintenance as M
+    g = U.load_golden(name)
+    cfg = json.loads(str(np.load(os.path.join(U.GOLDEN, "maint_oil_top_off.npz"), allow_pickle=False)["log"]))["maintenance_system"]
+    T = min(120, g["actions"].shape[0])
+    sims = []
+    for shape in (0, 1):
+        sim = _sim(g["state0"], g["params"])
+        sim.set_small_batch_shape(shape)
+        sim.set_thresholds(M.ThresholdTable(cfg).device_rows())
+        sim.enable_monitor(per_substep=True, max_k=32)
+        sims.append(sim)
+    outs = [[], []]
+    t = 0
+    for k in [1, 2, 5, 32, 17, 1, 32, 30]:
+        k = min(k, T - t)
+        if k <= 0:
+            break
+        for i, sim in enumerate(sims):
+            o = sim.step(actions=torch.from_numpy(np.ascontiguousarray(g["actions"][t:t + k])),
+                         magnitudes=torch.from_numpy(np.ascontiguousarray(g["magnitudes"][t:t + k])),
+                         noise=torch.from_numpy(np.ascontiguousarray(g["noise"][t:t + k].transpose(0, 2, 1))),
+                         power_setpoint=torch.from_numpy(np.ascontiguousarray(g["setpoint"][t:t + k])), K=k)
+            outs[i].append({q: v.clone() for q, v in o.items()})
+        t += k
+        assert torch.equal(sims[0].slab, sims[1].slab), f"state differs after step {t}"
+    for a, b in zip(*outs):
+        for q in a:
+            assert torch.equal(a[q], b[q]) or (torch.isnan(a[q]) == torch.isnan(b[q])).all() and torch.equal(torch.nan_to_num(a[q]), torch.nan_to_num(b[q])), q
+    ev = [s.drain_step_events() for s in sims]
+    assert ev[0].tolist() == ev[1].tolist()
+    for (wa, sa), (wb, sb) in zip(sims[0].watch_steps().items(), sims[1].watch_steps().items()):
+        assert torch.equal(sa, sb), wa
+    assert torch.equal(sims[0].first_scram_step, sims[1].first_scram_step) and torch.equal(sims[0].status, sims[1].status)
+
+
+def test_split_launch_shape_on_a_ragged_random_batch(oracle_lib):
+    """4 099 plants (ragged last block), random actions and noise, 3 fused launches: split shape == one thread per plant
+    bitwise, and both within tolerance of the host oracle."""
+    import torch
+    from nuclear_sim_b200 import load_snapshot
+    from nuclear_sim_b200 import scenarios as sc
+    s0, params = load_snapshot("pwr3000_reactor_dt1")
+    n, k = 4099, 6
+    pid = np.arange(n)
+    st = sc.randomized_states(s0, pid)
+    a, b = _sim(st, params), _sim(st, params)
+    b.set_small_batch_shape(1)
+    ref = st.copy()
+    for i in range(3):
+        acts, mags = sc.load_following_inputs(pid, i * k, k)
+        noise = sc.noise_inputs(pid, i * k, k)
+        for sim in (a, b):
+            sim.step(actions=torch.from_numpy(acts), magnitudes=torch.from_numpy(mags), noise=torch.from_numpy(noise), K=k)
+        ref = U.oracle_run(oracle_lib, ref, params, acts, mags, np.ascontiguousarray(noise.transpose(0, 2, 1)),
+                           np.full((k, n), np.nan), None, 0, k)
+    assert torch.equal(a.slab, b.slab)
+    U.assert_states_close(a.state_numpy(), ref, U.TOL_STEP * 3 * k, "split shape vs oracle")
