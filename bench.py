@@ -435,9 +435,9 @@ def main():
                                  "note": "the 65,536-plant batch of the north star split over the GPUs (strong scaling)"}
     else:
         extra["small_batch"] = {"unit": UNIT, "plants_4096": sub_batch(4096, 3), "plants_8192": sub_batch(8192, 3),
-                                "plants_16384": sub_batch(16384, 3),
+                                "plants_16384": sub_batch(16384, 3), "plants_32768": sub_batch(32768, 3),
                                 "one_thread_per_plant": {"plants_4096": sub_batch(4096, 3, 1), "plants_8192": sub_batch(8192, 3, 1),
-                                                         "plants_16384": sub_batch(16384, 3, 1)},
+                                                         "plants_16384": sub_batch(16384, 3, 1), "plants_32768": sub_batch(32768, 3, 1)},
                                 "note": "config #2 / strong-scaled config #3 share per GPU / config #4 sizes on one GPU; default "
                                         "launch shape below 33 K plants = two threads per plant (source / sink halves pipelined "
                                         "by one substep), bit-identical to one thread per plant"}

@@ -118,11 +118,6 @@ NPS_HD bool nps_pow_pos(double x, double y, double& out) {
     return nps_pow_exp(y, Lh, Ll, out);
 }
 
-// One base raised to several exponents (the wear laws: load_factor ** e_k, speed_factor ** e_k for every component of a
-// unit): the logarithm of the base is computed once and kept with the base's exact bits; a different base recomputes.
-// Same arithmetic as nps_pow_pos, so results are bit-identical to the unmemoised call.
-struct PowMemo { long long xbits = 0; double Lh = 0.0, Ll = 0.0; int state = 0; };   // state: 0 empty, 1 log valid, 2 base outside the guarded range
-
 #undef nps_pow_tab
 #undef NPS_POW_TAB
 }  // namespace nps

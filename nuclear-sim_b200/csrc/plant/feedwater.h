@@ -64,9 +64,8 @@ NPS_HD double fwp_dynamic_npsh_required(const FWPumpState& u, const PlantParams&
 // (the impeller receives no conditions from the wrapper, so it sees the defaults).
 NPS_HD double fwp_component_wear_rate(const FWPumpState& u, int comp, double load_factor, double speed_factor,
                                       double temperature, double cav, double electrical_load_factor,
-                                      double head_factor, double pressure_factor, PowMemo& ml, PowMemo& ms) {
+                                      double head_factor, double pressure_factor) {
     const LubComponent c = fw_lub_component(comp);
-    PowMemo once;   // bases used by one component only; ml / ms carry log(load_factor) / log(speed_factor) across components
     const double impeller_wear = u.lub.component_wear[FWL_IMPELLER];
     const double max_brg = py_max3(u.lub.component_wear[FWL_MOTOR_BRG], u.lub.component_wear[FWL_PUMP_BRG],
                                    u.lub.component_wear[FWL_THRUST_BRG]);
@@ -75,31 +74,31 @@ NPS_HD double fwp_component_wear_rate(const FWPumpState& u, int comp, double loa
         double cav_factor = 1.0 + cav * 3.0;
         double temp_factor = py_max(1.0, (temperature - 80.0) / 40.0);
         double brg_cpl = 1.0 + (max_brg / 100.0) * 0.3;
-        wear_rate = (c.base_wear_rate * py_pow_memo(load_factor, c.load_wear_exponent, ml) * py_pow_memo(speed_factor, c.speed_wear_exponent, ms) *
+        wear_rate = (c.base_wear_rate * py_pow(load_factor, c.load_wear_exponent) * py_pow(speed_factor, c.speed_wear_exponent) *
                      cav_factor * temp_factor * brg_cpl);
     } else if (comp == FWL_MOTOR_BRG) {
         double temp_factor = py_max(1.0, (temperature - 60.0) / 25.0);
         double imp_cpl = 1.0 + (impeller_wear / 100.0) * 0.2;
-        wear_rate = (c.base_wear_rate * py_pow_memo(electrical_load_factor, c.load_wear_exponent, once) *
-                     py_pow_memo(speed_factor, c.speed_wear_exponent, ms) * temp_factor * imp_cpl);
+        wear_rate = (c.base_wear_rate * py_pow(electrical_load_factor, c.load_wear_exponent) *
+                     py_pow(speed_factor, c.speed_wear_exponent) * temp_factor * imp_cpl);
     } else if (comp == FWL_PUMP_BRG) {
         double cav_factor = 1.0 + cav * 2.0;
         double temp_factor = py_max(1.0, (temperature - 50.0) / 30.0);
         double imp_cpl = 1.0 + (impeller_wear / 100.0) * 0.4;
-        wear_rate = (c.base_wear_rate * py_pow_memo(load_factor, c.load_wear_exponent, ml) * py_pow_memo(speed_factor, c.speed_wear_exponent, ms) *
+        wear_rate = (c.base_wear_rate * py_pow(load_factor, c.load_wear_exponent) * py_pow(speed_factor, c.speed_wear_exponent) *
                      cav_factor * temp_factor * imp_cpl);
     } else if (comp == FWL_THRUST_BRG) {
         double axial = head_factor * load_factor;
         double imp_cpl = 1.0 + (impeller_wear / 100.0) * 0.25;
-        wear_rate = (c.base_wear_rate * py_pow_memo(axial, c.load_wear_exponent, ml) * py_pow_memo(speed_factor, c.speed_wear_exponent, ms) * imp_cpl);
+        wear_rate = (c.base_wear_rate * py_pow(axial, c.load_wear_exponent) * py_pow(speed_factor, c.speed_wear_exponent) * imp_cpl);
     } else if (comp == FWL_SEALS) {
         double cav_seal = 1.0 + cav * 5.0;
         double imp_cpl = 1.0 + (impeller_wear / 100.0) * 0.15;
         double brg_cpl = 1.0 + (max_brg / 100.0) * 0.2;
-        wear_rate = (c.base_wear_rate * py_pow_memo(pressure_factor, c.load_wear_exponent, once) * 1.0 * cav_seal * imp_cpl * brg_cpl);
+        wear_rate = (c.base_wear_rate * py_pow(pressure_factor, c.load_wear_exponent) * 1.0 * cav_seal * imp_cpl * brg_cpl);
     } else {
         double brg_cpl = 1.0 + (max_brg / 100.0) * 0.3;
-        wear_rate = (c.base_wear_rate * 1.0 * 1.0 * py_pow_memo(load_factor, c.load_wear_exponent, ml) * brg_cpl);
+        wear_rate = (c.base_wear_rate * 1.0 * 1.0 * py_pow(load_factor, c.load_wear_exponent) * brg_cpl);
     }
     wear_rate *= 1.0;  // chemistry_wear_factor default
     return wear_rate;
@@ -161,16 +160,15 @@ NPS_HD void fwp_update_lubrication(FWPumpState& u, const PlantParams& p, const P
     lub_update_oil_quality(u.lub, FWL_NCOMP, lim, oil_temp, total_contam, 0.0001, dth);
 
     // update_component_wear (dict order; each rate sees wear already updated for earlier components)
-    PowMemo ml, ms;
     for (int c = 0; c < FWL_NCOMP; ++c) {
         double rate;
         switch (c) {
-            case FWL_IMPELLER:   rate = fwp_component_wear_rate(u, c, 1.0, 1.0, 55.0, 0.0, 1.0, 1.0, 1.0, ml, ms); break;
-            case FWL_MOTOR_BRG:  rate = fwp_component_wear_rate(u, c, elf, speed_factor, 60.0 + elf * 25.0, 0.0, elf, 1.0, 1.0, ml, ms); break;
-            case FWL_PUMP_BRG:   rate = fwp_component_wear_rate(u, c, load_factor, speed_factor, 50.0 + load_factor * 30.0, cav, 1.0, 1.0, 1.0, ml, ms); break;
-            case FWL_THRUST_BRG: rate = fwp_component_wear_rate(u, c, load_factor, speed_factor, 45.0 + load_factor * 30.0, 0.0, 1.0, 1.0, 1.0, ml, ms); break;
-            case FWL_SEALS:      rate = fwp_component_wear_rate(u, c, load_factor, speed_factor, 40.0 + load_factor * 30.0, cav, 1.0, 1.0, pressure_factor, ml, ms); break;
-            default:             rate = fwp_component_wear_rate(u, c, load_factor, speed_factor, 50.0 + load_factor * 20.0, 0.0, 1.0, 1.0, 1.0, ml, ms); break;
+            case FWL_IMPELLER:   rate = fwp_component_wear_rate(u, c, 1.0, 1.0, 55.0, 0.0, 1.0, 1.0, 1.0); break;
+            case FWL_MOTOR_BRG:  rate = fwp_component_wear_rate(u, c, elf, speed_factor, 60.0 + elf * 25.0, 0.0, elf, 1.0, 1.0); break;
+            case FWL_PUMP_BRG:   rate = fwp_component_wear_rate(u, c, load_factor, speed_factor, 50.0 + load_factor * 30.0, cav, 1.0, 1.0, 1.0); break;
+            case FWL_THRUST_BRG: rate = fwp_component_wear_rate(u, c, load_factor, speed_factor, 45.0 + load_factor * 30.0, 0.0, 1.0, 1.0, 1.0); break;
+            case FWL_SEALS:      rate = fwp_component_wear_rate(u, c, load_factor, speed_factor, 40.0 + load_factor * 30.0, cav, 1.0, 1.0, pressure_factor); break;
+            default:             rate = fwp_component_wear_rate(u, c, load_factor, speed_factor, 50.0 + load_factor * 20.0, 0.0, 1.0, 1.0, 1.0); break;
         }
         lub_apply_component_wear(u.lub, c, fw_lub_component(c), rate, dth);
     }

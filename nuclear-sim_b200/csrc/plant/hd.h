@@ -134,55 +134,6 @@ NPS_HD double py_pow(double x, double y) {
 #endif
     return nps_pow_general(x, y);
 }
-// py_pow with the base's logarithm memoised in `m` (fastpow.h PowMemo); pow(1, y) == 1 exactly for every y (C99 F.9.4.4).
-// The two halves are shared (non-inlined) bodies that take and return VALUES, and the memo test is inlined into the
-// caller, so the memo lives in the caller's registers rather than in its local-memory frame.
-struct PowLogResult { double Lh, Ll; int ok; };
-NPS_HD_SHARED PowLogResult nps_pow_log_shared(double x) {
-    PowLogResult r;
-    r.Lh = 0.0; r.Ll = 0.0;
-    r.ok = nps_pow_log(x, r.Lh, r.Ll) ? 1 : 0;
-    return r;
-}
-NPS_HD_SHARED double nps_pow_exp_shared(double x, double y, double Lh, double Ll) {
-    double r;
-    if (nps_pow_exp(y, Lh, Ll, r)) return r;
-    return pow(x, y);
-}
-NPS_HD double nps_pow_general_memo(double x, double y, PowMemo& m) {
-#if defined(__CUDA_ARCH__) && !defined(NPS_LIBDEVICE_POW)
-    const long long xb = nps_bits(x);
-    if (m.state == 0 || m.xbits != xb) {
-        const PowLogResult r = nps_pow_log_shared(x);
-        m.xbits = xb; m.Lh = r.Lh; m.Ll = r.Ll;
-        m.state = r.ok ? 1 : 2;
-    }
-    if (m.state == 1) return nps_pow_exp_shared(x, y, m.Lh, m.Ll);
-#else
-    (void)m;
-#endif
-    return pow(x, y);
-}
-NPS_HD double py_pow_memo(double x, double y, PowMemo& m) {
-#if defined(NPS_NO_POW_MEMO)
-    (void)m;
-    return py_pow(x, y);
-#elif defined(__CUDA_ARCH__) && !defined(NPS_GENERIC_POW)
-    if (y == 2.0) return x * x;
-    if (y == 1.0) return x;
-    if (x == 1.0) return 1.0;
-    if (x > 0.0 && x < 1.7e308) {
-        if (y == 0.5) return sqrt(x);
-        if (y == 3.0) return x * x * x;
-        if (y == 1.5) return x * sqrt(x);
-        if (y == 0.25) return sqrt(sqrt(x));
-    }
-    return nps_pow_general_memo(x, y, m);
-#else
-    (void)m;
-    return pow(x, y);
-#endif
-}
 // libm calls through one shared body each on the device (see NPS_HD_SHARED): log / log10 / exp expand to 60-100 SASS
 // instructions per call site when inlined, and the kernel is instruction-fetch bound (20 % of stall samples).
 NPS_HD_SHARED double nps_log(double x) { return log(x); }

@@ -76,7 +76,7 @@ NPS_HD void plant_step_source(PlantState& st, const PlantParams& p, const StepIn
         PrimaryConditions pc;
         plant_primary_to_secondary(st, pc);
         st.sim.load_demand = st.pri.power_level;   // sim.py:161 (percent; overrides the caller)
-        secondary_update_source(st, p, pc, st.sim.load_demand, st.sim.cooling_water_temp, dt, in, h);
+        secondary_update_source<true>(st, p, pc, st.sim.load_demand, st.sim.cooling_water_temp, dt, in, h);
         plant_secondary_to_primary(st);
         if (in.emit_outputs) plant_report_state(st, p);
     }
@@ -102,11 +102,9 @@ NPS_HD void plant_step(PlantState& st, const PlantParams& p, const StepInput& in
         plant_primary_to_secondary(st, pc);
         st.sim.load_demand = st.pri.power_level;   // sim.py:161 (percent; overrides the caller)
         SecHandoff h;
-        secondary_update_source(st, p, pc, st.sim.load_demand, st.sim.cooling_water_temp, dt, in, h);
+        secondary_update_source<false>(st, p, pc, st.sim.load_demand, st.sim.cooling_water_temp, dt, in, h);
         secondary_update_sink(st, p, h, dt);
-#if defined(NPS_CHEM_LAST)
-        secondary_update_chemistry(st, dt, in);     // tuning variant: the reference's textual order (monolithic shape only)
-#endif
+        secondary_update_chemistry(st, dt, in);     // :634-665, after the condenser as in the reference
         plant_secondary_to_primary(st);
         if (in.emit_outputs) plant_report_state(st, p);
     }

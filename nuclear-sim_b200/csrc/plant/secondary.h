@@ -58,6 +58,9 @@ NPS_HD void secondary_update_chemistry(PlantState& st, double dt, const StepInpu
 
 // systems/secondary/__init__.py:340-563 and :629-665 — everything of update_system that does not involve the turbine or
 // the condenser.  The chemistry block (:634-665) reads neither, so running it before them is the same arithmetic.
+// CHEMISTRY = false leaves the chemistry block to the caller (the one-thread-per-plant step runs it after the sink half,
+// in the reference's textual order: measured 1-2 % faster there, profiles/r02_ab_memo_chemistry.txt).
+template <bool CHEMISTRY>
 NPS_HD void secondary_update_source(PlantState& st, const PlantParams& p, const PrimaryConditions& pc, double load_demand,
                                     double cooling_water_temp, double dt, const StepInput& in, SecHandoff& h) {
     SecondaryState& S = st.sec;
@@ -120,9 +123,7 @@ NPS_HD void secondary_update_source(PlantState& st, const PlantParams& p, const 
     S.total_feedwater_flow = fwr.total_flow_rate;
     S.operating_hours += dt / 3600.0;
 
-#if !defined(NPS_CHEM_LAST)
-    secondary_update_chemistry(st, dt, in);
-#endif
+    if (CHEMISTRY) secondary_update_chemistry(st, dt, in);
 
     S.total_steam_flow = total_steam_flow;
     S.total_heat_transfer = total_heat_transfer;

@@ -137,26 +137,25 @@ NPS_HD void turbine_lubrication_prestep(TurbineState& T, const PlantParams& p, d
     const LubLimits lim = {p.tl_contamination_limit, p.tl_acidity_limit, p.tl_moisture_limit, p.tl_viscosity_change_limit};
     lub_update_oil_quality(T.lub, TBL_NCOMP, lim, system_oil_temp, contamination_input, moisture_input, dt);
     // update_component_wear with TurbineBearingLubricationSystem.calculate_component_wear (:261-329)
-    PowMemo mspeed, mload;
     for (int c = 0; c < TBL_NCOMP; ++c) {
         const LubComponent k = turb_lub_component(c);
         double rate;
         if (c == TBL_HP) {
             double stf = py_max(1.0, (b_temp[0] - 70.0) / 20.0);
             double lfa = b_load_factor[0] * 1.2;
-            rate = (k.base_wear_rate * py_pow_memo(lfa, k.load_wear_exponent, mload) * py_pow_memo(speed_factor, k.speed_wear_exponent, mspeed) * stf);
+            rate = (k.base_wear_rate * py_pow(lfa, k.load_wear_exponent) * py_pow(speed_factor, k.speed_wear_exponent) * stf);
         } else if (c == TBL_LP) {
             double mf = py_max(1.0, (1.0 - 0.99) * 10.0);
             double tf = py_max(1.0, (b_temp[1] - 60.0) / 25.0);
-            rate = (k.base_wear_rate * py_pow_memo(b_load_factor[1], k.load_wear_exponent, mload) *
-                    py_pow_memo(speed_factor, k.speed_wear_exponent, mspeed) * mf * tf);
+            rate = (k.base_wear_rate * py_pow(b_load_factor[1], k.load_wear_exponent) *
+                    py_pow(speed_factor, k.speed_wear_exponent) * mf * tf);
         } else if (c == TBL_THRUST) {
             double axial = b_load_factor[2] * 1.0;
             double tf = py_max(1.0, (b_temp[2] - 50.0) / 30.0);
-            rate = (k.base_wear_rate * py_pow_memo(axial, k.load_wear_exponent, mload) * py_pow_memo(speed_factor, k.speed_wear_exponent, mspeed) * tf);
+            rate = (k.base_wear_rate * py_pow(axial, k.load_wear_exponent) * py_pow(speed_factor, k.speed_wear_exponent) * tf);
         } else if (c == TBL_SEAL) {
             double cf = 1.0 + T.lub.oil_contamination_level / 10.0;
-            rate = (k.base_wear_rate * py_pow_memo(1.0, k.load_wear_exponent, mload) * cf);
+            rate = (k.base_wear_rate * py_pow(1.0, k.load_wear_exponent) * cf);
         } else {
             rate = (k.base_wear_rate * 1.0 * 1.0);
         }
