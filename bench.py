@@ -244,6 +244,21 @@ def _bind_to_gpu_numa_node(torch, local: int):
     return None
 
 
+class _StdoutToStderr:
+    """NCCL prints its version banner on stdout when NCCL_DEBUG asks for it; rank 0's stdout carries exactly one JSON
+    line, so file descriptor 1 points at stderr while the process group and its communicator come up."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -275,7 +290,10 @@ def main():
     numa_node = _bind_to_gpu_numa_node(torch, local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        with _StdoutToStderr():
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
     W = max(3, args.warmup)
     K = args.steps
     n = args.plants_per_gpu

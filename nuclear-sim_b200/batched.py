@@ -260,7 +260,8 @@ class BatchedNuclearPlantSimulator:
         g["n_events"].zero_()
         torch.cuda.current_stream(self.device).synchronize()
         ev = g["host"][:n].numpy().view(EVENT_DTYPE).reshape(-1).copy()
-        return ev[np.lexsort((ev["row"], ev["plant"], ev["step"]))]
+        key = (ev["step"].astype(np.int64) << 44) | (ev["plant"].astype(np.int64) << 12) | ev["row"].astype(np.int64)
+        return ev[np.argsort(key, kind="stable")]
 
     @property
     def first_scram_step(self) -> torch.Tensor:

@@ -532,7 +532,12 @@ class BatchedAutoMaintenance:
             if timers is not None:      # attribute the wall clock: step kernel (synchronised) vs everything after it
                 getattr(sim, "synchronize", lambda: None)()
                 c1 = _time.perf_counter()
-            self.handle_step_events(sim.drain_step_events())
+            if timers is not None:
+                c_d0 = _time.perf_counter()
+            ev_in_launch = sim.drain_step_events()
+            if timers is not None:
+                timers["event_drain"] = timers.get("event_drain", 0.0) + (_time.perf_counter() - c_d0)
+            self.handle_step_events(ev_in_launch)
             if on_gate:
                 self.update(t_end)
                 self.check(t_end)
@@ -641,6 +646,7 @@ class ColumnarAutoMaintenance(BatchedAutoMaintenance):
             return act_of[name]
         R = len(rows)
         self.row_comp = np.array([comp_of[r.component_id] for r in rows], dtype=np.int64)
+        assert (np.diff(self.row_comp) >= 0).all(), "threshold rows of one component must be contiguous in the table"
         max_rules = max([len(s[0]) for s in self._single] + [1])
         self.rule_thr = np.full((R, max_rules), np.inf)
         self.rule_act = np.zeros((R, max_rules), dtype=np.int64)
@@ -675,6 +681,10 @@ class ColumnarAutoMaintenance(BatchedAutoMaintenance):
         self.event_cols: List[dict] = []
         # rows whose cooldown a performed action re-arms (record_maintenance_result path, head_quirks=False)
         self._reset_rows: Dict[tuple, List[int]] = {}
+        # wall-clock split of the bookkeeping: pure host work (numpy) vs calls that wait for the device
+        # (event drains, the maintenance kernel with its copies, the gate-step flag kernel)
+        self.seconds_host = 0.0
+        self.seconds_device_calls = 0.0
 
     def _refresh_action_tables(self):
         np = self.np
@@ -711,12 +721,15 @@ class ColumnarAutoMaintenance(BatchedAutoMaintenance):
         return made
 
     def check(self, t_minutes: float):
+        import time as _time
         if not hasattr(self.sim, "check_thresholds_events"):
             return super().check(t_minutes)
         if getattr(self.sim, "_mon", None) is None:
             self.sim.enable_monitor()
+        c0 = _time.perf_counter()
         self.sim.check_thresholds_events()
         ev = self.sim.drain_step_events()
+        self.seconds_device_calls += _time.perf_counter() - c0
         if len(ev) == 0:
             return 0
         return self._process_arrays(t_minutes, ev["plant"].astype(self.np.int64), ev["row"].astype(self.np.int64), ev["value"])
@@ -731,11 +744,23 @@ class ColumnarAutoMaintenance(BatchedAutoMaintenance):
 
     def _process_arrays(self, t, plant, row, value) -> int:
         """One step's violations (sorted by (plant, row)) -> events, decisions, work orders."""
+        import time as _time
+        c0 = _time.perf_counter()
+        try:
+            return self._process_arrays_impl(t, plant, row, value)
+        finally:
+            self.seconds_host += _time.perf_counter() - c0
+
+    def _process_arrays_impl(self, t, plant, row, value) -> int:
         np = self.np
         comp = self.row_comp[row]
         gkey = plant * self.n_comp + comp
-        order = np.lexsort((row, comp, plant))          # components of a plant in table order, rows in config order
-        plant, row, value, comp, gkey = plant[order], row[order], value[order], comp[order], gkey[order]
+        # components of a plant in table order, rows in config order.  A component's rows are contiguous in the table, so
+        # events that arrive sorted by (plant, row) - drain_step_events() delivers them that way - are already in order
+        skey = plant * 4096 + row
+        if len(skey) > 1 and not bool((skey[1:] >= skey[:-1]).all()):
+            order = np.argsort(skey, kind="stable")
+            plant, row, value, comp, gkey = plant[order], row[order], value[order], comp[order], gkey[order]
         first = np.concatenate([[True], gkey[1:] != gkey[:-1]])
         starts = np.flatnonzero(first)
         counts = np.diff(np.concatenate([starts, [len(gkey)]]))
@@ -808,6 +833,14 @@ class ColumnarAutoMaintenance(BatchedAutoMaintenance):
 
     # -- due work orders -> device -------------------------------------------------------------------------------------
     def update(self, t_minutes: float):
+        import time as _time
+        c0, d0 = _time.perf_counter(), self.seconds_device_calls
+        try:
+            return self._update_impl(t_minutes)
+        finally:
+            self.seconds_host += (_time.perf_counter() - c0) - (self.seconds_device_calls - d0)
+
+    def _update_impl(self, t_minutes: float):
         np = self.np
         if not self.gate_open(t_minutes):
             return 0
@@ -828,7 +861,10 @@ class ColumnarAutoMaintenance(BatchedAutoMaintenance):
         d_act = P["act"][due]
         req = np.stack([P["plant"][due], self.comp_target[P["comp"][due]], self.act_code[d_act],
                         np.where(self.act_is_bearing[d_act], self.sub_arg[P["sub"][due]], 0)], axis=1).astype(np.int32)
+        import time as _time
+        c0 = _time.perf_counter()
         status = np.asarray(self.sim.apply_maintenance(req))
+        self.seconds_device_calls += _time.perf_counter() - c0
         if (status == 2).any():
             bad = int(np.flatnonzero(status == 2)[0])
             raise NotImplementedError(f"perform_maintenance on {self.comp_ids[int(P['comp'][due][bad])]} is not restated on the device")

@@ -62,11 +62,14 @@ def main():
     if world > 1:
         dist.barrier()
     timers = {}
+    maint.seconds_host = maint.seconds_device_calls = 0.0
     t0 = time.perf_counter()
     maint.advance(steps, timers=timers)
     torch.cuda.synchronize()
     total = time.perf_counter() - t0
-    t = torch.tensor([total, timers["step_kernel"], timers["bookkeeping"]], dtype=torch.float64, device=f"cuda:{local}")
+    dev_calls = maint.seconds_device_calls + timers.get("event_drain", 0.0)
+    t = torch.tensor([total, timers["step_kernel"], timers["bookkeeping"], maint.seconds_host, dev_calls], dtype=torch.float64,
+                     device=f"cuda:{local}")
     counts = torch.tensor([maint.n_work_orders_created, maint.n_work_orders_executed, sum(len(c["plant"]) for c in maint.event_cols)],
                           dtype=torch.int64, device=f"cuda:{local}")
     if world > 1:
@@ -74,7 +77,7 @@ def main():
         dist.all_reduce(counts, op=dist.ReduceOp.SUM)
     summary = shard.gather_summaries(["fw.pump[0].lub.oil_level", "pri.power_level"])
     if rank == 0:
-        total, t_dev, t_host = (float(x) for x in t)
+        total, t_dev, t_host, t_numpy, t_devcalls = (float(x) for x in t)
         print(json.dumps({
             "workload": "cfg5: long-horizon maintenance degradation, dt=5 min, launches cut at the 15-min gate, full loop",
             "n_gpus": world, "plants": world * n, "plants_per_gpu": n, "simulated_hours": args.hours, "steps": steps,
@@ -82,6 +85,10 @@ def main():
             "plant_steps_per_s_whole_loop": world * n * steps / total, "seconds_total_max_over_ranks": total,
             "seconds_step_kernel_max_over_ranks": t_dev, "seconds_bookkeeping_max_over_ranks": t_host,
             "bookkeeping_over_kernel": t_host / t_dev,
+            "seconds_host_numpy_max_over_ranks": t_numpy, "host_numpy_over_kernel": t_numpy / t_dev,
+            "seconds_device_side_of_bookkeeping_max_over_ranks": t_devcalls,
+            "split": "bookkeeping = host numpy (decisions, dedupe, work-order columns) + device-side calls (event drains, "
+                     "maintenance kernel with its request / status copies, gate-step flag kernel)",
             "threshold_events": int(counts[2]), "work_orders_created": int(counts[0]), "work_orders_executed": int(counts[1]),
             "by_action_rank0": maint.counts_by_action(), "mean_oil_level_pump0": float(summary[:, 0].mean()),
             "bookkeeping": "ColumnarAutoMaintenance (numpy columns; in-launch threshold events + event-list flag kernel at gate steps)"}))
