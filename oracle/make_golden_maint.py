@@ -189,3 +189,25 @@ if __name__ == "__main__":
         effects()
     if "scenarios" in what:
         scenarios()
+
+
+def state_log_csv(T=12):
+    """tests/golden/ref_state_log_oil_top_off.csv: the reference's OWN wide state log (StateManager.export_to_csv,
+    state_manager.py:296-386: `time` + 788 columns) for the first T steps of the maint_oil_top_off scenario — the same
+    plant, the same noise stream, so row t belongs to states[t] of tests/golden/maint_oil_top_off.npz.  The GPU export
+    test compares the device ring buffer's CSV with this file."""
+    rp, cfg = runner_style_plant("oil_top_off", dt=5.0)
+    rng = np.random.RandomState(2024)
+    for t in range(T):
+        z = np.array([0.0, rng.standard_normal(), rng.random_sample(), rng.random_sample(), rng.random_sample()])
+        rp.step(8, 1.0, z)
+    out = os.path.join(GOLDEN, "ref_state_log_oil_top_off.csv")
+    with R.quiet():
+        rp.sim.state_manager.export_to_csv(out)
+    import csv
+    rows = list(csv.reader(open(out)))
+    print(f"[state-log] {out}: {len(rows) - 1} rows x {len(rows[0])} columns")
+
+
+if __name__ == "__main__" and "state_log" in sys.argv[1:]:
+    state_log_csv()

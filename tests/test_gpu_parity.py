@@ -582,6 +582,45 @@ def test_batched_export_trajectory_in_reference_schema(tmp_path):
     assert open(tmp_path / "ring.csv").read() == open(tmp_path / "store.csv").read()
 
 
+def test_device_export_equals_the_reference_state_log(tmp_path):
+    """tests/golden/ref_state_log_oil_top_off.csv is the reference's own StateManager.export_to_csv of the first 12 steps
+    of the maint_oil_top_off scenario.  The device path — step kernel, TMA ring-buffer rows of every exportable field,
+    export_trajectory for one plant of a batch — must write the same header and, row by row, the same 788 values
+    (numbers to 1e-9, status strings and booleans exactly)."""
+    import csv
+    import torch
+    g = np.load(os.path.join(U.GOLDEN, "maint_oil_top_off.npz"), allow_pickle=False)
+    ref = list(csv.reader(open(os.path.join(U.GOLDEN, "ref_state_log_oil_top_off.csv"), newline="")))
+    T = len(ref) - 1
+    n, me = 6, 4
+    rng = np.random.RandomState(9)
+    st = np.tile(g["state0"], (n, 1)) * (1.0 + 1e-3 * rng.standard_normal((n, 1)))
+    st[me] = g["state0"]
+    sim = _sim(st, g["params"])
+    assert sim.set_logged_columns(None, ring_rows=16) > 600
+    for t in range(T):
+        z = np.tile(g["noise"][t][None, :, None], (1, 1, n))          # [1, 5, n]
+        sim.step(noise=torch.from_numpy(np.ascontiguousarray(z)), K=1)
+        sim.log_row()
+    assert sim.export_trajectory(me, str(tmp_path / "ours.csv")) == T
+    ours = list(csv.reader(open(tmp_path / "ours.csv", newline="")))
+    assert ours[0] == ref[0] and len(ours[0]) == 789
+    bad = []
+    for r in range(1, T + 1):
+        for j in range(1, 789):
+            a, b = ours[r][j], ref[r][j]
+            if a == b:
+                continue
+            try:
+                fa, fb = float(a), float(b)
+            except ValueError:
+                bad.append((r, ref[0][j], a, b))
+                continue
+            if not abs(fa - fb) <= 1e-9 * max(1e-6, abs(fb)) * r:
+                bad.append((r, ref[0][j], a, b))
+    assert not bad, f"{len(bad)} cells differ from the reference's state log, e.g. {bad[:5]}"
+
+
 # ---- in-launch monitoring: the step of every discrete event does not depend on how steps are fused into launches ---
 def _monitored_run(g, kmax, table_cfg=None):
     """Replay a trajectory fixture with launches of up to kmax substeps and the in-launch monitor; returns the simulator,
