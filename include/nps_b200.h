@@ -116,7 +116,7 @@ int nps_device_rng_draws(uint64_t seed, uint64_t plant, uint64_t step, double* o
  * specialisations, csrc/plant/fastpow.h for positive finite bases, libdevice pow otherwise), device arrays. */
 int nps_selftest_pow(const double* d_x, const double* d_y, double* d_out, int64_t n, void* cuda_stream);
 
-/* Launch shape of nps_step for batches below ~33 K plants (above, one thread per plant fills the GPU):
+/* Launch shape of nps_step for batches up to 148 x 4 x 32 = 18,944 plants (larger batches always run one thread per plant):
  *   0 (default)  two threads per plant — one advances primary side / feedwater / steam generators / chemistry, the other
  *                the turbine and condenser one substep behind it (they are pure sinks of the step's dataflow), so the
  *                dependency chain per substep is the longer half instead of the sum;

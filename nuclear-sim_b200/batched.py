@@ -282,7 +282,7 @@ class BatchedNuclearPlantSimulator:
         return {w: g["watch_step"][i] for i, w in enumerate(g["watch"])}
 
     def set_small_batch_shape(self, shape: int) -> None:
-        """Launch shape below ~33 K plants: 0 two threads per plant (source / sink halves pipelined by one substep,
+        """Launch shape up to 18 944 plants: 0 two threads per plant (source / sink halves pipelined by one substep,
         default), 1 one thread per plant.  Bit-identical results (tests/test_gpu_parity.py)."""
         _clib.check(self.L.nps_set_small_batch_shape(self._h, int(shape)))
 

@@ -91,7 +91,7 @@ struct nps_handle {
     int pipe_k = 0; int64_t pipe_count = 0;
     RngConfig rng = {0, 0, 0, 0, 0};
     int n_sms = 148; bool log_row_tile_only = false;
-    int small_shape = 0;   // batches below kLargeBatch: 0 split kernel (two threads per plant), 1 one thread per plant (NPS_SMALL_SHAPE=1)   // NPS_LOG_ROW_TILE=1 forces the shared-memory tile kernel
+    int small_shape = 0;   // batches up to n_sms x 4 x 32 plants: 0 split kernel (two threads per plant), 1 one thread per plant (NPS_SMALL_SHAPE=1)   // NPS_LOG_ROW_TILE=1 forces the shared-memory tile kernel
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -308,11 +308,10 @@ struct SplitShared {
     double b2a[3][kSplitPlants];            // electrical output, thermal efficiency, condenser pressure: final observation / reward
 };
 
-// MINBLOCKS 1: no register cap (216 registers, 4 blocks per SM) for up to 148 x 4 x 32 = 18,944 plants; MINBLOCKS 7: 144
-// registers, 7 blocks per SM, so that batches up to 33,152 plants (the 2-GPU share of the 65,536-plant workload) are
-// still one wave.
-template <int MINBLOCKS>
-__global__ void __launch_bounds__(2 * kSplitPlants, MINBLOCKS)
+// No register cap (224 registers, 4 blocks per SM): one wave up to 148 x 4 x 32 = 18,944 plants.  A 128-register
+// variant that keeps 33,152 plants in one wave was measured and dropped: at 32,768 plants it reaches 6.9e7 plant-steps/s
+// against 1.0e8 for one uncapped thread per plant (profiles/r02_bench_n1.json small_batch), so larger batches use that.
+__global__ void __launch_bounds__(2 * kSplitPlants, 1)
 nps_step_split_kernel(const __grid_constant__ PlantParams prm, const __grid_constant__ StepArgs a) {
     __shared__ Threshold s_rows[kMaxSharedRows];
     __shared__ SplitShared sh;
@@ -723,8 +722,7 @@ int nps_create(int64_t n_plants, int device, nps_handle** out) {
     // one-warp blocks: several of them share an SM, each with its 4 KB threshold-row stage; PreferL1 alone would leave
     // shared memory for a single block per SM (measured: 8 192 plants ran as two waves)
     NPS_CUDA(cudaFuncSetAttribute(nps_step_kernel<32, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 25));
-    NPS_CUDA(cudaFuncSetAttribute(nps_step_split_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 40));
-    NPS_CUDA(cudaFuncSetAttribute(nps_step_split_kernel<7>, cudaFuncAttributePreferredSharedMemoryCarveout, 60));
+    NPS_CUDA(cudaFuncSetAttribute(nps_step_split_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 40));
 #endif
     *out = h;
     return 0;
@@ -764,11 +762,10 @@ static int launch_step(nps_handle* h, const StepArgs& a, cudaStream_t s) {
     nps_step_kernel<NPS_STEP_BLOCK, NPS_STEP_MINBLOCKS><<<(int)((h->n + NPS_STEP_BLOCK - 1) / NPS_STEP_BLOCK), NPS_STEP_BLOCK, 0, s>>>(h->params, a);
 #else
     if (h->n >= kLargeBatch) nps_step_kernel<448, 1><<<(int)((h->n + 447) / 448), 448, 0, s>>>(h->params, a);
-    else if (h->small_shape == 1) nps_step_kernel<32, 1><<<(int)((h->n + 31) / 32), 32, 0, s>>>(h->params, a);
     else {
         const int blocks = (int)((h->n + kSplitPlants - 1) / kSplitPlants);
-        if (blocks <= h->n_sms * 4) nps_step_split_kernel<1><<<blocks, 2 * kSplitPlants, 0, s>>>(h->params, a);
-        else nps_step_split_kernel<7><<<blocks, 2 * kSplitPlants, 0, s>>>(h->params, a);
+        if (h->small_shape == 0 && blocks <= h->n_sms * 4) nps_step_split_kernel<<<blocks, 2 * kSplitPlants, 0, s>>>(h->params, a);
+        else nps_step_kernel<32, 1><<<(int)((h->n + 31) / 32), 32, 0, s>>>(h->params, a);
     }
 #endif
     NPS_CUDA(cudaGetLastError());

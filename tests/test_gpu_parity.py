@@ -832,11 +832,11 @@ def test_split_launch_shape_is_bit_identical_to_one_thread_per_plant(name):
     assert torch.equal(sims[0].first_scram_step, sims[1].first_scram_step) and torch.equal(sims[0].status, sims[1].status)
 
 
-@pytest.mark.parametrize("n,k", [(4099, 6), (20011, 3)])
+@pytest.mark.parametrize("n,k", [(4099, 6), (18913, 3)])
 def test_split_launch_shape_on_a_ragged_random_batch(oracle_lib, n, k):
-    """4 099 plants (ragged last block; no register cap) and 20 011 plants (the register-capped variant that keeps up to
-    33 152 plants in one wave), random actions and noise, 3 fused launches: split shape == one thread per plant bitwise,
-    and both within tolerance of the host oracle."""
+    """4 099 and 18 913 plants (ragged last block; the second is just under the split shape's one-wave limit of 18 944),
+    random actions and noise, 3 fused launches: split shape == one thread per plant bitwise, and both within tolerance
+    of the host oracle."""
     import torch
     from nuclear_sim_b200 import load_snapshot
     from nuclear_sim_b200 import scenarios as sc
