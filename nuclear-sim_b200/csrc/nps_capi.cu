@@ -164,44 +164,91 @@ __device__ __forceinline__ bool sink_owns(int f) {
 
 // role: -1 whole plant (one thread per plant), 0 source half, 1 sink half (evaluates only the rows / watched fields it owns;
 // `now` is the plant clock after the step, which a sink half gets from its source half)
-__device__ __noinline__ void monitor_substep(const PlantState& st, const MonitorArgs& mon, const Threshold* rows,
+// The monitor reads ~100 scattered fields of the frame once per substep.  NPS_MON_LD selects the cache operator of those
+// loads: 0 plain, 1 ld.local.cs (streaming: evict first), 2 ld.local.lu (last use) - so that they do not push the lines
+// the next substep starts with out of L1 (profiles/r02_monitor_cost.txt).
+#ifndef NPS_MON_LD
+#define NPS_MON_LD 0
+#endif
+__device__ __forceinline__ double mon_load(const double* __restrict__ sv, int f) {
+#if NPS_MON_LD == 0
+    return sv[f];
+#else
+    double v;
+    unsigned long long a;
+    asm volatile("cvta.to.local.u64 %0, %1;" : "=l"(a) : "l"(sv + f));
+#if NPS_MON_LD == 1
+    asm volatile("ld.local.cs.f64 %0, [%1];" : "=d"(v) : "l"(a));
+#else
+    asm volatile("ld.local.lu.f64 %0, [%1];" : "=d"(v) : "l"(a));
+#endif
+    return v;
+#endif
+}
+
+__device__ __noinline__ void monitor_substep(const PlantState& st, const MonitorArgs& mon_ref, const Threshold* __restrict__ rows,
                                              int64_t n, int64_t p, int k, bool last, unsigned warp_mask, unsigned step_status,
-                                             unsigned& seen_watch, int role = -1, double now_in = 0.0) {
-    const double* sv = reinterpret_cast<const double*>(&st);
+                                             unsigned& seen_watch_ref, int role = -1, double now_in = 0.0) {
+    const MonitorArgs mon = mon_ref;          // by value: the stores below cannot alias the argument record
+    unsigned seen_watch = seen_watch_ref;
+    const double* __restrict__ sv = reinterpret_cast<const double*>(&st);
     const int32_t step = (int32_t)(mon.step0 + k);
     if (step_status) {
         if (mon.status) mon.status[p] |= step_status;
         if ((step_status & kStatusScram) && mon.first_scram_step && mon.first_scram_step[p] < 0) mon.first_scram_step[p] = step;
         if ((step_status & kStatusNanReset) && mon.first_nan_reset_step && mon.first_nan_reset_step[p] < 0) mon.first_nan_reset_step[p] = step;
     }
-    for (int w = 0; w < mon.n_watch; ++w) {
-        if (role >= 0 && sink_owns(mon.watch_fields[w]) != (role == 1)) continue;
-        if (!((seen_watch >> w) & 1u) && sv[mon.watch_fields[w]] != 0.0) {
-            mon.watch_step[(int64_t)w * n + p] = step;
-            seen_watch |= 1u << w;
+    // Watched flags and threshold values are first touches of this substep's freshly written state, i.e. cache misses:
+    // every group of kMonChunk values is loaded with NO control flow between the loads (rows this thread does not own
+    // read field 0 and are masked afterwards), so a group costs one memory round trip instead of eight
+    // (profiles/r02_monitor_cost.txt).
+    constexpr int kMonChunk = 8;
+    for (int w0 = 0; w0 < mon.n_watch; w0 += kMonChunk) {
+        double wv[kMonChunk];
+        int wf[kMonChunk];
+#pragma unroll
+        for (int j = 0; j < kMonChunk; ++j) wf[j] = (w0 + j < mon.n_watch) ? __ldg(mon.watch_fields + w0 + j) : 0;
+#pragma unroll
+        for (int j = 0; j < kMonChunk; ++j) wv[j] = mon_load(sv, wf[j]);
+#pragma unroll
+        for (int j = 0; j < kMonChunk; ++j) {
+            const int w = w0 + j;
+            const bool own = (w < mon.n_watch) && (role < 0 || sink_owns(wf[j]) == (role == 1));
+            if (own && !((seen_watch >> w) & 1u) && wv[j] != 0.0) {
+                mon.watch_step[(int64_t)w * n + p] = step;
+                seen_watch |= 1u << w;
+            }
         }
     }
+    seen_watch_ref = seen_watch;
     if (mon.last_fired && !(last && mon.skip_last_check)) {
         const double now = (role == 1) ? now_in : st.sim.time_minutes;
         const unsigned lane = threadIdx.x & 31u;
-        // rows in groups of kMonChunk: the group's values are independent loads issued back to back (they are first
-        // touches of this substep's freshly written state, i.e. cache misses), then compared; the warp votes ONCE per
-        // group, and only a group in which some lane fired goes through the per-row ballots that build the event list
-        constexpr int kMonChunk = 8;
+        // the warp votes ONCE per group, and only a group in which some lane fired goes through the per-row ballots
+        // that build the event list
         for (int j0 = 0; j0 < mon.n_live; j0 += kMonChunk) {
             double v[kMonChunk];
-            unsigned hit = 0;
+            int fld[kMonChunk];
+            unsigned mine = 0, hit = 0;
 #pragma unroll
             for (int j = 0; j < kMonChunk; ++j) {
-                v[j] = 0.0;
-                if (j0 + j < mon.n_live) {
-                    const int f = rows[j0 + j].field;
-                    const bool mine = role < 0 || ((f >= 0 && sink_owns(f)) == (role == 1));   // derived rows: source half
-                    if (mine) {
-                        v[j] = (f >= 0) ? sv[f] : derived_from_state(st, f);
-                        if (threshold_compare(rows[j0 + j].cmp, v[j], rows[j0 + j].value)) hit |= 1u << j;
-                    }
-                }
+                const int f = (j0 + j < mon.n_live) ? rows[j0 + j].field : -1;      // -1: padding
+                fld[j] = f;
+                const bool own = (f != -1) && (role < 0 || ((f >= 0 && sink_owns(f)) == (role == 1)));   // derived rows: source half
+                mine |= (own ? 1u : 0u) << j;
+            }
+#pragma unroll
+            for (int j = 0; j < kMonChunk; ++j) v[j] = mon_load(sv, (((mine >> j) & 1u) && fld[j] >= 0) ? fld[j] : 0);
+#pragma unroll
+            for (int j = 0; j < kMonChunk; ++j) {
+                if (!((mine >> j) & 1u)) continue;
+                if (fld[j] < -1) v[j] = derived_from_state(st, fld[j]);
+                const double x = rows[j0 + j].value;
+                const int c = rows[j0 + j].cmp;
+                const double d = fabs(v[j] - x);
+                const bool fire = (c == 0 && v[j] > x) || (c == 1 && v[j] < x) || (c == 2 && v[j] >= x) || (c == 3 && v[j] <= x) ||
+                                  (c == 4 && d < 1e-3) || (c == 5 && d >= 1e-3);      // _check_threshold_condition
+                hit |= (fire ? 1u : 0u) << j;
             }
             if (!__ballot_sync(warp_mask, hit != 0)) continue;
 #pragma unroll
