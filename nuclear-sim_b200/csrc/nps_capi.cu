@@ -387,7 +387,13 @@ NPS_PRAGMA_UNROLL(NPS_COPY_UNROLL)
     if (mon.enabled && valid)
         for (int w = 0; w < mon.n_watch; ++w) if (mon.watch_step[(int64_t)w * n + p] >= 0) seen_watch |= 1u << w;
     const int K = a.k_substeps;
+#if defined(NPS_SPLIT_TIMING)
+    long long busy = 0;      // tuning build: cycles each half spends working (not waiting at the barrier)
+#endif
     for (int k = 0; k <= K; ++k) {
+#if defined(NPS_SPLIT_TIMING)
+        const long long c0 = clock64();
+#endif
         if (role == 0 && k < K && valid) {
             StepInput in;
             in.action = a.action ? (int)a.action[(int64_t)k * n + p] : (int)ACT_NO_ACTION;
@@ -433,8 +439,14 @@ NPS_PRAGMA_UNROLL(NPS_COPY_UNROLL)
                 }
             }
         }
+#if defined(NPS_SPLIT_TIMING)
+        busy += clock64() - c0;
+#endif
         __syncthreads();
     }
+#if defined(NPS_SPLIT_TIMING)
+    if (blockIdx.x == 0 && lane == 0) printf("[split timing] role %d busy cycles per substep %lld (K = %d)\n", role, busy / K, K);
+#endif
     if (valid) {
 NPS_PRAGMA_UNROLL(NPS_COPY_UNROLL)
         for (int f = 0; f < kNState; ++f) if (sink_owns(f) == (role == 1)) slab[(int64_t)f * n + p] = sv[f];
