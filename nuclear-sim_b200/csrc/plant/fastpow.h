@@ -118,6 +118,88 @@ NPS_HD bool nps_pow_pos(double x, double y, double& out) {
     return nps_pow_exp(y, Lh, Ll, out);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Table-driven variant (tuning builds with -DNPS_POW_TABLES; NOT the shipped path: it measured 2 % slower on B200 because
+// its table loads miss L1 under the frame's streaming traffic, profiles/r02_ab_pow.txt): the same double-double log / exp structure with two 128-entry tables
+// (csrc/tools/make_pow_tables.py -> fastpow_tables.inc) in place of the division + 12-term atanh series and the
+// degree-14 exponential series:
+//   x = 2^e z, z in [1, 2);  i = 7 leading mantissa bits;  r = z * invc_i - 1 (one FMA, |r| < 2^-8);
+//   log x = e ln2 + logc_i + log1p(r), log1p by its series to r^7, accumulated as hi + lo (absolute error ~2^-68);
+//   (Ph, Pl) = y * log x;  k = round(Ph * 128 / ln2), r' = Ph - k ln2/128 + Pl (|r'| < 0.0028);
+//   x^y = 2^(k >> 7) * t_(k & 127) * (1 + r' + ... + r'^5 / 120).
+// ------------------------------------------------------------------------------------------------
+#include "fastpow_tables.inc"
+#if defined(__CUDACC__)
+__device__ const double nps_pow_log_table_dev[128 * 3] = NPS_POW_LOG_TABLE;
+__device__ const double nps_pow_exp_table_dev[128 * 2] = NPS_POW_EXP_TABLE;
+#endif
+static const double nps_pow_log_table_host[128 * 3] = NPS_POW_LOG_TABLE;
+static const double nps_pow_exp_table_host[128 * 2] = NPS_POW_EXP_TABLE;
+#if defined(__CUDA_ARCH__)
+#define NPS_LOGT(i) __ldg(nps_pow_log_table_dev + (i))
+#define NPS_EXPT(i) __ldg(nps_pow_exp_table_dev + (i))
+#else
+#define NPS_LOGT(i) nps_pow_log_table_host[i]
+#define NPS_EXPT(i) nps_pow_exp_table_host[i]
+#endif
+
+NPS_HD bool nps_pow_log_tab(double x, double& Lh_out, double& Ll_out) {
+    const long long ix = nps_bits(x);
+    const int be = (int)((ix >> 52) & 0x7ff);
+    if (!(ix > 0) || (unsigned)(be - 23) >= 2000u) return false;
+    const int e = be - 1023;
+    const int i = (int)((ix >> 45) & 127);
+    const double z = nps_from_bits((ix & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);     // [1, 2)
+    const double invc = NPS_LOGT(3 * i), logc_hi = NPS_LOGT(3 * i + 1), logc_lo = NPS_LOGT(3 * i + 2);
+    const double r = fma(z, invc, -1.0);
+    const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
+    const double ed = (double)e;
+    const double a = ed * LN2_HI;                   // exact: LN2_HI has 21 trailing zero bits
+    const double s1 = a + logc_hi;
+    const double e1 = (a - s1) + logc_hi;           // fast two-sum: a == 0 or |a| >= ln2 > logc_hi
+    const double s2 = s1 + r;
+    const double bb = s2 - s1;
+    const double e2 = (s1 - (s2 - bb)) + (r - bb);  // two-sum (r may exceed s1 when e == 0 and i is small)
+    const double r2 = r * r;
+    // log1p(r) - r = -r^2/2 + r^3/3 - r^4/4 + r^5/5 - r^6/6 + r^7/7
+    const double q = fma(r, fma(r, fma(r, fma(r, 1.0 / 7, -1.0 / 6), 1.0 / 5), -1.0 / 4), 1.0 / 3);
+    const double tail = fma(r2 * r, q, -0.5 * r2);
+    const double lo = ((e1 + e2) + fma(ed, LN2_LO, logc_lo)) + tail;
+    const double Lh = s2 + lo;
+    Lh_out = Lh;
+    Ll_out = (s2 - Lh) + lo;
+    return true;
+}
+
+NPS_HD bool nps_pow_exp_tab(double y, double Lh, double Ll, double& out) {
+    if (!(fabs(y) < 1024.0)) return false;
+    const double Ph = y * Lh;
+    const double Pl = fma(y, Lh, -Ph) + y * Ll;
+    if (!(fabs(Ph) < 64.0)) return false;
+    const double magic = 6755399441055744.0;        // 1.5 * 2^52
+    const double kd = (Ph * NPS_POW_128_LN2 + magic) - magic;
+    const long long k = (long long)kd;
+    const double r1 = fma(-kd, NPS_POW_LN2_128_HI, Ph);            // exact: |kd| < 2^14, 24 trailing zero bits in the constant
+    const double rr = fma(-kd, NPS_POW_LN2_128_LO, r1) + Pl;
+    const int j = (int)(k & 127);
+    const double t_hi = NPS_EXPT(2 * j), t_lo = NPS_EXPT(2 * j + 1);
+    const double r2 = rr * rr;
+    // exp(rr) - 1 = rr + rr^2 (1/2 + rr/6 + rr^2 (1/24 + rr/120))
+    const double p = fma(r2, fma(r2, fma(rr, 1.0 / 120, 1.0 / 24), fma(rr, 1.0 / 6, 0.5)), rr);
+    const double res = t_hi + fma(t_hi, p, t_lo);
+    out = nps_from_bits(nps_bits(res) + ((k >> 7) << 52));
+    return true;
+}
+
+NPS_HD bool nps_pow_pos_tab(double x, double y, double& out) {
+    double Lh, Ll;
+    if (!(fabs(y) < 1024.0) || !nps_pow_log_tab(x, Lh, Ll)) return false;
+    return nps_pow_exp_tab(y, Lh, Ll, out);
+}
+
+#undef NPS_LOGT
+#undef NPS_EXPT
 #undef nps_pow_tab
 #undef NPS_POW_TAB
 }  // namespace nps

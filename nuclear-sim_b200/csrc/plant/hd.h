@@ -116,7 +116,13 @@ namespace nps {
 NPS_HD_SHARED double nps_pow_general(double x, double y) {
 #if defined(__CUDA_ARCH__) && !defined(NPS_LIBDEVICE_POW)
     double r;
-    if (nps_pow_pos(x, y, r)) return r;     // positive finite base, moderate result: fastpow.h (<= 1.1 ulp)
+#if defined(NPS_POW_TABLES)
+    // table-driven form: 0.50 ulp and ~30 fewer instructions per call, but its five table loads miss L1 under the state
+    // frame's streaming traffic: measured 2 % SLOWER than the series form (profiles/r02_ab_pow.txt) - tuning builds only
+    if (nps_pow_pos_tab(x, y, r)) return r;
+#else
+    if (nps_pow_pos(x, y, r)) return r;     // positive finite base, moderate result: fastpow.h series form (<= 1.1 ulp)
+#endif
 #endif
     return pow(x, y);
 }
@@ -124,6 +130,9 @@ NPS_HD double py_pow(double x, double y) {
 #if defined(__CUDA_ARCH__) && !defined(NPS_GENERIC_POW)
     if (y == 2.0) return x * x;
     if (y == 1.0) return x;
+#if defined(NPS_POW_ONE_SHORTCUT)
+    if (x == 1.0) return 1.0;               // pow(1, y) == 1 for every y (C99 F.9.4.4): the impeller / seal wear laws call it
+#endif
     if (x > 0.0 && x < 1.7e308) {
         if (y == 0.5) return sqrt(x);
         // two correctly-rounded operations: <= 1 ulp from the exact power, inside libdevice pow's own 2-ulp bound

@@ -76,6 +76,15 @@ extern "C" int nps_oracle_fastpow(const double* x, const double* y, double* out,
     return 0;
 }
 
+extern "C" int nps_oracle_fastpow_tab(const double* x, const double* y, double* out, unsigned char* taken, int64_t n) {
+    for (int64_t i = 0; i < n; ++i) {
+        double r = 0.0;
+        taken[i] = nps::nps_pow_pos_tab(x[i], y[i], r) ? 1 : 0;
+        out[i] = r;
+    }
+    return 0;
+}
+
 // maintenance effect on ONE plant (array-of-structs state): returns the MaintStatus code
 #include "maintenance.h"
 extern "C" int nps_oracle_apply_maintenance(double* state, const double* params, int target, int action, int arg) {
