@@ -38,7 +38,14 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)            # NCCL's version banner goes to stderr: stdout carries the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+        torch.cuda.synchronize()
+        os.dup2(saved, 1)
+        os.close(saved)
     n, dt = args.plants_per_gpu, 5.0
     s0, params = load_snapshot("pwr3000_oil_top_off_dt5")
     ix = field_index()
