@@ -585,30 +585,48 @@ nps_threshold_events_kernel(const double* __restrict__ slab, const Threshold* __
     __syncthreads();
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = p < n;
+    const int64_t pc = valid ? p : n - 1;             // out-of-range lanes read the last plant and never fire
     const unsigned lane = threadIdx.x & 31u;
-    const double now = valid ? slab[(int64_t)time_field * n + p] : 0.0;
-    for (int j = 0; j < n_live; ++j) {
-        const Threshold th = s_live[j];
-        bool fire = false;
-        double v = 0.0;
-        if (valid) {
-            v = (th.field >= 0) ? slab[(int64_t)th.field * n + p] : threshold_derived(slab, n, p, th.field);
-            fire = threshold_compare(th.cmp, v, th.value);
+    const double now = slab[(int64_t)time_field * n + pc];
+    // eight rows at a time: their values are independent coalesced loads issued together, the warp votes once per
+    // group, and only a group with a violation walks its rows to stamp cooldowns and append events
+    constexpr int kChunk = 8;
+    for (int j0 = 0; j0 < n_live; j0 += kChunk) {
+        double v[kChunk];
+        unsigned hit = 0;
+#pragma unroll
+        for (int j = 0; j < kChunk; ++j) {
+            const int f = (j0 + j < n_live) ? s_live[j0 + j].field : 0;
+            v[j] = slab[(int64_t)(f >= 0 ? f : 0) * n + pc];
+        }
+#pragma unroll
+        for (int j = 0; j < kChunk; ++j) {
+            if (j0 + j >= n_live) break;
+            const Threshold& th = s_live[j0 + j];
+            if (th.field < 0) v[j] = threshold_derived(slab, n, pc, th.field);
+            if (valid && threshold_compare(th.cmp, v[j], th.value)) hit |= 1u << j;
+        }
+        if (!__ballot_sync(0xffffffffu, hit != 0)) continue;
+#pragma unroll
+        for (int j = 0; j < kChunk; ++j) {
+            if (j0 + j >= n_live) break;
+            const Threshold th = s_live[j0 + j];
+            bool fire = (hit >> j) & 1u;
             if (fire) {
                 double* stamp = last_fired + (int64_t)th.row * n + p;
                 if ((now - *stamp) < th.cooldown) fire = false;
                 else *stamp = now;
             }
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, fire);
-        if (m) {
-            const int leader = __ffs(m) - 1;
-            uint32_t base = 0;
-            if ((int)lane == leader) base = atomicAdd(n_events, (uint32_t)__popc(m));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (fire) {
-                const uint32_t slot = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
-                if (slot < event_cap) events[slot] = nps_event{(int32_t)p, th.row, step, 0, v, now};
+            const unsigned m = __ballot_sync(0xffffffffu, fire);
+            if (m) {
+                const int leader = __ffs(m) - 1;
+                uint32_t base = 0;
+                if ((int)lane == leader) base = atomicAdd(n_events, (uint32_t)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (fire) {
+                    const uint32_t slot = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+                    if (slot < event_cap) events[slot] = nps_event{(int32_t)p, th.row, step, 0, v[j], now};
+                }
             }
         }
     }

@@ -85,9 +85,7 @@ def save_checkpoint(sim, path: str, maintenance=None, env=None) -> None:
           "ring": None if lg is None else {"names": list(lg["names"]), "rows": lg["rows"], "n": lg["n"], "ring": lg["ring"].cpu()},
           "maintenance": None, "env": None}
     if maintenance is not None:   # plain-data books; pickled bytes travel as a uint8 tensor so weights_only loading still works
-        books = {"last_check_time": maintenance.last_check_time, "books": maintenance.books, "pending": maintenance._pending,
-                 "created_log": maintenance.created_log, "executed_log": maintenance.executed_log, "event_log": maintenance.event_log}
-        ck["maintenance"] = torch.frombuffer(bytearray(pickle.dumps(books)), dtype=torch.uint8).clone()
+        ck["maintenance"] = torch.frombuffer(bytearray(pickle.dumps(maintenance.state_dict())), dtype=torch.uint8).clone()
     if env is not None:
         ck["env"] = {"gen": env._gen.get_state(), "episode_steps": env.episode_steps.cpu()}
     torch.save(ck, path)
@@ -129,10 +127,7 @@ def load_checkpoint(path: str, device: str = "cuda:0", maintenance_table=None, m
     if ck.get("maintenance") is not None:
         if maint is None:
             raise ValueError("checkpoint holds work-order books: pass maintenance=lambda sim: BatchedAutoMaintenance(sim, table)")
-        books = pickle.loads(bytes(ck["maintenance"].numpy().tobytes()))
-        maint.last_check_time = books["last_check_time"]
-        maint.books, maint._pending = books["books"], books["pending"]
-        maint.created_log, maint.executed_log, maint.event_log = books["created_log"], books["executed_log"], books["event_log"]
+        maint.load_state_dict(pickle.loads(bytes(ck["maintenance"].numpy().tobytes())))
     if env is not None and ck.get("env") is not None:
         env.sim = sim
         env._gen.set_state(ck["env"]["gen"])

@@ -428,6 +428,18 @@ class BatchedAutoMaintenance:
         self._single = [single_violation_rules(r.component_id, r.parameter, r.action) for r in table.rows]
         sim.set_thresholds(table.device_rows())
 
+    def state_dict(self) -> dict:
+        """Everything a resumed run needs to continue with the same work orders (env.save_checkpoint)."""
+        return {"kind": "object", "last_check_time": self.last_check_time, "books": self.books, "pending": self._pending,
+                "created_log": self.created_log, "executed_log": self.executed_log, "event_log": self.event_log}
+
+    def load_state_dict(self, d: dict) -> None:
+        if d.get("kind") != "object":
+            raise ValueError("checkpoint was written by a different bookkeeping class")
+        self.last_check_time = d["last_check_time"]
+        self.books, self._pending = d["books"], d["pending"]
+        self.created_log, self.executed_log, self.event_log = d["created_log"], d["executed_log"], d["event_log"]
+
     def reset(self, plants) -> None:
         """Forget the work-order books of plants that start a new episode (their clocks restart with the reset): pending
         orders, dedupe stamps and counters.  The simulator's own reset() clears their threshold cooldown stamps."""
@@ -692,6 +704,22 @@ class ColumnarAutoMaintenance(BatchedAutoMaintenance):
         self.act_known = np.array([a in known for a in self.actions], dtype=bool)
         self.act_code = np.array([action_code(a) for a in self.actions], dtype=np.int64)
         self.act_is_bearing = np.array([a == "bearing_replacement" for a in self.actions], dtype=bool)
+
+    def state_dict(self) -> dict:
+        return {"kind": "columnar", "last_check_time": self.last_check_time, "actions": list(self.actions), "rk": self.rk, "rt": self.rt,
+                "n_created": self.n_created, "pend": self.pend, "created_cols": self.created_cols,
+                "executed_cols": self.executed_cols, "event_cols": self.event_cols}
+
+    def load_state_dict(self, d: dict) -> None:
+        if d.get("kind") != "columnar":
+            raise ValueError("checkpoint was written by a different bookkeeping class")
+        for name in d["actions"]:            # action ids are positions in this list: restore it before the columns
+            self._aid(name)
+        assert self.actions[:len(d["actions"])] == list(d["actions"])
+        self._refresh_action_tables()
+        self.last_check_time = d["last_check_time"]
+        self.rk, self.rt, self.n_created, self.pend = d["rk"], d["rt"], d["n_created"], d["pend"]
+        self.created_cols, self.executed_cols, self.event_cols = d["created_cols"], d["executed_cols"], d["event_cols"]
 
     def _key(self, plant, comp, act):
         return (plant * self.n_comp + comp) * 4096 + act

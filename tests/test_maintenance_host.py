@@ -207,6 +207,43 @@ def test_columnar_equals_object_bookkeeping_on_a_busy_batch(head_quirks):
     np.testing.assert_array_equal(sims[0].state_numpy(), sims[1].state_numpy())
 
 
+@pytest.mark.parametrize("cls", ["BatchedAutoMaintenance", "ColumnarAutoMaintenance"])
+def test_bookkeeping_state_dict_round_trip(cls):
+    """A run cut in the middle (work orders pending), its books moved to a fresh bookkeeping object through state_dict /
+    pickle, continues to the same work orders and state as the uninterrupted run — for both bookkeeping classes."""
+    import pickle
+    M = _maint()
+    from nuclear_sim_b200 import field_index
+    g = np.load(os.path.join(U.GOLDEN, "maint_oil_top_off.npz"), allow_pickle=False)
+    cfg = json.loads(str(g["log"]))["maintenance_system"]
+    ix = field_index()
+    n = 24
+    st = np.tile(g["state0"], (n, 1))
+    st[:, ix["fw.pump[0].lub.oil_level"]] = 58.0 + np.linspace(-0.2, 0.8, n)
+    st[::4, ix["fw.pump[1].lub.oil_contamination_level"]] = 15.21
+    mk = lambda sim: getattr(M, cls)(sim, M.ThresholdTable(cfg), aggressive=True)   # noqa: E731
+    full_sim, part_sim = U.OracleSim(st, g["params"]), U.OracleSim(st, g["params"])
+    full, part = mk(full_sim), mk(part_sim)
+    full.advance(20)
+    part.advance(7)
+    resumed_sim = U.OracleSim(part_sim.state_numpy(), g["params"])
+    resumed_sim.step_index = part_sim.step_index
+    resumed_sim._last = None
+    resumed = mk(resumed_sim)
+    resumed_sim._last = part_sim._last.copy()                      # threshold cooldown stamps travel with the simulator
+    resumed.load_state_dict(pickle.loads(pickle.dumps(part.state_dict())))
+    resumed.advance(13)
+    for m in (full, resumed):
+        if hasattr(m, "materialize_logs"):
+            m.materialize_logs()
+    key = lambda w: (w.created, w.plant, w.component_id, w.action, w.work_order_id, w.executed_at, w.success)   # noqa: E731
+    assert sorted(key(w) for w in resumed.created_log) == sorted(key(w) for w in full.created_log) and len(full.created_log) > 10
+    np.testing.assert_array_equal(resumed_sim.state_numpy(), full_sim.state_numpy())
+    with pytest.raises(ValueError):
+        other = "ColumnarAutoMaintenance" if cls == "BatchedAutoMaintenance" else "BatchedAutoMaintenance"
+        getattr(M, other)(U.OracleSim(st, g["params"]), M.ThresholdTable(cfg)).load_state_dict(part.state_dict())
+
+
 def test_single_violation_fast_path_equals_orchestrate():
     """BatchedAutoMaintenance precomputes the decision for one-violation events; it must agree with orchestrate()
     for every threshold row of the reference configuration, below and above every rule threshold."""
