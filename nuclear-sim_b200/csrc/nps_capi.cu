@@ -91,6 +91,9 @@ struct nps_handle {
     int pipe_k = 0; int64_t pipe_count = 0;
     RngConfig rng = {0, 0, 0, 0, 0};
     int n_sms = 148; bool log_row_tile_only = false;
+    // from this many plants on: 448 threads x 128 registers per SM.  Up to 37,888 uncapped one-warp blocks are one wave
+    // and 4-8 % faster (profiles/r02_mid_batch.txt); NPS_LARGE_BATCH overrides (tuning)
+    int64_t large_batch = 148 * 8 * 32;
     int small_shape = 0;   // batches up to n_sms x 4 x 32 plants: 0 split kernel (two threads per plant), 1 one thread per plant (NPS_SMALL_SHAPE=1)   // NPS_LOG_ROW_TILE=1 forces the shared-memory tile kernel
 };
 
@@ -110,7 +113,6 @@ struct nps_handle {
 #endif
 #define NPS_STR_(x) #x
 #define NPS_PRAGMA_UNROLL(n) _Pragma(NPS_STR_(unroll n))
-constexpr int kLargeBatch = 148 * 448 / 2;
 
 // ------------------------------------------------------------------------------------------------
 // in-launch monitoring: what the reference does after the physics of EVERY step (sim.py:209-223,256) evaluated after
@@ -358,6 +360,9 @@ struct SplitShared {
 // No register cap (224 registers, 4 blocks per SM): one wave up to 148 x 4 x 32 = 18,944 plants.  A 128-register
 // variant that keeps 33,152 plants in one wave was measured and dropped: at 32,768 plants it reaches 6.9e7 plant-steps/s
 // against 1.0e8 for one uncapped thread per plant (profiles/r02_bench_n1.json small_batch), so larger batches use that.
+// Coupling the halves through a ring of 2-4 handoff slots with producer/consumer counters instead of the block barrier,
+// and giving L1 more of the SM (64 KB instead of 100 KB of shared memory), were both measured: no change outside run-to-run
+// noise at 1,024-18,944 plants, deeper rings lose L1 and are slower (profiles/r02_split_ring.txt).
 __global__ void __launch_bounds__(2 * kSplitPlants, 1)
 nps_step_split_kernel(const __grid_constant__ PlantParams prm, const __grid_constant__ StepArgs a) {
     __shared__ Threshold s_rows[kMaxSharedRows];
@@ -790,6 +795,7 @@ int nps_create(int64_t n_plants, int device, nps_handle** out) {
     cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, device);
     { const char* e = getenv("NPS_LOG_ROW_TILE"); h->log_row_tile_only = e && e[0] == '1'; }
     { const char* e = getenv("NPS_SMALL_SHAPE"); h->small_shape = (e && e[0] == '1') ? 1 : 0; }
+    { const char* e = getenv("NPS_LARGE_BATCH"); if (e && atoll(e) > 0) h->large_batch = atoll(e); }
     NPS_CUDA(cudaFuncSetAttribute(nps_log_row_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLogStages * kLogStageBytes));
     // the step kernel keeps one PlantState per thread in local memory
 #if defined(NPS_STEP_BLOCK)
@@ -838,7 +844,7 @@ static int launch_step(nps_handle* h, const StepArgs& a, cudaStream_t s) {
 #if defined(NPS_STEP_BLOCK)
     nps_step_kernel<NPS_STEP_BLOCK, NPS_STEP_MINBLOCKS><<<(int)((h->n + NPS_STEP_BLOCK - 1) / NPS_STEP_BLOCK), NPS_STEP_BLOCK, 0, s>>>(h->params, a);
 #else
-    if (h->n >= kLargeBatch) nps_step_kernel<448, 1><<<(int)((h->n + 447) / 448), 448, 0, s>>>(h->params, a);
+    if (h->n >= h->large_batch) nps_step_kernel<448, 1><<<(int)((h->n + 447) / 448), 448, 0, s>>>(h->params, a);
     else {
         const int blocks = (int)((h->n + kSplitPlants - 1) / kSplitPlants);
         if (h->small_shape == 0 && blocks <= h->n_sms * 4) nps_step_split_kernel<<<blocks, 2 * kSplitPlants, 0, s>>>(h->params, a);

@@ -20,8 +20,14 @@ N_ACTIONS = 15          # len(ControlAction): systems/primary/__init__.py:28-45
 
 
 class BatchedNuclearPlantEnv:
-    def __init__(self, sim, auto_reset: bool = True, seed: int = 0):
+    def __init__(self, sim, auto_reset: bool = True, seed: int = 0, frame_skip: int = 1):
+        """frame_skip = K repeats each action for K reference steps in ONE fused launch: the reward is the sum of the
+        per-step rewards up to and including the step a plant scrammed at, done is "scrammed in any of the K steps"
+        (the in-launch monitor supplies reward and done of every substep), the observation is the last step's."""
         self.sim = sim
+        self.frame_skip = int(frame_skip)
+        if self.frame_skip > 1:
+            sim.enable_monitor(per_substep=True, max_k=self.frame_skip)
         self.n_plants = sim.n_plants
         self.action_space_size = N_ACTIONS
         self.observation_space_size = 22
@@ -30,8 +36,9 @@ class BatchedNuclearPlantEnv:
         self.episode_steps = torch.zeros(self.n_plants, dtype=torch.int64, device=sim.device)
 
     def _noise(self) -> torch.Tensor:
-        z = torch.randn((1, 2, self.n_plants), generator=self._gen, dtype=torch.float64)
-        u = torch.rand((1, 3, self.n_plants), generator=self._gen, dtype=torch.float64)
+        k = self.frame_skip
+        z = torch.randn((k, 2, self.n_plants), generator=self._gen, dtype=torch.float64)
+        u = torch.rand((k, 3, self.n_plants), generator=self._gen, dtype=torch.float64)
         return torch.cat([z, u], dim=1)
 
     def reset(self, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -53,11 +60,17 @@ class BatchedNuclearPlantEnv:
             raise ValueError("action_idx must hold one ControlAction value (0..14) per plant")
         if cooling_water_temp is not None:
             self.sim.state["sim.cooling_water_temp"] = cooling_water_temp
-        out = self.sim.step(actions=a.reshape(1, -1), magnitudes=None if magnitude is None else torch.as_tensor(magnitude, dtype=torch.float64).reshape(1, -1),
-                            noise=self._noise(), K=1)
-        self.episode_steps += 1
+        k = self.frame_skip
+        out = self.sim.step(actions=a.reshape(1, -1).expand(k, -1),
+                            magnitudes=None if magnitude is None else torch.as_tensor(magnitude, dtype=torch.float64).reshape(1, -1).expand(k, -1),
+                            noise=self._noise(), K=k)
+        self.episode_steps += k
         done = out["done"].clone()
         obs, reward = out["observation"].clone(), out["reward"].clone()
+        if k > 1:      # rewards of the substeps up to and including the first done one
+            dk = out["done_k"].to(torch.float64)
+            alive = (torch.cumsum(dk, dim=0) - dk) == 0
+            reward = (out["reward_k"] * alive).sum(dim=0)
         info = {"episode_steps": self.episode_steps.clone(), "time_minutes": self.sim.state["sim.time_minutes"].clone()}
         if self.auto_reset and bool(done.any()):
             info["terminal_observation"] = obs[done].clone()

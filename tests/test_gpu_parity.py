@@ -447,6 +447,38 @@ def test_env_cooling_water_reset_cooldowns_and_maintenance_checkpoint(tmp_path):
     assert fired == [False, True, True]
 
 
+def test_env_frame_skip_sums_rewards_up_to_done():
+    """BatchedNuclearPlantEnv(frame_skip=4): one fused launch per env step; reward = sum of the per-step rewards up to and
+    including the scram step, done = scrammed in any of the 4 steps — equal to four frame_skip=1 steps of the same action
+    with the same noise."""
+    import torch
+    from nuclear_sim_b200 import load_snapshot, field_index
+    from nuclear_sim_b200.env import BatchedNuclearPlantEnv
+    s0, params = load_snapshot("pwr3000_reactor_dt1")
+    n = 48
+    st = np.tile(s0, (n, 1))
+    ix = field_index()
+    st[5, ix["pri.coolant_pressure"]] = 17.15            # OPEN valve / rod actions aside, this plant crosses 17.2 MPa within the 4 steps or not at all
+    st[9, ix["pri.fuel_temperature"]] = 1600.0           # scrams in the first of the 4 steps (scram_logic.py:19)
+    one = BatchedNuclearPlantEnv(_sim(st, params), auto_reset=False, seed=7, frame_skip=1)
+    four = BatchedNuclearPlantEnv(_sim(st, params), auto_reset=False, seed=7, frame_skip=4)
+    act = torch.full((n,), 1)                            # CONTROL_ROD_WITHDRAW
+    # the same draws: frame_skip=4 draws a [4, 5, N] block per step; feed the scalar env the rows of that block
+    gen = torch.Generator(device="cpu").manual_seed(7)
+    z = torch.randn((4, 2, n), generator=gen, dtype=torch.float64); u = torch.rand((4, 3, n), generator=gen, dtype=torch.float64)
+    block = torch.cat([z, u], dim=1)
+    rew = torch.zeros(n, dtype=torch.float64, device="cuda:0"); done_any = torch.zeros(n, dtype=torch.bool, device="cuda:0")
+    for k in range(4):
+        out = one.sim.step(actions=act.to(torch.int8).reshape(1, -1), noise=block[k:k + 1], K=1)
+        rew += out["reward"] * (~done_any)
+        done_any |= out["done"]
+    obs4, rew4, done4, info4 = four.step(act)
+    assert torch.equal(four.sim.slab, one.sim.slab)
+    assert torch.equal(done4, done_any) and bool(done4[9]) and int(done4.sum()) >= 1
+    assert torch.allclose(rew4, rew, rtol=1e-13, atol=0.0)
+    assert int(info4["episode_steps"][0]) == 4
+
+
 def test_cuda_batched_timing_sweep():
     """The batched TimingOptimizer replacement on the CUDA engine: 512 candidate oil levels in one batch; the committed
     initial level reproduces the reference's trigger time and the curve is monotone."""
