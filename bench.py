@@ -448,7 +448,7 @@ def main():
         pass
     elif world > 1:
         extra["strong_65536"] = {"value": sub_batch(PLANTS_PER_GPU // world, max(3, K // 2)), "unit": UNIT,
-                                 "one_thread_per_plant": sub_batch(PLANTS_PER_GPU // world, max(3, K // 2), 1) if PLANTS_PER_GPU // world < 33152 else None,
+                                 "one_thread_per_plant": sub_batch(PLANTS_PER_GPU // world, max(3, K // 2), 1) if PLANTS_PER_GPU // world <= 18944 else None,
                                  "plants_per_gpu": PLANTS_PER_GPU // world,
                                  "note": "the 65,536-plant batch of the north star split over the GPUs (strong scaling)"}
     else:
@@ -457,7 +457,7 @@ def main():
                                 "one_thread_per_plant": {"plants_4096": sub_batch(4096, 3, 1), "plants_8192": sub_batch(8192, 3, 1),
                                                          "plants_16384": sub_batch(16384, 3, 1), "plants_32768": sub_batch(32768, 3, 1)},
                                 "note": "config #2 / strong-scaled config #3 share per GPU / config #4 sizes on one GPU; default "
-                                        "launch shape below 33 K plants = two threads per plant (source / sink halves pipelined "
+                                        "launch shape up to 18,944 plants = two threads per plant (source / sink halves pipelined "
                                         "by one substep), bit-identical to one thread per plant"}
 
 

@@ -279,6 +279,8 @@ __device__ __noinline__ void monitor_substep(const PlantState& st, const Monitor
     }
 }
 
+// 448 threads get 128 registers: warps are allocated in fours, so the block counts as 16 warps and 136 or 144 registers
+// per thread (which 14 x 32 threads would fit) fail to launch (checked with __maxnreg__, GPU call 21).
 template <int BLOCK, int MINBLOCKS>
 __global__ void __launch_bounds__(BLOCK, MINBLOCKS)
 nps_step_kernel(const __grid_constant__ PlantParams prm, const __grid_constant__ StepArgs a) {
