@@ -1210,7 +1210,11 @@ static const char* const kMaintActionNames[MA_N_ACTIONS] = {
     "overhaul", "condenser_tube_cleaning", "condenser_tube_plugging", "condenser_chemical_cleaning", "vacuum_system_test",
     "vacuum_leak_detection", "turbine_performance_test", "turbine_system_optimization", "turbine_protection_test",
     "thermal_stress_analysis", "system_coordination_maintenance", "system_steam_quality_maintenance",
-    "load_balancing_maintenance", "other"};
+    "load_balancing_maintenance", "water_chemistry_adjustment", "tsp_inspection", "tsp_flow_test",
+    "tube_interior_inspection", "tube_interior_eddy_current_testing", "primary_chemistry_optimization",
+    "condenser_water_treatment", "turbine_oil_change", "turbine_oil_top_off", "oil_filter_replacement",
+    "oil_cooler_cleaning", "lubrication_system_test", "vacuum_ejector_cleaning", "vacuum_ejector_nozzle_replacement",
+    "vacuum_ejector_inspection", "vacuum_ejector_mechanical_cleaning", "other"};
 
 int nps_n_maintenance_actions(void) { return MA_N_ACTIONS; }
 const char* nps_maintenance_action_name(int action) {

@@ -31,7 +31,9 @@ enum MaintTarget : int {
     MT_STAGE0 = 9,         // HP-1 .. HP-8, LP-1 .. LP-6
     MT_TURBINE = 23,       // SECONDARY-COMP-001-TURB
     MT_CONDENSER = 24,     // SECONDARY-COMP-001-COND
-    MT_N_TARGETS = 25
+    MT_TURBINE_LUB = 25,   // TB-LUB-001 (TurbineBearingLubricationSystem)
+    MT_EJECTOR0 = 26,      // SJE-001, SJE-002 (SteamJetEjector)
+    MT_N_TARGETS = 28
 };
 
 // Action codes (names in nuclear_sim_b200/maintenance.py ACTION_CODES, same order).
@@ -47,6 +49,12 @@ enum MaintAction : int {
     MA_VACUUM_LEAK_DETECTION,
     MA_TURBINE_PERFORMANCE_TEST, MA_TURBINE_SYSTEM_OPTIMIZATION, MA_TURBINE_PROTECTION_TEST, MA_THERMAL_STRESS_ANALYSIS,
     MA_SYSTEM_COORDINATION_MAINTENANCE, MA_SYSTEM_STEAM_QUALITY_MAINTENANCE, MA_LOAD_BALANCING_MAINTENANCE,
+    MA_WATER_CHEMISTRY_ADJUSTMENT, MA_TSP_INSPECTION, MA_TSP_FLOW_TEST, MA_TUBE_INTERIOR_INSPECTION,
+    MA_TUBE_INTERIOR_EDDY_CURRENT_TESTING, MA_PRIMARY_CHEMISTRY_OPTIMIZATION, MA_CONDENSER_WATER_TREATMENT,
+    MA_TURBINE_OIL_CHANGE, MA_TURBINE_OIL_TOP_OFF, MA_OIL_FILTER_REPLACEMENT, MA_OIL_COOLER_CLEANING,
+    MA_LUBRICATION_SYSTEM_TEST,
+    MA_VACUUM_EJECTOR_CLEANING, MA_VACUUM_EJECTOR_NOZZLE_REPLACEMENT, MA_VACUUM_EJECTOR_INSPECTION,
+    MA_VACUUM_EJECTOR_MECHANICAL_CLEANING,
     MA_OTHER,              // any action name without a handler on the target: no state change
     MA_N_ACTIONS
 };
@@ -249,6 +257,19 @@ NPS_HD int maintain_sg(SGState& g, int action) {
         case MA_EDDY_CURRENT_TESTING: return MS_FAILED;
         case MA_SECONDARY_SIDE_CLEANING: g.tsp_fouling_fraction *= (1.0 - 0.3); return MS_SUCCESS;   // :1243-1261
         case MA_ROUTINE_MAINTENANCE: g.steam_quality = py_min(0.999, g.steam_quality + 0.001); return MS_SUCCESS;   // :1303-1315
+        // :1203-1216 WaterChemistry.reset() on WAT-001, the SG system's own instance: it is never updated, so its members
+        // stay at the design values reset() would write (they are PlantParams sgwc_* here) -> success, no change
+        case MA_WATER_CHEMISTRY_ADJUSTMENT: return MS_SUCCESS;
+        // :1263-1271 -> TSPFoulingModel.perform_maintenance (tsp_fouling_model.py:489-521): report only, then
+        // FoulingModelBase._update_maintenance_history (fouling_model_base.py:210-214) counts it as a cleaning cycle
+        case MA_TSP_INSPECTION:
+        case MA_TSP_FLOW_TEST: g.tsp_total_cleaning_cycles += 1.0; g.tsp_last_cleaning_time = 0.0; return MS_SUCCESS;
+        // :1273-1291 -> TubeInteriorFouling.perform_maintenance (tube_interior_fouling.py:327-359): inspection and eddy
+        // current testing report only; primary_chemistry_optimization writes boric acid 1000 / lithium 2.0 / pH 7.2, the
+        // values the model is built with (:82-84) and nothing else ever changes; all three end in _update_maintenance_history
+        case MA_TUBE_INTERIOR_INSPECTION:
+        case MA_TUBE_INTERIOR_EDDY_CURRENT_TESTING:
+        case MA_PRIMARY_CHEMISTRY_OPTIMIZATION: g.tif_last_cleaning_time = 0.0; return MS_SUCCESS;
         default: return MS_FAILED;               // :1317-1324
     }
 }
@@ -266,6 +287,14 @@ NPS_HD int maintain_stage(TurbineStageState& s, const PlantParams& p, int k, int
     return MS_SUCCESS;
 }
 
+// AdvancedFoulingModel.calculate_total_fouling_resistance: condenser/physics.py:297-322
+NPS_HD double cond_total_fouling_resistance(const CondenserState& C) {
+    double tr = (C.fl_biofouling_thickness / 1000.0) / 0.5 + (C.fl_scale_thickness / 1000.0) / 2.0 +
+                (C.fl_corrosion_product_thickness / 1000.0) / 1.0;
+    tr *= C.fl_distribution_factor;
+    return tr;
+}
+
 // AdvancedFoulingModel.perform_cleaning("chemical"): condenser/physics.py:386-450
 NPS_HD void cond_perform_chemical_cleaning(CondenserState& C) {
     double bio_removed = C.fl_biofouling_thickness * 0.8;
@@ -276,10 +305,7 @@ NPS_HD void cond_perform_chemical_cleaning(CondenserState& C) {
     C.fl_corrosion_product_thickness -= corrosion_removed;
     C.fl_time_since_cleaning = 0.0;
     C.fl_distribution_factor = 1.0;
-    double tr = (C.fl_biofouling_thickness / 1000.0) / 0.5 + (C.fl_scale_thickness / 1000.0) / 2.0 +
-                (C.fl_corrosion_product_thickness / 1000.0) / 1.0;
-    tr *= C.fl_distribution_factor;
-    C.fl_total_fouling_resistance = tr;
+    C.fl_total_fouling_resistance = cond_total_fouling_resistance(C);
 }
 
 // EnhancedCondenserPhysics.perform_maintenance: condenser/physics.py:1188-1372
@@ -312,6 +338,18 @@ NPS_HD int maintain_condenser(CondenserState& C, const PlantParams& p, int actio
         case MA_VACUUM_LEAK_DETECTION:                   // :1345-1362
             C.vs_current_air_leakage *= 0.5;
             return MS_SUCCESS;
+        case MA_CONDENSER_WATER_TREATMENT: {             // :1291-1317
+            // WaterChemistry.perform_chemical_treatment("standard") on WAT-002: water_chemistry.py:508-521
+            WaterChemState& w = C.wc;
+            w.ph += (9.2 - w.ph) * 0.3;
+            w.chlorine_residual = 1.0; w.antiscalant_concentration = 5.0; w.corrosion_inhibitor_level = 10.0;
+            w.treatment_efficiency = 0.95;
+            w.last_treatment_time = 0.0;
+            wc_composite(w);
+            C.fl_biofouling_thickness *= 0.9; C.fl_scale_thickness *= 0.8; C.fl_corrosion_product_thickness *= 0.7;
+            C.fl_total_fouling_resistance = cond_total_fouling_resistance(C);
+            return MS_SUCCESS;
+        }
         default: return MS_FAILED;                       // :1364-1371
     }
 }
@@ -385,6 +423,82 @@ NPS_HD int maintain_sg_system(SGSystemState& S, int action) {
     }
 }
 
+// TurbineBearingLubricationSystem.perform_maintenance: turbine/turbine_bearing_lubrication.py:481-665
+// (component_wear order: hp_journal_bearing, lp_journal_bearing, thrust_bearing, seal_oil_system, oil_coolers)
+NPS_HD int maintain_turbine_lub(TurbineState& T, int action) {
+    LubCore& L = T.lub;
+    switch (action) {
+        case MA_TURBINE_OIL_CHANGE:              // :492-523
+            L.oil_contamination_level = 1.0; L.oil_acidity_number = 0.05; L.oil_moisture_content = 0.01; L.oil_level = 100.0;
+            L.lubrication_effectiveness = py_min(1.0, L.lubrication_effectiveness + 0.15);
+            L.oil_temperature = py_max(45.0, L.oil_temperature - 5.0);
+            return MS_SUCCESS;
+        case MA_TURBINE_OIL_TOP_OFF: {           // :525-547
+            double oil_added = py_min(100.0 - L.oil_level, 50.0);
+            L.oil_level += oil_added;
+            double dilution = oil_added / 100.0;
+            L.oil_contamination_level = py_max(1.0, L.oil_contamination_level - dilution * 2.0);
+            L.oil_acidity_number = py_max(0.05, L.oil_acidity_number - dilution * 0.1);
+            return MS_SUCCESS;
+        }
+        case MA_OIL_FILTER_REPLACEMENT: {        // :549-571
+            double reduction = py_min(5.0, L.oil_contamination_level * 0.6);
+            L.oil_contamination_level -= reduction;
+            L.oil_contamination_level = py_max(1.0, L.oil_contamination_level);
+            L.lubrication_effectiveness = py_min(1.0, L.lubrication_effectiveness + 0.05);
+            return MS_SUCCESS;
+        }
+        case MA_OIL_COOLER_CLEANING: {           // :573-598
+            double original = T.lub_oil_cooling_effectiveness;
+            T.lub_oil_cooling_effectiveness = py_min(1.0, T.lub_oil_cooling_effectiveness + 0.15);
+            double temp_reduction = (1.0 - original) * 15.0;
+            L.oil_temperature = py_max(45.0, L.oil_temperature - temp_reduction);
+            L.component_wear[4] = py_max(0.0, L.component_wear[4] - 5.0);
+            return MS_SUCCESS;
+        }
+        case MA_LUBRICATION_SYSTEM_TEST:         // :600-637
+            L.lubrication_effectiveness = py_min(1.0, L.lubrication_effectiveness + 0.1);
+            return MS_SUCCESS;
+        case MA_ROUTINE_MAINTENANCE:             // :639-657
+            L.lubrication_effectiveness = py_min(1.0, L.lubrication_effectiveness + 0.02);
+            L.oil_contamination_level = py_max(1.0, L.oil_contamination_level - 0.5);
+            L.oil_temperature = py_max(45.0, L.oil_temperature - 1.0);
+            for (int c = 0; c < 5; ++c) L.component_wear[c] = py_max(0.0, L.component_wear[c] - 0.5);
+            return MS_SUCCESS;
+        default: return MS_FAILED;               // :659-667
+    }
+}
+
+// SteamJetEjector.perform_maintenance: condenser/vacuum_pump.py:338-466 (perform_cleaning :309-336); every name succeeds,
+// names without a branch of their own take the "general" reset
+NPS_HD int maintain_ejector(EjectorState& e, int action) {
+    switch (action) {
+        case MA_VACUUM_EJECTOR_CLEANING:         // chemical
+            e.nozzle_fouling_factor = py_min(1.0, e.nozzle_fouling_factor + 0.3);
+            e.diffuser_fouling_factor = py_min(1.0, e.diffuser_fouling_factor + 0.4);
+            break;
+        case MA_VACUUM_EJECTOR_MECHANICAL_CLEANING:
+            e.nozzle_fouling_factor = py_min(1.0, e.nozzle_fouling_factor + 0.4);
+            e.diffuser_fouling_factor = py_min(1.0, e.diffuser_fouling_factor + 0.5);
+            e.nozzle_erosion_factor = py_min(1.0, e.nozzle_erosion_factor + 0.1);
+            break;
+        case MA_VACUUM_EJECTOR_NOZZLE_REPLACEMENT:
+            e.nozzle_fouling_factor = 1.0; e.diffuser_fouling_factor = 1.0; e.nozzle_erosion_factor = 1.0;
+            break;
+        case MA_VACUUM_EJECTOR_INSPECTION: return MS_SUCCESS;
+        case MA_ROUTINE_MAINTENANCE:
+            e.nozzle_fouling_factor = py_min(1.0, e.nozzle_fouling_factor + 0.05);
+            e.diffuser_fouling_factor = py_min(1.0, e.diffuser_fouling_factor + 0.05);
+            break;
+        default:
+            e.nozzle_fouling_factor = 1.0; e.diffuser_fouling_factor = 1.0; e.nozzle_erosion_factor = 1.0;
+            e.overall_performance_factor = 1.0;
+            return MS_SUCCESS;
+    }
+    e.overall_performance_factor = (e.nozzle_fouling_factor * e.diffuser_fouling_factor * e.nozzle_erosion_factor);
+    return MS_SUCCESS;
+}
+
 // One request: (target, action, arg).  Targets without a perform_maintenance restatement report
 // MS_UNSUPPORTED_TARGET so the host can refuse instead of silently diverging.
 NPS_HD int maintenance_apply_target(PlantState& st, const PlantParams& p, int target, int action, int arg) {
@@ -394,9 +508,15 @@ NPS_HD int maintenance_apply_target(PlantState& st, const PlantParams& p, int ta
     if (target == MT_CONDENSER) return maintain_condenser(st.cond, p, action);
     if (target == MT_TURBINE) return maintain_turbine(st.turb, action);
     if (target == MT_SG_SYSTEM) return maintain_sg_system(st.sgs, action);
+    if (target == MT_TURBINE_LUB) return maintain_turbine_lub(st.turb, action);
+    if (target >= MT_EJECTOR0 && target < MT_EJECTOR0 + 2) return maintain_ejector(st.cond.ejector[target - MT_EJECTOR0], action);
     // FEE-001: FeedwaterPumpSystem has no perform_maintenance method (the one in pump_system.py:750 belongs to
     // FeedwaterPump), so _perform_maintenance_action reports "does not support maintenance": success False, no change
     if (target == MT_FW_SYSTEM) return MS_FAILED;
+    // Not a target: SECONDARY-COMP-001-FW (EnhancedFeedwaterPhysics.perform_maintenance, feedwater/physics.py:984-1128).
+    // No threshold of the reference template is bound to that id, so no automatic work order reaches it; its
+    // system_cleaning branch scales the three members of PerformanceDiagnostics.wear_tracking separately, of which the
+    // state log (and therefore PlantState) carries only the sum (rep.fw_diag_total_wear).  The host refuses the id.
     return MS_UNSUPPORTED_TARGET;
 }
 

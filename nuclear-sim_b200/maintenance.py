@@ -41,7 +41,11 @@ ACTION_NAMES = (
     "overhaul", "condenser_tube_cleaning", "condenser_tube_plugging", "condenser_chemical_cleaning", "vacuum_system_test",
     "vacuum_leak_detection", "turbine_performance_test", "turbine_system_optimization", "turbine_protection_test",
     "thermal_stress_analysis", "system_coordination_maintenance", "system_steam_quality_maintenance",
-    "load_balancing_maintenance", "other")
+    "load_balancing_maintenance", "water_chemistry_adjustment", "tsp_inspection", "tsp_flow_test",
+    "tube_interior_inspection", "tube_interior_eddy_current_testing", "primary_chemistry_optimization",
+    "condenser_water_treatment", "turbine_oil_change", "turbine_oil_top_off", "oil_filter_replacement",
+    "oil_cooler_cleaning", "lubrication_system_test", "vacuum_ejector_cleaning", "vacuum_ejector_nozzle_replacement",
+    "vacuum_ejector_inspection", "vacuum_ejector_mechanical_cleaning", "other")
 ACTION_CODE = {n: i for i, n in enumerate(ACTION_NAMES)}
 BEARING_ARG = {None: 0, "": 0, "all": 0, "motor_bearings": 1, "pump_bearings": 2, "thrust_bearing": 3}
 
@@ -64,6 +68,10 @@ def target_code(component_id: str) -> int:
         return 23
     if component_id == "SECONDARY-COMP-001-COND":
         return 24
+    if component_id == "TB-LUB-001":
+        return 25
+    if component_id.startswith("SJE-"):
+        return 26 + int(component_id[4:]) - 1
     raise KeyError(component_id)
 
 

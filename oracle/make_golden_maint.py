@@ -2,10 +2,17 @@
 
   python oracle/make_golden_maint.py effects     -> tests/golden/maint_effects.npz
   python oracle/make_golden_maint.py scenarios   -> tests/golden/maint_<scenario>.npz
+  python oracle/make_golden_maint.py sweep       -> tests/golden/maint_effects_sweep.npz
 
 effects:   before/after PlantState vectors around AutoMaintenanceSystem._perform_maintenance_action
            (systems/maintenance/auto_maintenance.py:582-673) for every (component, action) pair the engine restates,
            called exactly as _execute_work_order calls it, on plants with degraded initial conditions.
+sweep:     EVERY action name of the reference catalogue (MaintenanceActionType, systems/maintenance/maintenance_actions.py:19-198,
+           127 names) plus the uncatalogued names the template and the components use, against every component class a
+           work order can address (pump, pump system, steam generator, SG system, HP / LP stage, turbine, condenser,
+           turbine bearing lubrication, steam jet ejector):
+           success flag and the sparse state change of each call, so that "which branch does this name take on this
+           class" is pinned for the whole catalogue and not only for the pairs the engine restates.
 scenarios: full NuclearPlantSimulator.step with state management and the automatic maintenance system, set up the
            way MaintenanceScenarioRunner does (data_gen/runners/maintenance_scenario_runner.py:205-330): per step the
            state after the step, the threshold events StateManager emitted, the work orders created and executed.
@@ -53,7 +60,30 @@ EFFECT_CASES = [
     ("SECONDARY-COMP-001-SG", "load_balancing_maintenance", None), ("SECONDARY-COMP-001-SG", "routine_maintenance", None),
     ("SECONDARY-COMP-001-SG", "tsp_chemical_cleaning", None),
     ("FEE-001", "oil_change", None), ("FEE-001", "routine_maintenance", None),
+    # turbine bearing lubrication system and steam jet ejectors (degraded by hand just before the call: EFFECT_TWEAKS)
+    ("TB-LUB-001", "turbine_oil_change", None), ("TB-LUB-001", "turbine_oil_top_off", None),
+    ("TB-LUB-001", "oil_filter_replacement", None), ("TB-LUB-001", "oil_cooler_cleaning", None),
+    ("TB-LUB-001", "lubrication_system_test", None), ("TB-LUB-001", "routine_maintenance", None),
+    ("TB-LUB-001", "oil_change", None),
+    ("SJE-001", "vacuum_ejector_cleaning", None), ("SJE-002", "vacuum_ejector_mechanical_cleaning", None),
+    ("SJE-001", "vacuum_ejector_nozzle_replacement", None), ("SJE-002", "vacuum_ejector_inspection", None),
+    ("SJE-001", "routine_maintenance", None), ("SJE-002", "oil_change", None),
 ]
+
+
+def _degrade_turbine_lub(inst):
+    inst.oil_level, inst.oil_contamination_level, inst.oil_acidity_number = 62.0, 11.5, 0.42
+    inst.oil_moisture_content, inst.oil_temperature, inst.lubrication_effectiveness = 0.06, 63.0, 0.71
+    inst.oil_cooling_effectiveness = 0.68
+    inst.component_wear["oil_coolers"] = 7.25
+
+
+def _degrade_ejector(inst):
+    inst.nozzle_fouling_factor, inst.diffuser_fouling_factor, inst.nozzle_erosion_factor = 0.62, 0.48, 0.86
+    inst.overall_performance_factor = inst.nozzle_fouling_factor * inst.diffuser_fouling_factor * inst.nozzle_erosion_factor
+
+
+EFFECT_TWEAKS = {"TB-LUB-001": _degrade_turbine_lub, "SJE-001": _degrade_ejector, "SJE-002": _degrade_ejector}
 
 
 def runner_style_plant(action, dt=5.0, noise=False):
@@ -77,7 +107,7 @@ def effects():
         plants[ic] = runner_style_plant(ic)[0]
     rng = np.random.RandomState(11)
     for i, (cid, action, sub) in enumerate(EFFECT_CASES):
-        rp = plants["oil_change"] if (cid.startswith("FWP") or "COND" in cid or cid[:2] in ("HP", "LP") or "TURB" in cid or cid == "FEE-001") \
+        rp = plants["oil_change"] if (cid.startswith(("FWP", "TB-", "SJE")) or "COND" in cid or cid[:2] in ("HP", "LP") or "TURB" in cid or cid == "FEE-001") \
             else plants["tsp_chemical_cleaning"]
         sim = rp.sim
         for _ in range(2):
@@ -90,6 +120,8 @@ def effects():
             pr = sim.secondary_physics.turbine.protection_system
             pr.trip_active, pr.trip_reasons = True, ["Low Vacuum"]
             pr.trip_timers["vibration"] = 1.5
+        if cid in EFFECT_TWEAKS:
+            EFFECT_TWEAKS[cid](inst)
         b = R.extract_state(sim)
         with R.quiet():
             res = ms._perform_maintenance_action(inst, action, wo)
@@ -105,6 +137,59 @@ def effects():
     np.savez_compressed(os.path.join(GOLDEN, "maint_effects.npz"), before=np.array(before), after=np.array(after),
                         component=np.array(comp), action=np.array(act), arg=np.array(arg), success=np.array(ok),
                         params=params, state_names=sn, param_names=pn)
+
+
+SWEEP_TARGETS = ["FWP-2", "FEE-001", "SG-1", "SECONDARY-COMP-001-SG", "HP-2", "LP-3", "SECONDARY-COMP-001-TURB",
+                 "SECONDARY-COMP-001-COND", "TB-LUB-001", "SJE-001", "SJE-002"]
+SWEEP_EXTRA_ACTIONS = ["tube_bundle_overhaul", "cleaning", "overhaul", "system_cleaning", "primary_scale_cleaning",
+                       "system_coordination_maintenance", "system_steam_quality_maintenance", "load_balancing_maintenance",
+                       "vacuum_ejector_mechanical_cleaning", "no_such_action"]
+
+
+def sweep():
+    R.setup_paths()
+    from systems.maintenance.maintenance_actions import MaintenanceActionType
+    L = R._layout()
+    actions = [t.value for t in MaintenanceActionType] + SWEEP_EXTRA_ACTIONS
+    rng = np.random.RandomState(23)
+    comp, act, ok, start, idx, val, bases, seg_target = [], [], [], [0], [], [], [], []
+    params = None
+    for ti, cid in enumerate(SWEEP_TARGETS):
+        # a fresh degraded plant per target class: the calls of one class act on one evolving state
+        rp = runner_style_plant("oil_change" if not cid.startswith("SG") and "-SG" not in cid else "tsp_chemical_cleaning")[0]
+        sim = rp.sim
+        for _ in range(3):
+            z = np.array([0.0, rng.standard_normal(), rng.random_sample(), rng.random_sample(), rng.random_sample()])
+            rp.step(8, 1.0, z)
+        if params is None:
+            params = R.extract_params(sim)
+        ms = sim.maintenance_system
+        inst = sim.state_manager.get_registered_instance_info()[cid]["instance"]
+        # two passes: catalogue order, then (after three more plant steps, so that timers and wear have moved again)
+        # reverse order - a call that only resets what an earlier call already reset shows its effect in the other pass
+        for order in (actions, actions[::-1]):
+            cur = R.extract_state(sim)
+            bases.append(cur.copy()); seg_target.append(cid)
+            n_ok = n_changed = 0
+            for action in order:
+                wo = types.SimpleNamespace(metadata={})
+                with R.quiet():
+                    res = ms._perform_maintenance_action(inst, action, wo)
+                a = R.extract_state(sim)
+                ch = np.nonzero(~((a == cur) | (np.isnan(a) & np.isnan(cur))))[0]
+                comp.append(len(bases) - 1); act.append(action); ok.append(bool(res.success))
+                idx.extend(ch.tolist()); val.extend(a[ch].tolist()); start.append(len(idx))
+                n_ok += bool(res.success); n_changed += len(ch) > 0
+                cur = a
+            print(f"[sweep] {cid:26s} {len(order)} actions: {n_ok} succeed, {n_changed} change the state")
+            for _ in range(3):
+                z = np.array([0.0, rng.standard_normal(), rng.random_sample(), rng.random_sample(), rng.random_sample()])
+                rp.step(8, 1.0, z)
+    np.savez_compressed(os.path.join(GOLDEN, "maint_effects_sweep.npz"), targets=np.array(seg_target),
+                        base=np.array(bases), target=np.array(comp, np.int32), action=np.array(act),
+                        success=np.array(ok), start=np.array(start, np.int64), index=np.array(idx, np.int32),
+                        value=np.array(val, np.float64), params=params,
+                        state_names=np.array(L.field_names("PlantState")))
 
 
 def scenario(name, action, T, dt=5.0, tweak=None):
@@ -189,6 +274,8 @@ if __name__ == "__main__":
         effects()
     if "scenarios" in what:
         scenarios()
+    if "sweep" in what:
+        sweep()
 
 
 def state_log_csv(T=12):

@@ -231,6 +231,23 @@ def test_cuda_maintenance_effects_match_reference():
     U.assert_states_close(sim.state_numpy(), z["after"], 1e-13, "maintenance effects")
 
 
+def test_cuda_catalogue_sweep_matches_reference():
+    """Every catalogued action name x every addressable component class (tests/golden/maint_effects_sweep.npz, 3 014 calls
+    of the live reference): one plant per call, started from the state the reference had before that call, all applied
+    in ONE nps_apply_maintenance; success flags and resulting states must equal the reference's."""
+    from nuclear_sim_b200 import maintenance as M
+    from tests.test_maintenance_host import _load_sweep, sweep_cases
+    z = _load_sweep()
+    cases = list(sweep_cases(z))
+    before = np.ascontiguousarray(np.stack([c[3] for c in cases]))
+    after = np.stack([c[4] for c in cases])
+    sim = _sim(before, z["params"])
+    status = sim.apply_maintenance([(i, M.target_code(c[0]), M.action_code(c[1]), 0) for i, c in enumerate(cases)])
+    bad = [(c[0], c[1]) for c, s in zip(cases, status) if bool(s == 1) != c[2]]
+    assert not bad, f"success flag differs from the reference for {bad[:5]}"
+    U.assert_states_close(sim.state_numpy(), after, 1e-13, "catalogue sweep")
+
+
 def test_cuda_maintenance_batched_equals_oracle_host_logic():
     """256 plants with staggered oil levels / fouling: the device loop and the oracle stand-in must issue the same
     work orders for the same plants at the same steps, and end in the same state."""

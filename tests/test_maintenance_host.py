@@ -49,6 +49,49 @@ def test_effects_match_reference(oracle_lib):
         U.assert_states_close(st[None, :], z["after"][i][None, :], 1e-13, f"{cid} {action} {sub}")
 
 
+def _load_sweep():
+    z = np.load(os.path.join(U.GOLDEN, "maint_effects_sweep.npz"), allow_pickle=False)
+    from nuclear_sim_b200 import field_names
+    assert tuple(str(s) for s in z["state_names"]) == field_names("PlantState")
+    return z
+
+
+def sweep_cases(z):
+    """(target id, action, reference success flag, reference state after the call) in the order the reference ran them;
+    the calls of one segment (a target, one pass over the action list) act on one evolving plant state that starts
+    from z['base'][segment]."""
+    cur, last = None, -1
+    for i in range(len(z["action"])):
+        t = int(z["target"][i])
+        if t != last:
+            cur, last = z["base"][t].copy(), t
+        lo, hi = int(z["start"][i]), int(z["start"][i + 1])
+        after = cur.copy()
+        after[z["index"][lo:hi]] = z["value"][lo:hi]
+        yield str(z["targets"][t]), str(z["action"][i]), bool(z["success"][i]), cur, after
+        cur = after
+
+
+def test_catalogue_sweep_matches_reference(oracle_lib):
+    """All 127 catalogued action names (+ 10 uncatalogued) x 11 components of the 9 classes a work order can address, in
+    catalogue order and again in reverse order: success flag and state change of every call equal the live reference's
+    (3 014 calls, oracle/make_golden_maint.py sweep)."""
+    M = _maint()
+    z = _load_sweep()
+    assert len(z["action"]) == 11 * 2 * 137 and len(set(str(t) for t in z["targets"])) == 11
+    params = np.ascontiguousarray(z["params"])
+    oracle_lib.nps_oracle_apply_maintenance.restype = ctypes.c_int
+    n_changed = 0
+    for cid, action, ok, before, after in sweep_cases(z):
+        st = np.ascontiguousarray(before).copy()
+        rc = oracle_lib.nps_oracle_apply_maintenance(U.ptr(st), U.ptr(params), M.target_code(cid), M.action_code(action), 0)
+        assert rc in (0, 1), f"{cid} {action}: unsupported target"
+        assert bool(rc) == ok, f"{cid} {action}: success flag {rc} vs reference {ok}"
+        U.assert_states_close(st[None, :], after[None, :], 1e-13, f"{cid} {action}")
+        n_changed += int(not np.array_equal(before, after, equal_nan=True))
+    assert n_changed >= 30
+
+
 def _template_maintenance_config():
     z = np.load(os.path.join(U.GOLDEN, "maint_oil_top_off.npz"), allow_pickle=False)
     return json.loads(str(z["log"]))["maintenance_system"]
