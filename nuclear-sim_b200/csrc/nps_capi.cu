@@ -204,7 +204,10 @@ __device__ __noinline__ void monitor_substep(const PlantState& st, const Monitor
     // every group of kMonChunk values is loaded with NO control flow between the loads (rows this thread does not own
     // read field 0 and are masked afterwards), so a group costs one memory round trip instead of eight
     // (profiles/r02_monitor_cost.txt).
-    constexpr int kMonChunk = 8;
+#ifndef NPS_MON_CHUNK
+#define NPS_MON_CHUNK 8
+#endif
+    constexpr int kMonChunk = NPS_MON_CHUNK;
     for (int w0 = 0; w0 < mon.n_watch; w0 += kMonChunk) {
         double wv[kMonChunk];
         int wf[kMonChunk];
