@@ -245,7 +245,43 @@ def cfg7():
     run_scenario("cfg7_turbine_trips_fouling", plants, 240, [1, 2, 3, 5, 8, 12, 20, 40, 80, 160, 240], lambda p, t, sim: NO)
 
 
-ALL = {"cfg1": cfg1, "cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5, "cfg6": cfg6, "cfg7": cfg7}
+def _set(obj, **kw):
+    for k, v in kw.items():
+        assert hasattr(obj, k), k
+        setattr(obj, k, v)
+
+
+# Protection limits moved so that the NORMAL operating point violates them: every trip / alarm branch of the turbine
+# protection, the rotor vibration monitor, the condenser vacuum system and the feedwater protection runs in the reference
+# itself and stays latched for the rest of the run.  The limits are PlantParams, so each case is its own one-plant fixture.
+TRIP_CASES = {
+    "overspeed": lambda sp: _set(sp.turbine.protection_system.config, overspeed_trip=3500.0),
+    "vibration": lambda sp: _set(sp.turbine.protection_system.config, vibration_trip=-1.0, vibration_delay=3.0),
+    "bearing_temp": lambda sp: _set(sp.turbine.protection_system.config, bearing_temp_trip=35.0, bearing_temp_delay=4.0),
+    "thrust_bearing": lambda sp: _set(sp.turbine.protection_system.config, thrust_bearing_trip=1e-4),
+    "low_vacuum": lambda sp: _set(sp.turbine.protection_system.config, low_vacuum_trip=0.004),
+    "thermal_stress": lambda sp: _set(sp.turbine.protection_system.config, max_thermal_stress=1.0e3),
+    "rotor_vibration_alarms": lambda sp: _set(sp.turbine.rotor_dynamics.config, displacement_alarm=-1.0, velocity_alarm=-1.0,
+                                              acceleration_alarm=-1.0, first_critical_speed=3500.0),
+    "vacuum_alarms": lambda sp: _set(sp.condenser.vacuum_system.config, high_pressure_alarm=0.003, high_pressure_trip=0.0035,
+                                     low_motive_pressure_alarm=5.0),
+    "fw_low_suction": lambda sp: _set(sp.feedwater_system.protection_system.config, low_suction_pressure_trip=5.0),
+    "fw_high_discharge": lambda sp: _set(sp.feedwater_system.protection_system.config, high_discharge_pressure_trip=2.0),
+    "fw_low_flow": lambda sp: _set(sp.feedwater_system.protection_system.config, low_flow_trip=5000.0),
+}
+
+
+def cfg8(only=None):
+    """One fixture per protection path (tests/golden/trip_<case>.npz): 60 steps at dt = 1 s."""
+    for name, tweak in TRIP_CASES.items():
+        if only and name not in only:
+            continue
+        plants = _plants(["oil_top_off"], dt=1.0, heat_source="constant", noise_enabled=False)
+        tweak(plants[0].sim.secondary_physics)
+        run_scenario("trip_" + name, plants, 60, [1, 2, 3, 4, 5, 6, 8, 12, 20, 40, 60], lambda p, t, sim: NO)
+
+
+ALL = {"cfg8": cfg8, "cfg1": cfg1, "cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5, "cfg6": cfg6, "cfg7": cfg7}
 
 if __name__ == "__main__":
     if not R.reference_available():

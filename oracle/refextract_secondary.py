@@ -514,7 +514,24 @@ def secondary(sec, d):
     d[P + "condenser_pressure"] = float(last["condenser_pressure"]) if last else 0.0
     d[P + "heat_rate_kj_kwh"] = float(last["heat_rate_kj_kwh"]) if last else 0.0
     tnet = float(last["turbine_electrical_power_net"]) if last else 0.0
-    d[P + "power_reduction_factor"] = (float(last["electrical_power_mw"]) / tnet if tnet else (1.0 if not last else 0.0))
+    # power_reduction_factor is a local of update_system (systems/secondary/__init__.py:864-921): electrical = net * factor.
+    # With a tripped turbine the net output is 0 and the quotient says nothing; the factor then follows from the same
+    # three conditions on the reference's own outputs (the energy-conservation branch cannot fire: thermal_power_mw IS
+    # the primary thermal power there).
+    if tnet:
+        factor = float(last["electrical_power_mw"]) / tnet
+    elif not last:
+        factor = 1.0
+    else:
+        factor = 1.0
+        if float(last["feedwater_total_flow"]) < 300.0:
+            factor = 0.0
+        else:
+            if float(last["total_steam_flow"]) < 150.0:
+                factor *= 0.1
+            if float(last["sg_avg_pressure"]) < 0.5:
+                factor *= 0.1
+    d[P + "power_reduction_factor"] = factor
 
 
 def report(sec, d):

@@ -11,7 +11,10 @@ from tests import _util as U
 
 pytestmark = pytest.mark.gpu
 
-SCENARIOS = ["cfg1_oil_top_off", "cfg2_steady", "cfg3_loadfollow", "cfg4_scram", "cfg5_degradation", "cfg6_secondary_trips", "cfg7_turbine_trips_fouling"]
+from tests.test_oracle_vs_reference_golden import TRIP_SCENARIOS  # noqa: E402  (one plant per protection path)
+
+SCENARIOS = ["cfg1_oil_top_off", "cfg2_steady", "cfg3_loadfollow", "cfg4_scram", "cfg5_degradation", "cfg6_secondary_trips",
+             "cfg7_turbine_trips_fouling"] + TRIP_SCENARIOS
 
 
 def _sim(state0, params):
@@ -730,6 +733,40 @@ def test_fused_launches_report_the_same_event_steps_as_single_steps(name):
         assert len(ev_a) > 0                                        # degraded plants do cross maintenance thresholds
         trips = torch.stack(list(a.watch_steps().values()))
         assert int((trips >= 0).sum()) >= 2                         # and do latch trips, at known steps
+
+
+@pytest.mark.parametrize("name", TRIP_SCENARIOS)
+def test_trip_latch_steps_equal_the_reference_inside_one_fused_launch(name):
+    """Each trip_* fixture latches one protection path of the live reference.  All 60 steps run as ONE monitored launch;
+    the step the monitor stamps for every watched latch must be the step at which the reference's flag first reads 1
+    (the fixtures checkpoint steps 1..6 one by one), and latches the reference never sets must stay unstamped."""
+    import torch
+    from nuclear_sim_b200 import field_index
+    g = U.load_golden(name)
+    ix = field_index()
+    watch = ["turb.prot_trip_active", "fw.prot_system_trip_active", "cond.vs_trip_high_pressure", "cond.vs_alarm_high_pressure",
+             "turb.vib_displacement_alarm", "turb.vib_critical_speed_alarm"]
+    sim = _sim(g["state0"], g["params"])
+    sim.enable_monitor(watch=watch, max_k=60)
+    _advance(sim, g, 0, 60, kmax=60)
+    assert sim.n_launches == 1
+    got = {w: int(s[0]) for w, s in sim.watch_steps().items()}
+    cps = [int(c) for c in g["checkpoints"]]
+    n_latched = 0
+    for w in watch:
+        col = g["states"][:, 0, ix[w]]
+        if float(g["state0"][0, ix[w]]) != 0.0:
+            continue
+        on = np.flatnonzero(col != 0.0)
+        if len(on) == 0:
+            assert got[w] == -1, (w, got[w])
+            continue
+        c = int(on[0])
+        lo = cps[c - 1] if c > 0 else 0              # flag still 0 after `lo` steps, 1 after cps[c] steps
+        assert lo <= got[w] < cps[c], (w, got[w], lo, cps[c])
+        n_latched += 1
+    assert n_latched >= 1, "the fixture latches nothing that is watched"
+    U.assert_states_close(sim.state_numpy(), g["states"][-1], U.TOL_STEP * 60, f"{name} step 60 (one launch)")
 
 
 def test_status_word_reports_the_nan_reset():
