@@ -268,6 +268,13 @@ TRIP_CASES = {
     "fw_low_suction": lambda sp: _set(sp.feedwater_system.protection_system.config, low_suction_pressure_trip=5.0),
     "fw_high_discharge": lambda sp: _set(sp.feedwater_system.protection_system.config, high_discharge_pressure_trip=2.0),
     "fw_low_flow": lambda sp: _set(sp.feedwater_system.protection_system.config, low_flow_trip=5000.0),
+    # the NPSH protection object is shared by the four pumps and keeps what the LAST pump left in it
+    "fw_npsh_alarm": lambda sp: _set(list(sp.feedwater_system.pump_system.pumps.values())[3].state, npsh_available=6.0),
+    "fw_npsh_trip": lambda sp: (_set(list(sp.feedwater_system.pump_system.pumps.values())[3].state, npsh_available=6.0),
+                                _set(sp.feedwater_system.protection_system.config, low_suction_pressure_trip=8.0)),
+    # lag ejector started by the pressure rule, then lead / lag rotation after 20 s
+    "vacuum_lag_rotation": lambda sp: _set(sp.condenser.vacuum_system.config, auto_start_pressure=0.003, auto_stop_pressure=0.002,
+                                           rotation_interval=20.0 / 3600.0),
 }
 
 
