@@ -272,6 +272,9 @@ TRIP_CASES = {
     "fw_npsh_alarm": lambda sp: _set(list(sp.feedwater_system.pump_system.pumps.values())[3].state, npsh_available=6.0),
     "fw_npsh_trip": lambda sp: (_set(list(sp.feedwater_system.pump_system.pumps.values())[3].state, npsh_available=6.0),
                                 _set(sp.feedwater_system.protection_system.config, low_suction_pressure_trip=8.0)),
+    # cooling-water velocity above the tube vibration-damage threshold; steam demand split evenly instead of by primary flow
+    "cond_tube_vibration": lambda sp: _set(sp.condenser.tube_degradation.config, vibration_damage_threshold=0.5),
+    "sg_no_load_balancing": lambda sp: _set(sp.steam_generator_system.config, auto_load_balancing=False),
     # lag ejector started by the pressure rule, then lead / lag rotation after 20 s
     "vacuum_lag_rotation": lambda sp: _set(sp.condenser.vacuum_system.config, auto_start_pressure=0.003, auto_stop_pressure=0.002,
                                            rotation_interval=20.0 / 3600.0),
@@ -288,7 +291,59 @@ def cfg8(only=None):
         run_scenario("trip_" + name, plants, 60, [1, 2, 3, 4, 5, 6, 8, 12, 20, 40, 60], lambda p, t, sim: NO)
 
 
-ALL = {"cfg8": cfg8, "cfg1": cfg1, "cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5, "cfg6": cfg6, "cfg7": cfg7}
+def cfg9():
+    """Pump-level trips, pump start / stop dynamics, the un-frozen sensor path and pH-controller modes that no other
+    fixture reaches (found with gcov on the host build of the restatement): one forced condition per plant, written into
+    the reference's own objects before the first step."""
+    plants = _plants(["oil_top_off"] * 17, dt=1.0, heat_source="constant", noise_enabled=False)
+
+    def pumps(i):
+        return list(plants[i].sim.secondary_physics.feedwater_system.pump_system.pumps.values())
+    from systems.primary.coolant.pump_models import PumpStatus
+    # 0: suction pressure (frozen at its IC value) below the 0.2 MPa pump trip
+    pumps(0)[0].state.suction_pressure = 0.15
+    # 1 / 2: oil reservoir nearly empty / overfilled
+    pumps(1)[1].lubrication_system.oil_level = 3.0
+    pumps(2)[2].lubrication_system.oil_level = 106.0
+    # 3: seal leakage above its trip
+    pumps(3)[0].lubrication_system.seal_leakage_rate = 12.0
+    # 4: every component moderately worn: no single wear trip, the combined-wear trip
+    for k in pumps(4)[1].lubrication_system.component_wear:
+        pumps(4)[1].lubrication_system.component_wear[k] = 7.5
+    # 5: mild NPSH deficit on a running pump: cavitation without a trip (intensity, damage, noise, vibration)
+    pumps(5)[2].state.npsh_available = 13.0
+    # 6: NPSH below the critical 4 m
+    pumps(6)[0].state.npsh_available = 3.0
+    # 7: the standby pump started, a running pump stopped (STARTING / STOPPING ramps)
+    pumps(7)[3].start_pump()
+    pumps(7)[0].stop_pump()
+    # 8: no pump carries the initial-conditions flag: suction pressure and NPSH follow the system every step
+    for q in pumps(8):
+        if hasattr(q, "_initial_conditions_applied"):
+            del q._initial_conditions_applied
+    # 9: hot pump motor and oil (equipment-protection timers and alarms)
+    pumps(9)[1].lubrication_system.oil_temperature = 118.0
+    # 10 / 11 / 12: pH controller in manual mode / low chemical tanks / measured pH above the trip band
+    ph = lambda i: plants[i].sim.secondary_physics.ph_control_system.controller
+    st10 = ph(10).state
+    st10.control_mode = type(st10.control_mode)("MANUAL") if not hasattr(type(st10.control_mode), "MANUAL") else type(st10.control_mode).MANUAL
+    st10.manual_output = 35.0
+    ph(11).state.ammonia_tank_level, ph(11).state.morpholine_tank_level = 12.0, 15.0
+    plants[12].sim.secondary_physics.water_chemistry.ph = 10.4
+    # 13: feedwater diagnostics health collapsed (system-level diagnostic trip)
+    plants[13].sim.secondary_physics.feedwater_system.diagnostics.overall_health_score = 0.2
+    # 14: rotor almost at rest (thermal-bow accumulation below 100 rpm)
+    plants[14].sim.secondary_physics.turbine.rotor_dynamics.rotor_speed = 40.0
+    # 15: a running pump far below its speed setpoint (rate-limited speed ramp)
+    pumps(15)[1].state.speed_percent = 55.0
+    # 16: a NaN written into the fuel temperature before step 3: the silent reset of thermal_hydraulics.py:257-269
+    def inject(p, t):
+        return ("pri.fuel_temperature", float("nan")) if (p == 16 and t == 3) else None
+    run_scenario("cfg9_pump_trips_modes", plants, 90, [1, 2, 3, 4, 5, 6, 8, 12, 20, 30, 45, 60, 90], lambda p, t, sim: NO,
+                 inject=inject)
+
+
+ALL = {"cfg9": cfg9, "cfg8": cfg8, "cfg1": cfg1, "cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5, "cfg6": cfg6, "cfg7": cfg7}
 
 if __name__ == "__main__":
     if not R.reference_available():

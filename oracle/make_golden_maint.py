@@ -68,7 +68,16 @@ EFFECT_CASES = [
     ("SJE-001", "vacuum_ejector_cleaning", None), ("SJE-002", "vacuum_ejector_mechanical_cleaning", None),
     ("SJE-001", "vacuum_ejector_nozzle_replacement", None), ("SJE-002", "vacuum_ejector_inspection", None),
     ("SJE-001", "routine_maintenance", None), ("SJE-002", "oil_change", None),
+    # the findings-dependent branches of the pump inspections and the lubrication check (worn pump, low oil: EFFECT_TWEAKS)
+    ("FWP-4", "bearing_inspection", None), ("FWP-4", "impeller_inspection", None), ("FWP-4", "lubrication_system_check", None),
 ]
+
+
+def _worn_pump(inst):
+    L = inst.lubrication_system
+    for k in L.component_wear:
+        L.component_wear[k] = 12.5
+    L.oil_level, L.oil_contamination_level = 81.0, 13.0
 
 
 def _degrade_turbine_lub(inst):
@@ -83,7 +92,8 @@ def _degrade_ejector(inst):
     inst.overall_performance_factor = inst.nozzle_fouling_factor * inst.diffuser_fouling_factor * inst.nozzle_erosion_factor
 
 
-EFFECT_TWEAKS = {"TB-LUB-001": _degrade_turbine_lub, "SJE-001": _degrade_ejector, "SJE-002": _degrade_ejector}
+EFFECT_TWEAKS = {"TB-LUB-001": _degrade_turbine_lub, "SJE-001": _degrade_ejector, "SJE-002": _degrade_ejector,
+                 "FWP-4": _worn_pump}
 
 
 def runner_style_plant(action, dt=5.0, noise=False):
