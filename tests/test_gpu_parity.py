@@ -735,7 +735,8 @@ def test_fused_launches_report_the_same_event_steps_as_single_steps(name):
         assert int((trips >= 0).sum()) >= 2                         # and do latch trips, at known steps
 
 
-@pytest.mark.parametrize("name", TRIP_SCENARIOS)
+@pytest.mark.parametrize("name", [t for t in TRIP_SCENARIOS if t not in ("trip_vacuum_lag_rotation", "trip_cond_tube_vibration",
+                                                                       "trip_sg_no_load_balancing")])
 def test_trip_latch_steps_equal_the_reference_inside_one_fused_launch(name):
     """Each trip_* fixture latches one protection path of the live reference.  All 60 steps run as ONE monitored launch;
     the step the monitor stamps for every watched latch must be the step at which the reference's flag first reads 1
@@ -745,7 +746,8 @@ def test_trip_latch_steps_equal_the_reference_inside_one_fused_launch(name):
     g = U.load_golden(name)
     ix = field_index()
     watch = ["turb.prot_trip_active", "fw.prot_system_trip_active", "cond.vs_trip_high_pressure", "cond.vs_alarm_high_pressure",
-             "turb.vib_displacement_alarm", "turb.vib_critical_speed_alarm"]
+             "turb.vib_displacement_alarm", "turb.vib_critical_speed_alarm", "fw.prot_npsh_low_alarm_active",
+             "fw.prot_npsh_critical_trip_active"]
     sim = _sim(g["state0"], g["params"])
     sim.enable_monitor(watch=watch, max_k=60)
     _advance(sim, g, 0, 60, kmax=60)
