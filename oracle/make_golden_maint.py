@@ -202,6 +202,48 @@ def sweep():
                         state_names=np.array(L.field_names("PlantState")))
 
 
+def orchestrator_sweep(n_per_component=100, seed=77):
+    """tests/golden/orchestrator_sweep.json.gz: decisions of the reference's MaintenanceOrchestrator (decision_only, called the
+    way StateManager calls it: state_manager.py:1540-1572) for random sets of 1-5 simultaneous violations of one component,
+    drawn from that component's own threshold rows of the maintenance template, with values on both sides of every
+    promotion / comprehensive trigger."""
+    R.setup_paths()
+    from systems.maintenance.maintenance_orchestrator import MaintenanceOrchestrator
+    with open(os.path.join(_REPO, "nuclear-sim_b200", "data", "maintenance_system_template.json")) as fh:
+        cfg = json.load(fh)
+    from nuclear_sim_b200.maintenance import ThresholdTable
+    rows = ThresholdTable(cfg).rows
+    by_comp = {}
+    for r in rows:
+        by_comp.setdefault(r.component_id, []).append(r)
+    orch = MaintenanceOrchestrator()
+    rng = np.random.RandomState(seed)
+    cases = []
+    for cid in list(by_comp) + ["TB-LUB-001", "XX-UNKNOWN-9"]:
+        pool = by_comp.get(cid) or by_comp["FWP-1"]
+        for _ in range(n_per_component):
+            k = int(rng.randint(1, 6))
+            pick = [pool[j] for j in rng.choice(len(pool), size=min(k, len(pool)), replace=False)]
+            viol = []
+            for r in pick:
+                thr = float(r.threshold)
+                scale = rng.choice([0.2, 0.9, 1.01, 1.2, 2.0, 5.0, 20.0])
+                val = float(thr * scale if thr != 0 else scale)
+                viol.append({"parameter": r.parameter, "value": val, "action": r.action, "threshold": thr,
+                             "comparison": r.comparison, "priority": r.priority, "component_id": r.sub_component})
+            requested = viol[0]["action"] if rng.rand() < 0.9 else None
+            with R.quiet():
+                d = orch.orchestrate_maintenance(component=None, component_id=cid, violations=[dict(v) for v in viol],
+                                                 requested_action=requested, decision_only=True)
+            cases.append({"component": cid, "violations": viol, "requested": requested, "selected": d.get("selected_action"),
+                          "decision": d.get("orchestration_decision")})
+    import gzip
+    with gzip.open(os.path.join(GOLDEN, "orchestrator_sweep.json.gz"), "wt", compresslevel=9) as fh:
+        json.dump({"cases": cases}, fh, separators=(",", ":"))
+    from collections import Counter
+    print("[orchestrator]", len(cases), "cases;", Counter(c["decision"] for c in cases))
+
+
 def scenario(name, action, T, dt=5.0, tweak=None):
     """Full step with maintenance; records states, events, work orders."""
     rp, cfg = runner_style_plant(action, dt=dt)
@@ -286,6 +328,8 @@ if __name__ == "__main__":
         scenarios()
     if "sweep" in what:
         sweep()
+    if "orchestrator" in what:
+        orchestrator_sweep()
 
 
 def state_log_csv(T=12):

@@ -139,6 +139,22 @@ def test_orchestrator_decisions():
     assert M.infer_component_type("SECONDARY-COMP-001-SG") == "steam_generator"
 
 
+def test_orchestrator_sweep_matches_reference():
+    """2 700 random sets of 1-5 simultaneous violations (every component of the template + two ids outside it), decided by
+    the reference's own MaintenanceOrchestrator (oracle/make_golden_maint.py orchestrator): same selected action."""
+    import gzip
+    M = _maint()
+    with gzip.open(os.path.join(U.GOLDEN, "orchestrator_sweep.json.gz"), "rt") as fh:
+        cases = json.load(fh)["cases"]
+    assert len(cases) >= 2000
+    changed = 0
+    for c in cases:
+        got = M.orchestrate(c["component"], c["violations"], c["requested"])
+        assert got == c["selected"], (c["component"], c["requested"], [(v["parameter"], v["value"]) for v in c["violations"]])
+        changed += int(c["selected"] != c["requested"])
+    assert changed >= 200          # promotions / comprehensive actions do occur in the sweep
+
+
 SCENARIOS = ["oil_top_off", "tsp_chemical_cleaning", "oil_change", "scale_removal"]
 
 
