@@ -182,7 +182,8 @@ int nps_log_row(nps_handle* h, const double* d_state, double* d_ring, int64_t ri
 /* --- maintenance action effects (AutoMaintenanceSystem._execute_work_order -> component.perform_maintenance,
  *     systems/maintenance/auto_maintenance.py:504-673) ---
  * Applies n_requests (plant, target, action, arg) requests IN ORDER to the device state; requests for the same plant
- * are serialised.  target: 0-3 FWP-1..4, 4 FEE-001, 5-7 SG-0..2, 8 SG system, 9-22 HP-1..LP-6, 23 turbine, 24 condenser.
+ * are serialised.  target: 0-3 FWP-1..4, 4 FEE-001, 5-7 SG-0..2, 8 SG system, 9-22 HP-1..LP-6, 23 turbine, 24 condenser,
+ * 25 TB-LUB-001 (turbine bearing lubrication), 26-27 SJE-001..2 (steam jet ejectors).
  * action: index into nps_maintenance_action_name(); arg: bearing selector for bearing_replacement
  * (0 all, 1 motor_bearings, 2 pump_bearings, 3 thrust_bearing).  h_status[i]: 0 failed (MaintenanceResult.success
  * False), 1 success, 2 target has no restated perform_maintenance.  Host arrays; synchronises on the stream. */
