@@ -198,6 +198,43 @@ int nps_apply_maintenance(nps_handle* h, double* d_state, const int32_t* h_plant
 int nps_read_fields(nps_handle* h, const double* d_state, const int32_t* fields, int n_fields, double* out_host,
                     void* cuda_stream);
 
+/* --- work-order table: the host side of the automatic maintenance loop, native (no device work) ---
+ * What AutoMaintenanceSystem keeps per plant, for N plants: StateManager._check_maintenance_thresholds batching
+ * (simulator/state/state_manager.py:1307-1369: the violations of one component in one step are ONE event),
+ * _create_automatic_work_order (systems/maintenance/auto_maintenance.py:398-466: known action, the 24-"hour" dedupe stamp
+ * compared in minutes, no active order for the same (component, action), priority delay) and update /
+ * _execute_work_order (auto_maintenance.py:200-236, 504-580: due orders in creation order, at HEAD one per plant per
+ * update).  Threshold rows are described once: component of the row, its rule table (value > rule_thr[r][j] selects
+ * rule_act[r][j], first match wins), fallback action, own action, priority 0..4 (LOW..EMERGENCY), sub-component.
+ * All arrays are host arrays owned by the caller; every function returns < 0 on bad arguments. */
+typedef struct nps_wo_table nps_wo_table;
+int nps_wo_create(int64_t n_plants, int n_components, int n_rows, int max_rules, const int64_t* row_comp,
+                  const double* rule_thr, const int64_t* rule_act, const int64_t* fallback, const int64_t* row_action,
+                  const int64_t* row_prio, const int64_t* row_sub, const double* prio_delay_minutes, double dedupe_window,
+                  int head_quirks, nps_wo_table** out);
+void nps_wo_destroy(nps_wo_table* t);
+/* violations of one step, sorted by (plant, row) -> groups per (plant, component) with the single-violation decision;
+ * groups with several violations are counted in *n_multi (MaintenanceOrchestrator decides those: the caller patches
+ * g_act / g_prio / g_sub before nps_wo_issue).  Returns the number of groups. */
+int64_t nps_wo_group(const nps_wo_table* t, int64_t n, const int64_t* plant, const int64_t* row, const double* value,
+                     int64_t* g_start, int64_t* g_count, int64_t* g_plant, int64_t* g_comp, int64_t* g_act,
+                     int64_t* g_prio, int64_t* g_sub, int64_t* n_multi);
+/* decided events -> work orders; out_group / out_seq: group index and WO number of every order created; returns how many */
+int64_t nps_wo_issue(nps_wo_table* t, double t_minutes, int64_t n_groups, const int64_t* g_plant, const int64_t* g_comp,
+                     const int64_t* g_act, const int64_t* g_prio, const int64_t* g_sub, const uint8_t* act_ok,
+                     int64_t n_actions, int64_t* out_group, int64_t* out_seq);
+int64_t nps_wo_n_pending(const nps_wo_table* t);
+/* the orders update(t_minutes) executes, as columns (capacity cap each); returns the count, or the capacity needed */
+int64_t nps_wo_due(nps_wo_table* t, double t_minutes, int64_t cap, int64_t* plant, int64_t* comp, int64_t* act,
+                   int64_t* prio, int64_t* sub, int64_t* seq, double* created, double* planned);
+int nps_wo_complete(nps_wo_table* t);                                    /* the orders of the last nps_wo_due are done */
+int nps_wo_reset_plants(nps_wo_table* t, const int64_t* plants, int64_t n);
+int nps_wo_sizes(const nps_wo_table* t, int64_t* n_pending, int64_t* n_stamps);
+int nps_wo_export(const nps_wo_table* t, int64_t* pend_cols, double* pend_times, int64_t* stamp_keys, double* stamp_times,
+                  int64_t* n_created);
+int nps_wo_import(nps_wo_table* t, int64_t n_pending, const int64_t* pend_cols, const double* pend_times, int64_t n_stamps,
+                  const int64_t* stamp_keys, const double* stamp_times, const int64_t* n_created);
+
 #ifdef __cplusplus
 }
 #endif

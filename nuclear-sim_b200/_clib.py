@@ -65,6 +65,24 @@ def lib() -> ctypes.CDLL:
     L.nps_maintenance_action_name.restype = c_char_p
     L.nps_maintenance_action_name.argtypes = [c_int]
     L.nps_apply_maintenance.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]
+    # host-side work-order table (csrc/nps_workorders.cpp)
+    c_double = ctypes.c_double
+    L.nps_wo_create.argtypes = [c_int64, c_int, c_int, c_int] + [c_void_p] * 8 + [c_double, c_int, POINTER(c_void_p)]
+    L.nps_wo_destroy.argtypes = [c_void_p]
+    L.nps_wo_destroy.restype = None
+    L.nps_wo_group.argtypes = [c_void_p, c_int64] + [c_void_p] * 11
+    L.nps_wo_group.restype = c_int64
+    L.nps_wo_issue.argtypes = [c_void_p, c_double, c_int64] + [c_void_p] * 6 + [c_int64, c_void_p, c_void_p]
+    L.nps_wo_issue.restype = c_int64
+    L.nps_wo_n_pending.argtypes = [c_void_p]
+    L.nps_wo_n_pending.restype = c_int64
+    L.nps_wo_due.argtypes = [c_void_p, c_double, c_int64] + [c_void_p] * 8
+    L.nps_wo_due.restype = c_int64
+    L.nps_wo_complete.argtypes = [c_void_p]
+    L.nps_wo_reset_plants.argtypes = [c_void_p, c_void_p, c_int64]
+    L.nps_wo_sizes.argtypes = [c_void_p, c_void_p, c_void_p]
+    L.nps_wo_export.argtypes = [c_void_p] + [c_void_p] * 5
+    L.nps_wo_import.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
     if L.nps_abi_version() != 2:
         raise NpsError("libnps_b200.so ABI version mismatch")
     _LIB = L
@@ -82,4 +100,6 @@ EXPORTED_SYMBOLS = [
     "nps_wait", "nps_pipe_depth", "nps_set_small_batch_shape", "nps_measure_fp64_peak", "nps_set_device_rng", "nps_device_rng_draws", "nps_selftest_pow", "nps_observe",
     "nps_set_thresholds", "nps_check_thresholds", "nps_check_thresholds_events", "nps_set_logged_fields", "nps_log_row", "nps_read_fields",
     "nps_n_maintenance_actions", "nps_maintenance_action_name", "nps_apply_maintenance",
+    "nps_wo_create", "nps_wo_destroy", "nps_wo_group", "nps_wo_issue", "nps_wo_n_pending", "nps_wo_due", "nps_wo_complete",
+    "nps_wo_reset_plants", "nps_wo_sizes", "nps_wo_export", "nps_wo_import",
 ]

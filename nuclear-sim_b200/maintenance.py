@@ -971,3 +971,179 @@ class ColumnarAutoMaintenance(BatchedAutoMaintenance):
                                  "action": r.action, "priority": r.priority, "component_id": r.sub_component})
                 self.event_log.append({"t": c["t"], "plant": int(c["plant"][i]), "component": self.comp_ids[int(c["comp"][i])],
                                        "action": self.actions[int(c["act"][i])], "violations": viol})
+
+
+class NativeAutoMaintenance(ColumnarAutoMaintenance):
+    """ColumnarAutoMaintenance with the per-step bookkeeping in the library's native work-order table
+    (csrc/nps_workorders.cpp, nps_wo_* in include/nps_b200.h): grouping of a step's violations, the single-violation
+    decision, dedupe stamps, the pending table, numbering and the due-order selection run in C++ over plain arrays;
+    numpy only carries the log columns.  Same rules, same order, same results as the two classes above
+    (tests/test_maintenance_host.py runs all three on the same scenarios); events with several violations still go
+    through orchestrate() one by one."""
+
+    def __init__(self, sim, table: ThresholdTable, aggressive: bool = True, head_quirks: bool = True):
+        super().__init__(sim, table, aggressive, head_quirks)
+        import ctypes
+        from . import _clib
+        np = self.np
+        self._L = _clib.lib()
+        self._ct = ctypes
+        rule_thr = np.ascontiguousarray(self.rule_thr, dtype=np.float64)
+        rule_act = np.ascontiguousarray(self.rule_act, dtype=np.int64)
+        h = ctypes.c_void_p()
+        keep = [np.ascontiguousarray(a, dtype=np.int64) for a in (self.row_comp, self.fallback, self.row_action, self.row_prio, self.row_sub)]
+        delay = np.ascontiguousarray(self.prio_delay, dtype=np.float64)
+        rc = self._L.nps_wo_create(int(sim.n_plants), int(self.n_comp), int(len(self.row_comp)), int(rule_thr.shape[1]),
+                                   self._p(keep[0]), self._p(rule_thr), self._p(rule_act), self._p(keep[1]), self._p(keep[2]),
+                                   self._p(keep[3]), self._p(keep[4]), self._p(delay), float(self.work_order_cooldown_hours),
+                                   int(bool(head_quirks)), ctypes.byref(h))
+        if rc != 0:
+            raise ValueError("nps_wo_create: bad arguments")
+        self._h = h
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                self._L.nps_wo_destroy(h)
+            except Exception:
+                pass
+
+    @staticmethod
+    def _p(a):
+        return a.__array_interface__["data"][0]      # the raw address (argtypes are c_void_p); ndarray.ctypes costs ~7 us a call
+
+    # -- events -> work orders ---------------------------------------------------------------------------------------
+    def _process_arrays_impl(self, t, plant, row, value) -> int:
+        np = self.np
+        plant = np.ascontiguousarray(plant, dtype=np.int64)
+        row = np.ascontiguousarray(row, dtype=np.int64)
+        value = np.ascontiguousarray(value, dtype=np.float64)
+        n = len(plant)
+        if n == 0:
+            return 0
+        skey = plant * 4096 + row
+        if n > 1 and not bool((skey[1:] >= skey[:-1]).all()):
+            order = np.argsort(skey, kind="stable")
+            plant, row, value = plant[order], row[order], value[order]
+        g = [np.empty(n, dtype=np.int64) for _ in range(7)]       # start, count, plant, comp, act, prio, sub
+        n_multi = self._ct.c_int64(0)
+        ng = int(self._L.nps_wo_group(self._h, n, self._p(plant), self._p(row), self._p(value), *[self._p(a) for a in g],
+                                      self._ct.byref(n_multi)))
+        if ng < 0:
+            raise ValueError("nps_wo_group: event outside the threshold table / plant range")
+        starts, counts, g_plant, g_comp, act, prio, sub = [a[:ng] for a in g]
+        if n_multi.value:
+            for gi in np.flatnonzero(counts > 1):                # several violations of one component in one step
+                lo, hi = int(starts[gi]), int(starts[gi] + counts[gi])
+                viol = []
+                for t_row, v in zip(row[lo:hi], value[lo:hi]):
+                    r = self.table.rows[int(t_row)]
+                    viol.append({"parameter": r.parameter, "value": float(v), "threshold": r.threshold, "comparison": r.comparison,
+                                 "action": r.action, "priority": r.priority, "component_id": r.sub_component})
+                name = orchestrate(self.comp_ids[int(g_comp[gi])], viol, viol[0]["action"])
+                if name not in self.actions:
+                    self._aid(name)
+                    self._refresh_action_tables()
+                act[gi] = self.actions.index(name)
+                pr = max((v["priority"] for v in viol), key=lambda q: _PRIORITY_RANK.get(q, 2))
+                prio[gi] = self._PRIOS.index(pr.upper()) if pr.upper() in self.delays else 1
+                sub[gi] = 0
+                for v in viol:
+                    if v.get("action") == name and v.get("component_id"):
+                        sub[gi] = self.subs.index(v["component_id"])
+                        break
+        self.event_cols.append({"t": t, "plant": g_plant, "comp": g_comp, "act": act.copy(), "starts": starts, "n": counts,
+                                "row_all": row, "value_all": value})
+        ok = np.ascontiguousarray(self.act_known, dtype=np.uint8)
+        out_g, out_seq = np.empty(ng, dtype=np.int64), np.empty(ng, dtype=np.int64)
+        made = int(self._L.nps_wo_issue(self._h, float(t), ng, self._p(g_plant), self._p(g_comp), self._p(act), self._p(prio),
+                                        self._p(sub), self._p(ok), len(ok), self._p(out_g), self._p(out_seq)))
+        if made < 0:
+            raise ValueError("nps_wo_issue: bad arguments")
+        if made == 0:
+            return 0
+        idx = out_g[:made]
+        c_prio = prio[idx]
+        self.created_cols.append({"plant": g_plant[idx], "comp": g_comp[idx], "act": act[idx], "prio": c_prio, "sub": sub[idx],
+                                  "seq": out_seq[:made].copy(), "created": np.full(made, float(t)),
+                                  "planned": float(t) + self.prio_delay[c_prio]})
+        return made
+
+    # -- due work orders -> device -------------------------------------------------------------------------------------
+    def _update_impl(self, t_minutes: float):
+        np = self.np
+        if not self.gate_open(t_minutes):
+            return 0
+        self.last_check_time = t_minutes
+        cap = int(self._L.nps_wo_n_pending(self._h))
+        if cap == 0:
+            return 0
+        ci = [np.empty(cap, dtype=np.int64) for _ in range(6)]    # plant, comp, act, prio, sub, seq
+        cf = [np.empty(cap, dtype=np.float64) for _ in range(2)]  # created, planned
+        nd = int(self._L.nps_wo_due(self._h, float(t_minutes), cap, *[self._p(a) for a in ci], *[self._p(a) for a in cf]))
+        if nd <= 0:
+            return 0
+        d_plant, d_comp, d_act, d_prio, d_sub, d_seq = [a[:nd] for a in ci]
+        req = np.stack([d_plant, self.comp_target[d_comp], self.act_code[d_act],
+                        np.where(self.act_is_bearing[d_act], self.sub_arg[d_sub], 0)], axis=1).astype(np.int32)
+        import time as _time
+        c0 = _time.perf_counter()
+        status = np.asarray(self.sim.apply_maintenance(req))
+        self.seconds_device_calls += _time.perf_counter() - c0
+        if (status == 2).any():
+            bad = int(np.flatnonzero(status == 2)[0])
+            raise NotImplementedError(f"perform_maintenance on {self.comp_ids[int(d_comp[bad])]} is not restated on the device")
+        self._L.nps_wo_complete(self._h)
+        done = {"plant": d_plant, "comp": d_comp, "act": d_act, "prio": d_prio, "sub": d_sub, "seq": d_seq,
+                "created": cf[0][:nd], "planned": cf[1][:nd], "executed_at": np.full(nd, t_minutes), "success": status == 1}
+        self.executed_cols.append(done)
+        if not self.head_quirks:
+            for i in np.flatnonzero(done["success"]):
+                name, cid = self.actions[int(done["act"][i])], self.comp_ids[int(done["comp"][i])]
+                rows = self._reset_rows.get((cid, name))
+                if rows is None:
+                    addressed = _COOLDOWN_RESET.get(name, [])
+                    rows = [r for r in self._rows_by_component.get(cid, []) if self.table.rows[r].parameter in addressed]
+                    self._reset_rows[(cid, name)] = rows
+                if rows:
+                    self.sim.reset_cooldowns(int(done["plant"][i]), rows)
+        return nd
+
+    def reset(self, plants) -> None:
+        np = self.np
+        plants = np.ascontiguousarray(list(plants), dtype=np.int64)
+        self._L.nps_wo_reset_plants(self._h, self._p(plants), len(plants))
+        self.n_created[plants] = 0
+
+    # -- checkpoints -------------------------------------------------------------------------------------------------
+    def state_dict(self) -> dict:
+        np, ct = self.np, self._ct
+        n_p, n_s = ct.c_int64(0), ct.c_int64(0)
+        self._L.nps_wo_sizes(self._h, ct.byref(n_p), ct.byref(n_s))
+        pc, pt = np.zeros((6, n_p.value), dtype=np.int64), np.zeros((2, n_p.value), dtype=np.float64)
+        sk, stt = np.zeros((2, n_s.value), dtype=np.int64), np.zeros(n_s.value, dtype=np.float64)
+        ncr = np.zeros(self.sim.n_plants, dtype=np.int64)
+        self._L.nps_wo_export(self._h, self._p(pc), self._p(pt), self._p(sk), self._p(stt), self._p(ncr))
+        return {"kind": "native", "last_check_time": self.last_check_time, "actions": list(self.actions), "pend_cols": pc,
+                "pend_times": pt, "stamp_keys": sk, "stamp_times": stt, "n_created": ncr, "created_cols": self.created_cols,
+                "executed_cols": self.executed_cols, "event_cols": self.event_cols}
+
+    def load_state_dict(self, d: dict) -> None:
+        if d.get("kind") != "native":
+            raise ValueError("checkpoint was written by a different bookkeeping class")
+        np = self.np
+        for name in d["actions"]:
+            self._aid(name)
+        assert self.actions[:len(d["actions"])] == list(d["actions"])
+        self._refresh_action_tables()
+        self.last_check_time = d["last_check_time"]
+        pc = np.ascontiguousarray(d["pend_cols"], dtype=np.int64)
+        pt = np.ascontiguousarray(d["pend_times"], dtype=np.float64)
+        sk = np.ascontiguousarray(d["stamp_keys"], dtype=np.int64)
+        stt = np.ascontiguousarray(d["stamp_times"], dtype=np.float64)
+        ncr = np.ascontiguousarray(d["n_created"], dtype=np.int64)
+        rc = self._L.nps_wo_import(self._h, pc.shape[1], self._p(pc), self._p(pt), sk.shape[1], self._p(sk), self._p(stt), self._p(ncr))
+        if rc != 0:
+            raise ValueError("nps_wo_import: bad arguments")
+        self.created_cols, self.executed_cols, self.event_cols = d["created_cols"], d["executed_cols"], d["event_cols"]

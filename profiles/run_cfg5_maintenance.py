@@ -23,7 +23,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from nuclear_sim_b200 import load_snapshot, field_index  # noqa: E402
 from nuclear_sim_b200 import scenarios as sc  # noqa: E402
-from nuclear_sim_b200.maintenance import ColumnarAutoMaintenance, ThresholdTable  # noqa: E402
+from nuclear_sim_b200 import maintenance as M  # noqa: E402
+from nuclear_sim_b200.maintenance import ThresholdTable  # noqa: E402
 from nuclear_sim_b200.sharded import ShardedBatchedSimulator  # noqa: E402
 
 
@@ -31,6 +32,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--plants-per-gpu", type=int, default=131072)
     ap.add_argument("--hours", type=float, default=24.0)
+    ap.add_argument("--bookkeeping", choices=["native", "columnar"], default="native",
+                    help="native: the library's work-order table (nps_wo_*); columnar: numpy columns")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -61,7 +64,8 @@ def main():
         return st
     shard = ShardedBatchedSimulator(world * n, s0, params, rank=rank, world=world, device=f"cuda:{local}", states=states)
     cfg = json.load(open(os.path.join(ROOT, "nuclear-sim_b200", "data", "maintenance_system_template.json")))
-    maint = ColumnarAutoMaintenance(shard.sim, ThresholdTable(cfg), aggressive=True)
+    cls = M.NativeAutoMaintenance if args.bookkeeping == "native" else M.ColumnarAutoMaintenance
+    maint = cls(shard.sim, ThresholdTable(cfg), aggressive=True)
     shard.sim.enable_monitor(event_capacity=8 * n)
     steps = int(args.hours * 60 / dt)
     maint.advance(3)                                    # warm-up: first launches, allocations
@@ -98,7 +102,7 @@ def main():
                      "maintenance kernel with its request / status copies, gate-step flag kernel)",
             "threshold_events": int(counts[2]), "work_orders_created": int(counts[0]), "work_orders_executed": int(counts[1]),
             "by_action_rank0": maint.counts_by_action(), "mean_oil_level_pump0": float(summary[:, 0].mean()),
-            "bookkeeping": "ColumnarAutoMaintenance (numpy columns; in-launch threshold events + event-list flag kernel at gate steps)"}))
+            "bookkeeping": type(maint).__name__ + " (in-launch threshold events + event-list flag kernel at gate steps; native = nps_wo_* work-order table in the library, columnar = numpy columns)"}))
     if world > 1:
         dist.destroy_process_group()
 

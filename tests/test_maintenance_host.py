@@ -213,15 +213,17 @@ def test_advance_with_fused_launches_equals_single_steps(name, max_k):
     U.assert_states_close(sim.state_numpy(), g["states"][T - 1][None, :], U.TOL_STEP * T, f"{name} final state")
 
 
+@pytest.mark.parametrize("cls", ["ColumnarAutoMaintenance", "NativeAutoMaintenance"])
 @pytest.mark.parametrize("name", SCENARIOS)
-def test_columnar_bookkeeping_on_reference_scenarios(name):
-    """ColumnarAutoMaintenance (array bookkeeping) through advance(): same events, orders and state as the live reference."""
+def test_columnar_bookkeeping_on_reference_scenarios(name, cls):
+    """ColumnarAutoMaintenance (numpy columns) and NativeAutoMaintenance (the library's work-order table) through
+    advance(): same events, orders and state as the live reference."""
     M = _maint()
     g = np.load(os.path.join(U.GOLDEN, f"maint_{name}.npz"), allow_pickle=False)
     log = json.loads(str(g["log"]))
     T = g["states"].shape[0]
     sim = U.OracleSim(g["state0"], g["params"])
-    maint = M.ColumnarAutoMaintenance(sim, M.ThresholdTable(log["maintenance_system"]), aggressive=True)
+    maint = getattr(M, cls)(sim, M.ThresholdTable(log["maintenance_system"]), aggressive=True)
     noise = np.ascontiguousarray((g["noise"][:, None, :] if g["noise"].ndim == 2 else g["noise"]).transpose(0, 2, 1))
     maint.advance(T, noise=noise)
     maint.materialize_logs()
@@ -229,8 +231,9 @@ def test_columnar_bookkeeping_on_reference_scenarios(name):
     U.assert_states_close(sim.state_numpy(), g["states"][T - 1][None, :], U.TOL_STEP * T, f"{name} final state")
 
 
+@pytest.mark.parametrize("cls", ["ColumnarAutoMaintenance", "NativeAutoMaintenance"])
 @pytest.mark.parametrize("head_quirks", [True, False])
-def test_columnar_equals_object_bookkeeping_on_a_busy_batch(head_quirks):
+def test_columnar_equals_object_bookkeeping_on_a_busy_batch(head_quirks, cls):
     """192 plants with oil levels, contamination and bearing wear staggered around their thresholds (several components
     and several violations per component fire in the same check): the columnar and the object implementation create and
     execute the same work orders at the same times and leave the same state."""
@@ -250,7 +253,7 @@ def test_columnar_equals_object_bookkeeping_on_a_busy_batch(head_quirks):
     st[::5, ix["fw.pump[3].lub.component_wear[4]"]] = 16.5         # seal wear above 16: seal_replacement (-> overhaul with the above)
     sims = [U.OracleSim(st, g["params"]), U.OracleSim(st, g["params"])]
     maints = [M.BatchedAutoMaintenance(sims[0], M.ThresholdTable(cfg), aggressive=True, head_quirks=head_quirks),
-              M.ColumnarAutoMaintenance(sims[1], M.ThresholdTable(cfg), aggressive=True, head_quirks=head_quirks)]
+              getattr(M, cls)(sims[1], M.ThresholdTable(cfg), aggressive=True, head_quirks=head_quirks)]
     for m in maints:
         m.advance(24)
     maints[1].materialize_logs()
@@ -266,7 +269,7 @@ def test_columnar_equals_object_bookkeeping_on_a_busy_batch(head_quirks):
     np.testing.assert_array_equal(sims[0].state_numpy(), sims[1].state_numpy())
 
 
-@pytest.mark.parametrize("cls", ["BatchedAutoMaintenance", "ColumnarAutoMaintenance"])
+@pytest.mark.parametrize("cls", ["BatchedAutoMaintenance", "ColumnarAutoMaintenance", "NativeAutoMaintenance"])
 def test_bookkeeping_state_dict_round_trip(cls):
     """A run cut in the middle (work orders pending), its books moved to a fresh bookkeeping object through state_dict /
     pickle, continues to the same work orders and state as the uninterrupted run — for both bookkeeping classes."""
