@@ -300,7 +300,7 @@ def test_cuda_columnar_maintenance_equals_object_bookkeeping():
     st[::3, ix["fw.pump[3].lub.component_wear[1]"]] = 8.6
     st[::5, ix["fw.pump[3].lub.component_wear[4]"]] = 16.5
     dev, host = _sim(st, g["params"]), U.OracleSim(st, g["params"])
-    md = M.ColumnarAutoMaintenance(dev, M.ThresholdTable(cfg), aggressive=True)
+    md = getattr(M, cls)(dev, M.ThresholdTable(cfg), aggressive=True)
     mh = M.BatchedAutoMaintenance(host, M.ThresholdTable(cfg), aggressive=True)
     md.advance(36)
     mh.advance(36)
