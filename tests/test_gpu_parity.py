@@ -282,9 +282,10 @@ def test_cuda_maintenance_batched_equals_oracle_host_logic():
     U.assert_states_close(sims[0].state_numpy(), sims[1].state_numpy(), U.TOL_STEP * 30, "batched maintenance")
 
 
-def test_cuda_columnar_maintenance_equals_object_bookkeeping():
+@pytest.mark.parametrize("cls", ["ColumnarAutoMaintenance", "NativeAutoMaintenance"])
+def test_cuda_columnar_maintenance_equals_object_bookkeeping(cls):
     """The large-batch path end to end on the device: in-launch threshold events, event-list flag kernel at the gate
-    steps, ColumnarAutoMaintenance, effects applied by the maintenance kernel — against the object bookkeeping on the
+    steps, array bookkeeping (numpy columns / the library's native work-order table), effects applied by the maintenance kernel — against the object bookkeeping on the
     host oracle stand-in, 512 plants staggered around several thresholds, 36 steps."""
     import json
     from nuclear_sim_b200 import maintenance as M, field_index
