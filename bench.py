@@ -461,6 +461,25 @@ def main():
                                         "by one substep), bit-identical to one thread per plant"}
 
 
+    # ------------------------------------------------------------------ config #5: the loop with automatic maintenance
+    # 131,072 plants per GPU, 24 h at dt = 5 min, every pump crossing its oil thresholds: monitored fused launches cut at
+    # the 15-minute gate, native work-order table, maintenance kernel (profiles/run_cfg5_maintenance.py is the same loop)
+    if not args.no_small and not args.quick:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("run_cfg5_maintenance", os.path.join(os.path.dirname(os.path.abspath(__file__)),
+                                                                                      "profiles", "run_cfg5_maintenance.py"))
+        cfg5 = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(cfg5)
+        rec = cfg5.run_loop(131072, 24.0, "native", rank, world, local)
+        if rank == 0:
+            extra["cfg5_maintenance_loop"] = {
+                "value": rec["plant_steps_per_s_whole_loop"], "unit": UNIT, "plants_per_gpu": rec["plants_per_gpu"],
+                "steps": rec["steps"], "launches_per_rank": rec["launches_per_rank"], "work_orders_executed": rec["work_orders_executed"],
+                "seconds_step_kernel": rec["seconds_step_kernel_max_over_ranks"], "seconds_bookkeeping": rec["seconds_bookkeeping_max_over_ranks"],
+                "bookkeeping_over_kernel": rec["bookkeeping_over_kernel"],
+                "note": "BASELINE config #5 end to end: thresholds every step inside the launches, work orders created / executed "
+                        "by the native work-order table and the maintenance kernel; wall clock, max over ranks"}
+
     # ------------------------------------------------------------------ trajectory summaries: the only collective
     summary = shard.gather_summaries(["pri.power_level", "sec.electrical_power_output", "pri.fuel_temperature", "pri.scram_status"])
     mean_power = float(summary[:, 0].mean())

@@ -28,27 +28,10 @@ from nuclear_sim_b200.maintenance import ThresholdTable  # noqa: E402
 from nuclear_sim_b200.sharded import ShardedBatchedSimulator  # noqa: E402
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--plants-per-gpu", type=int, default=131072)
-    ap.add_argument("--hours", type=float, default=24.0)
-    ap.add_argument("--bookkeeping", choices=["native", "columnar"], default="native",
-                    help="native: the library's work-order table (nps_wo_*); columnar: numpy columns")
-    args = ap.parse_args()
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        sys.stdout.flush()
-        saved = os.dup(1)
-        os.dup2(2, 1)            # NCCL's version banner goes to stderr: stdout carries the one JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        dist.barrier()
-        torch.cuda.synchronize()
-        os.dup2(saved, 1)
-        os.close(saved)
+def run_loop(plants_per_gpu=131072, hours=24.0, bookkeeping="native", rank=0, world=1, local=0):
+    """The loop itself (torch.distributed already initialised when world > 1); returns the result record on rank 0,
+    None elsewhere.  bench.py calls this for the `cfg5_maintenance_loop` key of its line."""
+    args = argparse.Namespace(plants_per_gpu=plants_per_gpu, hours=hours, bookkeeping=bookkeeping)
     n, dt = args.plants_per_gpu, 5.0
     s0, params = load_snapshot("pwr3000_oil_top_off_dt5")
     ix = field_index()
@@ -89,7 +72,7 @@ def main():
     summary = shard.gather_summaries(["fw.pump[0].lub.oil_level", "pri.power_level"])
     if rank == 0:
         total, t_dev, t_host, t_numpy, t_devcalls = (float(x) for x in t)
-        print(json.dumps({
+        return {
             "workload": "cfg5: long-horizon maintenance degradation, dt=5 min, launches cut at the 15-min gate, full loop",
             "n_gpus": world, "plants": world * n, "plants_per_gpu": n, "simulated_hours": args.hours, "steps": steps,
             "launches_per_rank": timers["launches"], "plant_steps": world * n * steps,
@@ -102,7 +85,34 @@ def main():
                      "maintenance kernel with its request / status copies, gate-step flag kernel)",
             "threshold_events": int(counts[2]), "work_orders_created": int(counts[0]), "work_orders_executed": int(counts[1]),
             "by_action_rank0": maint.counts_by_action(), "mean_oil_level_pump0": float(summary[:, 0].mean()),
-            "bookkeeping": type(maint).__name__ + " (in-launch threshold events + event-list flag kernel at gate steps; native = nps_wo_* work-order table in the library, columnar = numpy columns)"}))
+            "bookkeeping": type(maint).__name__ + " (in-launch threshold events + event-list flag kernel at gate steps; native = nps_wo_* work-order table in the library, columnar = numpy columns)"}
+    return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--plants-per-gpu", type=int, default=131072)
+    ap.add_argument("--hours", type=float, default=24.0)
+    ap.add_argument("--bookkeeping", choices=["native", "columnar"], default="native",
+                    help="native: the library's work-order table (nps_wo_*); columnar: numpy columns")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)            # NCCL's version banner goes to stderr: stdout carries the one JSON line
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+        torch.cuda.synchronize()
+        os.dup2(saved, 1)
+        os.close(saved)
+    rec = run_loop(args.plants_per_gpu, args.hours, args.bookkeeping, rank, world, local)
+    if rank == 0:
+        print(json.dumps(rec))
     if world > 1:
         dist.destroy_process_group()
 
