@@ -389,8 +389,9 @@ class BatchedNuclearPlantSimulator:
 
     # -- state access -------------------------------------------------------------------------
     def current_time_minutes(self) -> float:
-        """The batch clock (plants stepped in lockstep share it): sim.time_minutes of plant 0."""
-        return float(self.slab[field_index()["sim.time_minutes"], 0].item())
+        """The batch clock: plants stepped in lockstep share it; after a partial reset() the reset plants' own clocks start
+        again, so the largest sim.time_minutes of the batch is the one that keeps running."""
+        return float(self.slab[field_index()["sim.time_minutes"]].max().item())
 
     def state_numpy(self) -> np.ndarray:
         """[n_plants, n_state] host copy in PlantState field order."""

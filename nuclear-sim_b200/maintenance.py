@@ -957,8 +957,9 @@ class ColumnarAutoMaintenance(BatchedAutoMaintenance):
 
     def materialize_logs(self) -> None:
         """Fill created_log / executed_log / event_log (lists of objects, as BatchedAutoMaintenance keeps them)."""
-        ex = {(w.plant, w.work_order_id): w for w in self._orders(self.executed_cols, executed=True)}
-        self.created_log = [ex.get((w.plant, w.work_order_id), w) for w in self._orders(self.created_cols)]
+        # (plant, number, creation time): numbering restarts when a plant's episode is reset
+        ex = {(w.plant, w.work_order_id, w.created): w for w in self._orders(self.executed_cols, executed=True)}
+        self.created_log = [ex.get((w.plant, w.work_order_id, w.created), w) for w in self._orders(self.created_cols)]
         self.executed_log = list(ex.values())
         self.event_log = []
         for c in self.event_cols:

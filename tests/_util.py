@@ -187,7 +187,7 @@ class OracleSim:
         self._step_events = []
 
     def current_time_minutes(self):
-        return float(self.st[0, self.ix["sim.time_minutes"]])
+        return float(self.st[:, self.ix["sim.time_minutes"]].max())
 
     def check_thresholds_events(self):
         self.check_thresholds()

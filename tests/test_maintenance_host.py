@@ -306,6 +306,37 @@ def test_bookkeeping_state_dict_round_trip(cls):
         getattr(M, other)(U.OracleSim(st, g["params"]), M.ThresholdTable(cfg)).load_state_dict(part.state_dict())
 
 
+def test_bookkeeping_reset_of_some_plants_agrees_across_classes():
+    """Episode reset in the middle of a run: the reset plants lose their pending orders, dedupe stamps and numbering (they
+    start again at WO-000001) in all three bookkeeping classes alike; the other plants are untouched."""
+    M = _maint()
+    from nuclear_sim_b200 import field_index
+    g = np.load(os.path.join(U.GOLDEN, "maint_oil_top_off.npz"), allow_pickle=False)
+    cfg = json.loads(str(g["log"]))["maintenance_system"]
+    ix = field_index()
+    n = 16
+    st = np.tile(g["state0"], (n, 1))
+    st[:, ix["fw.pump[0].lub.oil_level"]] = 58.0 + np.linspace(-0.2, 0.6, n)
+    st[::2, ix["fw.pump[1].lub.oil_contamination_level"]] = 15.21
+    logs = []
+    for cls in ("BatchedAutoMaintenance", "ColumnarAutoMaintenance", "NativeAutoMaintenance"):
+        sim = U.OracleSim(st, g["params"])
+        m = getattr(M, cls)(sim, M.ThresholdTable(cfg), aggressive=True)
+        m.advance(5)
+        for p in (3, 6, 9):
+            sim.reset_plant(p)
+            sim._last[:, p] = -np.inf
+        m.reset([3, 6, 9])
+        m.advance(9)
+        if hasattr(m, "materialize_logs"):
+            m.materialize_logs()
+        logs.append(sorted((w.created, w.plant, w.component_id, w.action, w.work_order_id,
+                            -1.0 if w.executed_at is None else w.executed_at, bool(w.success)) for w in m.created_log))
+    assert logs[0] == logs[1] == logs[2] and len(logs[0]) > 20
+    again = [k for k in logs[0] if k[1] in (3, 6, 9) and k[4] == "WO-000001"]
+    assert len(again) >= 2          # numbering restarted for reset plants (their first order before and after the reset)
+
+
 def test_single_violation_fast_path_equals_orchestrate():
     """BatchedAutoMaintenance precomputes the decision for one-violation events; it must agree with orchestrate()
     for every threshold row of the reference configuration, below and above every rule threshold."""
