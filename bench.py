@@ -470,15 +470,15 @@ def main():
                                                                                       "profiles", "run_cfg5_maintenance.py"))
         cfg5 = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(cfg5)
-        rec = cfg5.run_loop(131072, 24.0, "native", rank, world, local)
+        rec = cfg5.run_loop(131072, 24.0, "native", rank, world, local, parts=2, threads=True)
         if rank == 0:
             extra["cfg5_maintenance_loop"] = {
                 "value": rec["plant_steps_per_s_whole_loop"], "unit": UNIT, "plants_per_gpu": rec["plants_per_gpu"],
-                "steps": rec["steps"], "launches_per_rank": rec["launches_per_rank"], "work_orders_executed": rec["work_orders_executed"],
-                "seconds_step_kernel": rec["seconds_step_kernel_max_over_ranks"], "seconds_bookkeeping": rec["seconds_bookkeeping_max_over_ranks"],
-                "bookkeeping_over_kernel": rec["bookkeeping_over_kernel"],
+                "steps": rec["steps"], "parts_per_gpu": rec["parts_per_gpu"], "work_orders_executed": rec["work_orders_executed"],
+                "seconds_total": rec["seconds_total_max_over_ranks"],
                 "note": "BASELINE config #5 end to end: thresholds every step inside the launches, work orders created / executed "
-                        "by the native work-order table and the maintenance kernel; wall clock, max over ranks"}
+                        "by the native work-order table and the maintenance kernel; each GPU's plants as two independent batches "
+                        "whose host work and launches overlap; wall clock, max over ranks"}
 
     # ------------------------------------------------------------------ trajectory summaries: the only collective
     summary = shard.gather_summaries(["pri.power_level", "sec.electrical_power_output", "pri.fuel_temperature", "pri.scram_status"])

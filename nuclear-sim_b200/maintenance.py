@@ -530,6 +530,15 @@ class BatchedAutoMaintenance:
         launch therefore runs up to and including the next gate step, skips the in-launch check of that last substep,
         and the host then does what the reference does at that step, in its order (sim.py:209-223): update() - execute
         due orders on the device - then the threshold check of the gate step (flag kernel)."""
+        for _ in self.advance_launches(n_steps, actions, magnitudes, noise, power_setpoint, t0_minutes, max_k, timers):
+            pass
+
+    def advance_launches(self, n_steps: int, actions=None, magnitudes=None, noise=None, power_setpoint=None,
+                         t0_minutes: Optional[float] = None, max_k: int = 128, timers: Optional[dict] = None):
+        """advance() as a generator: yields right after each launch has been QUEUED (nothing waited for yet) and does
+        that launch's host work - event drain, bookkeeping, maintenance, gate-step check - when resumed.  A driver that
+        holds several independent plant batches (advance_interleaved) resumes them in turn, so one batch's host work
+        runs while another batch's launch occupies the GPU."""
         sim = self.sim
         if getattr(sim, "_mon", None) is None:
             sim.enable_monitor()
@@ -549,6 +558,7 @@ class BatchedAutoMaintenance:
             sim.step(actions=sl(actions, done, done + k), magnitudes=sl(magnitudes, done, done + k),
                      noise=sl(noise, done, done + k), power_setpoint=sl(power_setpoint, done, done + k), K=k,
                      skip_last_check=on_gate)
+            yield done + k
             if timers is not None:      # attribute the wall clock: step kernel (synchronised) vs everything after it
                 getattr(sim, "synchronize", lambda: None)()
                 c1 = _time.perf_counter()
@@ -1148,3 +1158,83 @@ class NativeAutoMaintenance(ColumnarAutoMaintenance):
         if rc != 0:
             raise ValueError("nps_wo_import: bad arguments")
         self.created_cols, self.executed_cols, self.event_cols = d["created_cols"], d["executed_cols"], d["event_cols"]
+
+
+def advance_interleaved(maints: Sequence["BatchedAutoMaintenance"], n_steps: int, inputs: Optional[Sequence[dict]] = None,
+                        streams: Optional[Sequence] = None, max_k: int = 128) -> None:
+    """advance() for several INDEPENDENT plant batches on one GPU, software-pipelined from one host thread.
+
+    Plants do not interact, so a batch can be cut into parts with their own simulator and bookkeeping object (the same
+    global plant ids, initial conditions and inputs).  Each part's launches go to its own CUDA stream; the parts are
+    resumed in turn (advance_launches), so while the host drains and processes the events of part A the GPU runs the
+    launch of part B.  Results are those of advance() on every part - and therefore those of one big batch.
+    inputs: per part, the keyword arguments of advance() (actions, magnitudes, noise, power_setpoint, t0_minutes)."""
+    import contextlib
+    n = len(maints)
+    inputs = list(inputs) if inputs is not None else [{} for _ in range(n)]
+    if streams is None:
+        try:
+            import torch
+            streams = [torch.cuda.Stream(device=m.sim.device) for m in maints] if all(hasattr(m.sim, "slab") for m in maints) else None
+        except Exception:
+            streams = None
+
+    def ctx(i):
+        if streams is None:
+            return contextlib.nullcontext()
+        import torch
+        return torch.cuda.stream(streams[i])
+    if streams is not None:
+        import torch
+        for i, m in enumerate(maints):                 # what was queued on the current stream before (state writes) comes first
+            streams[i].wait_stream(torch.cuda.current_stream(m.sim.device))
+    gens = []
+    for i, m in enumerate(maints):
+        with ctx(i):
+            gens.append(m.advance_launches(n_steps, max_k=max_k, **inputs[i]))
+    live = list(range(n))
+    while live:
+        for i in list(live):
+            with ctx(i):
+                try:
+                    next(gens[i])
+                except StopIteration:
+                    live.remove(i)
+    if streams is not None:
+        import torch
+        for i, m in enumerate(maints):
+            torch.cuda.current_stream(m.sim.device).wait_stream(streams[i])
+
+
+def advance_threaded(maints: Sequence["BatchedAutoMaintenance"], n_steps: int, inputs: Optional[Sequence[dict]] = None,
+                     max_k: int = 128) -> None:
+    """advance() for several INDEPENDENT plant batches on one GPU, one host thread and one CUDA stream per batch.
+
+    Same contract as advance_interleaved; here the overlap comes from the threads: a thread that waits for its stream
+    (event drain, maintenance status) or runs inside the native work-order table has released the interpreter lock, so
+    another batch's host work proceeds and its launch is queued as soon as it is ready."""
+    import threading
+    import torch
+    n = len(maints)
+    inputs = list(inputs) if inputs is not None else [{} for _ in range(n)]
+    streams = [torch.cuda.Stream(device=m.sim.device) for m in maints]
+    for i, m in enumerate(maints):
+        streams[i].wait_stream(torch.cuda.current_stream(m.sim.device))
+    errors: List[BaseException] = []
+
+    def work(i):
+        try:
+            torch.cuda.set_device(maints[i].sim.device)
+            with torch.cuda.stream(streams[i]):
+                maints[i].advance(n_steps, max_k=max_k, **inputs[i])
+        except BaseException as e:      # noqa: BLE001  (re-raised in the caller's thread)
+            errors.append(e)
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(n)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    for i, m in enumerate(maints):
+        torch.cuda.current_stream(m.sim.device).wait_stream(streams[i])

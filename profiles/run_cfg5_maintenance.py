@@ -28,7 +28,7 @@ from nuclear_sim_b200.maintenance import ThresholdTable  # noqa: E402
 from nuclear_sim_b200.sharded import ShardedBatchedSimulator  # noqa: E402
 
 
-def run_loop(plants_per_gpu=131072, hours=24.0, bookkeeping="native", rank=0, world=1, local=0):
+def run_loop(plants_per_gpu=131072, hours=24.0, bookkeeping="native", rank=0, world=1, local=0, parts=1, threads=True):
     """The loop itself (torch.distributed already initialised when world > 1); returns the result record on rank 0,
     None elsewhere.  bench.py calls this for the `cfg5_maintenance_loop` key of its line."""
     args = argparse.Namespace(plants_per_gpu=plants_per_gpu, hours=hours, bookkeeping=bookkeeping)
@@ -45,9 +45,11 @@ def run_loop(plants_per_gpu=131072, hours=24.0, bookkeeping="native", rank=0, wo
             st[:, ix[f"fw.pump[{p}].lub.oil_level"]] = 58.0 + 6.0 * u[p // 3, p % 3]
             st[:, ix[f"fw.pump[{p}].lub.oil_contamination_level"]] = 15.2 - 0.6 * u[(p + 1) // 3 % 2, (p + 1) % 3]
         return st
-    shard = ShardedBatchedSimulator(world * n, s0, params, rank=rank, world=world, device=f"cuda:{local}", states=states)
     cfg = json.load(open(os.path.join(ROOT, "nuclear-sim_b200", "data", "maintenance_system_template.json")))
     cls = M.NativeAutoMaintenance if args.bookkeeping == "native" else M.ColumnarAutoMaintenance
+    if parts > 1:
+        return _run_interleaved(n, dt, args, parts, rank, world, local, s0, params, states, cfg, cls, threads)
+    shard = ShardedBatchedSimulator(world * n, s0, params, rank=rank, world=world, device=f"cuda:{local}", states=states)
     maint = cls(shard.sim, ThresholdTable(cfg), aggressive=True)
     shard.sim.enable_monitor(event_capacity=8 * n)
     steps = int(args.hours * 60 / dt)
@@ -89,10 +91,58 @@ def run_loop(plants_per_gpu=131072, hours=24.0, bookkeeping="native", rank=0, wo
     return None
 
 
+def _run_interleaved(n, dt, args, parts, rank, world, local, s0, params, states, cfg, cls, threads=True):
+    """The same loop with this rank's plants cut into `parts` independent batches (contiguous global id ranges, own
+    simulator, stream and books each) resumed in turn: one part's host work overlaps another part's launch."""
+    shards = [ShardedBatchedSimulator(world * n, s0, params, rank=rank * parts + j, world=world * parts, device=f"cuda:{local}",
+                                      states=states) for j in range(parts)]
+    maints = [cls(sh.sim, ThresholdTable(cfg), aggressive=True) for sh in shards]
+    for sh in shards:
+        sh.sim.enable_monitor(event_capacity=8 * sh.n_plants)
+    steps = int(args.hours * 60 / dt)
+    run = M.advance_threaded if threads else M.advance_interleaved
+    run(maints, 3)                                      # warm-up
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    for m in maints:
+        m.seconds_host = m.seconds_device_calls = 0.0
+    t0 = time.perf_counter()
+    run(maints, steps)
+    torch.cuda.synchronize()
+    total = time.perf_counter() - t0
+    t = torch.tensor([total, sum(m.seconds_host for m in maints)], dtype=torch.float64, device=f"cuda:{local}")
+    counts = torch.tensor([sum(m.n_work_orders_created for m in maints), sum(m.n_work_orders_executed for m in maints),
+                           sum(len(c["plant"]) for m in maints for c in m.event_cols)], dtype=torch.int64, device=f"cuda:{local}")
+    oil = torch.cat([sh.sim.state["fw.pump[0].lub.oil_level"] for sh in shards]).sum().reshape(1)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+        dist.all_reduce(oil, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        by = {}
+        for m in maints:
+            for k, v in m.counts_by_action().items():
+                by[k] = by.get(k, 0) + v
+        return {"workload": "cfg5: long-horizon maintenance degradation, dt=5 min, launches cut at the 15-min gate, full loop",
+                "n_gpus": world, "plants": world * n, "plants_per_gpu": n, "parts_per_gpu": parts, "simulated_hours": args.hours,
+                "steps": steps, "plant_steps": world * n * steps, "plant_steps_per_s_whole_loop": world * n * steps / float(t[0]),
+                "seconds_total_max_over_ranks": float(t[0]), "seconds_host_numpy_max_over_ranks": float(t[1]),
+                "threshold_events": int(counts[2]), "work_orders_created": int(counts[0]), "work_orders_executed": int(counts[1]),
+                "by_action_rank0": by, "mean_oil_level_pump0": float(oil[0]) / (world * n),
+                "bookkeeping": cls.__name__ + f", {parts} independent plant batches per GPU, " +
+                               ("one host thread and CUDA stream each (advance_threaded)" if threads else
+                                "resumed in turn by one host thread (advance_interleaved)") +
+                               ": one batch's host work runs while another batch's launch occupies the GPU"}
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--plants-per-gpu", type=int, default=131072)
     ap.add_argument("--hours", type=float, default=24.0)
+    ap.add_argument("--parts", type=int, default=2, help="independent plant batches per GPU whose host work and launches overlap (1: one batch)")
+    ap.add_argument("--one-thread", action="store_true", help="resume the batches in turn from one host thread instead of one thread per batch")
     ap.add_argument("--bookkeeping", choices=["native", "columnar"], default="native",
                     help="native: the library's work-order table (nps_wo_*); columnar: numpy columns")
     args = ap.parse_args()
@@ -110,7 +160,7 @@ def main():
         torch.cuda.synchronize()
         os.dup2(saved, 1)
         os.close(saved)
-    rec = run_loop(args.plants_per_gpu, args.hours, args.bookkeeping, rank, world, local)
+    rec = run_loop(args.plants_per_gpu, args.hours, args.bookkeeping, rank, world, local, args.parts, not args.one_thread)
     if rank == 0:
         print(json.dumps(rec))
     if world > 1:

@@ -772,6 +772,39 @@ def test_trip_latch_steps_equal_the_reference_inside_one_fused_launch(name):
     U.assert_states_close(sim.state_numpy(), g["states"][-1], U.TOL_STEP * 60, f"{name} step 60 (one launch)")
 
 
+@pytest.mark.parametrize("driver", ["advance_interleaved", "advance_threaded"])
+def test_interleaved_parts_on_streams_equal_one_batch(driver):
+    """advance_interleaved (one host thread resuming the batches in turn) / advance_threaded (one host thread per batch) on the device: 1 024 plants as one batch against the same plants as two batches of 512 with their
+    own CUDA streams, resumed in turn - same work orders at the same times, bit-identical final states."""
+    import json
+    import torch
+    from nuclear_sim_b200 import maintenance as M, field_index
+    g = np.load(os.path.join(U.GOLDEN, "maint_oil_top_off.npz"), allow_pickle=False)
+    cfg = json.loads(str(g["log"]))["maintenance_system"]
+    ix = field_index()
+    n = 1024
+    st = np.tile(g["state0"], (n, 1))
+    rng = np.random.RandomState(8)
+    st[:, ix["fw.pump[0].lub.oil_level"]] = 58.0 + rng.uniform(-0.3, 1.5, n)
+    st[:, ix["fw.pump[2].lub.oil_level"]] = 58.0 + rng.uniform(0.0, 3.0, n)
+    st[:, ix["fw.pump[1].lub.oil_contamination_level"]] = 15.2 - rng.uniform(-0.01, 0.03, n)
+    whole_sim = _sim(st, g["params"])
+    whole = M.NativeAutoMaintenance(whole_sim, M.ThresholdTable(cfg), aggressive=True)
+    whole.advance(30)
+    part_sims = [_sim(st[:512], g["params"]), _sim(st[512:], g["params"])]
+    parts = [M.NativeAutoMaintenance(q, M.ThresholdTable(cfg), aggressive=True) for q in part_sims]
+    getattr(M, driver)(parts, 30)
+    torch.cuda.synchronize()
+    key = lambda w, off: (w.created, w.plant + off, w.component_id, w.action, w.work_order_id,  # noqa: E731
+                          -1.0 if w.executed_at is None else w.executed_at, bool(w.success))
+    for m in [whole] + parts:
+        m.materialize_logs()
+    a = sorted(key(w, 0) for w in whole.created_log)
+    b = sorted([key(w, 0) for w in parts[0].created_log] + [key(w, 512) for w in parts[1].created_log])
+    assert a == b and len(a) > 500
+    assert torch.equal(torch.cat([q.slab for q in part_sims], dim=1), whole_sim.slab)
+
+
 def test_status_word_reports_the_nan_reset():
     """thermal_hydraulics.py:257-269 resets five primary fields when one of them is NaN — silently in the reference; the
     batched engine reproduces the reset and raises bit 0 of the plant's status word, with the step it happened at."""

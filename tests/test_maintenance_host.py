@@ -337,6 +337,36 @@ def test_bookkeeping_reset_of_some_plants_agrees_across_classes():
     assert len(again) >= 2          # numbering restarted for reset plants (their first order before and after the reset)
 
 
+@pytest.mark.parametrize("cls", ["ColumnarAutoMaintenance", "NativeAutoMaintenance"])
+def test_interleaved_parts_equal_one_batch(cls):
+    """advance_interleaved on two halves of a batch (own simulator and books each, resumed in turn launch by launch) creates
+    and executes the same work orders at the same times and ends in the same states as advance() on the whole batch."""
+    M = _maint()
+    from nuclear_sim_b200 import field_index
+    g = np.load(os.path.join(U.GOLDEN, "maint_oil_top_off.npz"), allow_pickle=False)
+    cfg = json.loads(str(g["log"]))["maintenance_system"]
+    ix = field_index()
+    n = 32
+    st = np.tile(g["state0"], (n, 1))
+    rng = np.random.RandomState(3)
+    st[:, ix["fw.pump[0].lub.oil_level"]] = 58.0 + rng.uniform(-0.2, 0.9, n)
+    st[:, ix["fw.pump[1].lub.oil_contamination_level"]] = 15.2 - rng.uniform(-0.02, 0.03, n)
+    whole_sim = U.OracleSim(st, g["params"])
+    whole = getattr(M, cls)(whole_sim, M.ThresholdTable(cfg), aggressive=True)
+    whole.advance(21)
+    parts_sim = [U.OracleSim(st[:16], g["params"]), U.OracleSim(st[16:], g["params"])]
+    parts = [getattr(M, cls)(q, M.ThresholdTable(cfg), aggressive=True) for q in parts_sim]
+    M.advance_interleaved(parts, 21)
+    key = lambda w, off: (w.created, w.plant + off, w.component_id, w.action, w.work_order_id,  # noqa: E731
+                          -1.0 if w.executed_at is None else w.executed_at, bool(w.success))
+    for m in [whole] + parts:
+        m.materialize_logs()
+    a = sorted(key(w, 0) for w in whole.created_log)
+    b = sorted([key(w, 0) for w in parts[0].created_log] + [key(w, 16) for w in parts[1].created_log])
+    assert a == b and len(a) > 30
+    np.testing.assert_array_equal(np.concatenate([q.state_numpy() for q in parts_sim]), whole_sim.state_numpy())
+
+
 def test_single_violation_fast_path_equals_orchestrate():
     """BatchedAutoMaintenance precomputes the decision for one-violation events; it must agree with orchestrate()
     for every threshold row of the reference configuration, below and above every rule threshold."""
