@@ -299,7 +299,6 @@ def cfg9():
 
     def pumps(i):
         return list(plants[i].sim.secondary_physics.feedwater_system.pump_system.pumps.values())
-    from systems.primary.coolant.pump_models import PumpStatus
     # 0: suction pressure (frozen at its IC value) below the 0.2 MPa pump trip
     pumps(0)[0].state.suction_pressure = 0.15
     # 1 / 2: oil reservoir nearly empty / overfilled

@@ -21,7 +21,6 @@ import contextlib
 import io
 import os
 import sys
-import types
 from typing import Dict, Optional
 
 import numpy as np
