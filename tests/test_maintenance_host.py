@@ -367,6 +367,60 @@ def test_interleaved_parts_equal_one_batch(cls):
     np.testing.assert_array_equal(np.concatenate([q.state_numpy() for q in parts_sim]), whole_sim.state_numpy())
 
 
+def test_native_work_order_table_c_api():
+    """nps_wo_* directly through the C ABI (no simulator, no device): grouping with the rule table, the three issuance
+    rules, due selection with and without the one-per-plant quirk, capacity report, bad arguments, export / import."""
+    import ctypes
+    from nuclear_sim_b200 import _clib
+    L = _clib.lib()
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)   # noqa: E731
+    i64 = lambda *v: np.array(v, dtype=np.int64)      # noqa: E731
+    # 3 rows: rows 0, 1 -> component 0, row 2 -> component 1; row 0 promotes to action 5 above 10.0
+    row_comp, fallback, row_action, row_prio, row_sub = i64(0, 0, 1), i64(1, 2, 3), i64(1, 2, 3), i64(1, 3, 0), i64(0, 0, 2)
+    rule_thr, rule_act = np.array([[10.0], [np.inf], [np.inf]]), i64(5, 0, 0).reshape(3, 1)
+    delay = np.array([60.0, 0.0, 0.0, 0.0, 0.0])
+
+    def make(head):
+        h = ctypes.c_void_p()
+        assert L.nps_wo_create(4, 2, 3, 1, P(row_comp), P(rule_thr), P(rule_act), P(fallback), P(row_action), P(row_prio), P(row_sub),
+                               P(delay), 24.0, head, ctypes.byref(h)) == 0
+        return h
+    h = make(1)
+    plant, row, value = i64(0, 0, 1, 3), i64(0, 1, 0, 2), np.array([11.0, 1.0, 9.0, 7.0])
+    g = [np.zeros(4, dtype=np.int64) for _ in range(7)]
+    nm = ctypes.c_int64(0)
+    ng = L.nps_wo_group(h, 4, P(plant), P(row), P(value), *[P(a) for a in g], ctypes.byref(nm))
+    assert ng == 3 and nm.value == 1
+    assert g[0][:3].tolist() == [0, 2, 3] and g[1][:3].tolist() == [2, 1, 1] and g[2][:3].tolist() == [0, 1, 3]
+    assert g[4][:3].tolist() == [5, 1, 3]                    # promoted (11 > 10), fallback (9 < 10), row 2's own action
+    assert g[6][:3].tolist() == [0, 0, 2]                    # sub-component only when the row's own action was selected
+    assert L.nps_wo_group(h, 1, P(i64(9)), P(i64(0)), P(np.array([1.0])), *[P(a) for a in g], ctypes.byref(nm)) == -1
+    ok = np.ones(8, dtype=np.uint8)
+    og, os_ = np.zeros(4, dtype=np.int64), np.zeros(4, dtype=np.int64)
+    issue = lambda t: L.nps_wo_issue(h, t, 3, P(g[2]), P(g[3]), P(g[4]), P(g[5]), P(g[6]), P(ok), 8, P(og), P(os_))   # noqa: E731
+    assert issue(5.0) == 3 and os_[:3].tolist() == [1, 1, 1]
+    assert issue(10.0) == 0                                   # active order / stamp younger than the window
+    cols = [np.zeros(8, dtype=np.int64) for _ in range(6)] + [np.zeros(8), np.zeros(8)]
+    due = lambda t, cap: L.nps_wo_due(h, t, cap, *[P(a) for a in cols])   # noqa: E731
+    assert due(5.0, 8) == 2 and cols[0][:2].tolist() == [0, 1]            # plant 3's order has priority 0: 60 minutes delay
+    assert L.nps_wo_complete(h) == 0 and L.nps_wo_n_pending(h) == 1
+    assert issue(12.0) == 0 and issue(30.0) == 2              # stamps: 12 - 5 < 24 blocks, 30 - 5 >= 24 does not; plant 3 still active
+    assert due(65.0, 1) == 3                                  # capacity too small: the needed size, nothing handed out
+    assert due(65.0, 8) == 3 and sorted(cols[0][:3].tolist()) == [0, 1, 3]
+    n_p, n_s = ctypes.c_int64(0), ctypes.c_int64(0)
+    L.nps_wo_sizes(h, ctypes.byref(n_p), ctypes.byref(n_s))
+    pc, pt = np.zeros((6, n_p.value), dtype=np.int64), np.zeros((2, n_p.value))
+    sk, st_, nc = np.zeros((2, n_s.value), dtype=np.int64), np.zeros(n_s.value), np.zeros(4, dtype=np.int64)
+    assert L.nps_wo_export(h, P(pc), P(pt), P(sk), P(st_), P(nc)) == 0 and nc.tolist() == [2, 2, 0, 1]
+    h2 = make(0)
+    assert L.nps_wo_import(h2, pc.shape[1], P(pc), P(pt), sk.shape[1], P(sk), P(st_), P(nc)) == 0
+    assert L.nps_wo_n_pending(h2) == 3
+    cols2 = [np.zeros(8, dtype=np.int64) for _ in range(6)] + [np.zeros(8), np.zeros(8)]
+    assert L.nps_wo_due(h2, 65.0, 8, *[P(a) for a in cols2]) == 3 and cols2[0][:3].tolist() == sorted(cols2[0][:3].tolist())
+    L.nps_wo_destroy(h)
+    L.nps_wo_destroy(h2)
+
+
 def test_single_violation_fast_path_equals_orchestrate():
     """BatchedAutoMaintenance precomputes the decision for one-violation events; it must agree with orchestrate()
     for every threshold row of the reference configuration, below and above every rule threshold."""
