@@ -194,10 +194,28 @@ NPS_HD void turbine_lubrication_prestep(TurbineState& T, const PlantParams& p, d
     }
 }
 
+// The seven members of a stage that are carried from one step to the next (everything else of the stage is written
+// before it is read).  The stage loop fetches the NEXT stage's copy while it works on the current one (NPS_STAGE_AHEAD):
+// a stage's first touches then wait behind ~1 300 instructions of the previous stage instead of in front of its own.
+struct StageCarried {
+    double actual_efficiency, blade_condition_factor, fouling_factor, blade_wear_factor, deposit_thickness, operating_hours,
+           efficiency_degradation;
+};
+NPS_HD StageCarried stage_carried(const TurbineStageState& s) {
+#if defined(__CUDA_ARCH__) && !defined(NPS_NO_STAGE_AHEAD)
+    const volatile TurbineStageState& v = s;      // volatile: issued here, not sunk to the first use
+    return StageCarried{v.actual_efficiency, v.blade_condition_factor, v.fouling_factor, v.blade_wear_factor, v.deposit_thickness,
+                        v.operating_hours, v.efficiency_degradation};
+#else
+    return StageCarried{s.actual_efficiency, s.blade_condition_factor, s.fouling_factor, s.blade_wear_factor, s.deposit_thickness,
+                        s.operating_hours, s.efficiency_degradation};
+#endif
+}
+
 // TurbineStage.calculate_stage_expansion: stage_system.py:98-292
-NPS_HD void stage_expand(TurbineStageState& s, const PlantParams& p, int k, double inlet_pressure, double inlet_temperature,
-                         double inlet_flow, double outlet_pressure, double extraction_demand, TurbSatMemo& memo,
-                         bool emit_outputs = true) {
+NPS_HD void stage_expand(TurbineStageState& s, const StageCarried& c, const PlantParams& p, int k, double inlet_pressure,
+                         double inlet_temperature, double inlet_flow, double outlet_pressure, double extraction_demand,
+                         TurbSatMemo& memo, bool emit_outputs = true) {
     s.inlet_pressure = inlet_pressure;
     s.inlet_temperature = inlet_temperature;
     s.inlet_flow = inlet_flow;
@@ -239,7 +257,7 @@ NPS_HD void stage_expand(TurbineStageState& s, const PlantParams& p, int k, doub
     double t_isen = (inlet_temperature + 273.15) * py_pow(pr, 0.25) - 273.15;
     double h_isen = stage_steam_enthalpy(t_isen, s.outlet_pressure, memo);
     const double quality_factor = 1.0;   // steam_quality hard-coded 0.99 at stage_system.py:217
-    double total_eff = (s.actual_efficiency * s.blade_condition_factor * s.fouling_factor * s.blade_wear_factor * quality_factor);
+    double total_eff = (c.actual_efficiency * c.blade_condition_factor * c.fouling_factor * c.blade_wear_factor * quality_factor);
     double isen_drop = s.inlet_enthalpy - h_isen;
     if (isen_drop <= 0) {
         double ratio = s.outlet_pressure / inlet_pressure;
@@ -316,6 +334,22 @@ NPS_HD TurbineInlet turbine_inlet_from(const SGSystemState& S) {
     return t;
 }
 
+// A bearing record read with loads that are issued where they stand (device: volatile), so that the NEXT bearing's
+// record travels while the current one is processed - the stage loop's scheme (StageCarried).
+NPS_HD TurbineBearingState bearing_fetch(const TurbineBearingState& b) {
+#if defined(__CUDA_ARCH__) && !defined(NPS_NO_STAGE_AHEAD)
+    const volatile TurbineBearingState& v = b;
+    TurbineBearingState r;
+    r.current_load = v.current_load; r.metal_temperature = v.metal_temperature; r.vibration_displacement = v.vibration_displacement;
+    r.operating_hours = v.operating_hours; r.wear_factor = v.wear_factor; r.efficiency_factor = v.efficiency_factor;
+    r.clearance_increase = v.clearance_increase; r.oil_temperature = v.oil_temperature; r.oil_flow_rate = v.oil_flow_rate;
+    r.oil_contamination_level = v.oil_contamination_level; r.external_oil_temp = v.external_oil_temp;
+    return r;
+#else
+    return b;
+#endif
+}
+
 // Wrapped EnhancedTurbinePhysics.update_state (dt in hours; load_demand as passed = percent)
 NPS_HD void turbine_update(TurbineState& T, const PlantParams& p, const TurbineInlet& S, double load_demand,
                            double condenser_pressure, double dt, TurbineResult& out,
@@ -346,9 +380,11 @@ NPS_HD void turbine_update(TurbineState& T, const PlantParams& p, const TurbineI
         double cur_p = steam_pressure, cur_t = steam_temperature_in, cur_f = steam_flow;
         const double final_pressure = 0.007;
         TurbSatMemo memo; turb_memo_init(memo);
+        StageCarried nxt = stage_carried(T.stage[0]);
         NPS_UNIT_LOOP
         for (int k = 0; k < 14; ++k) {
-            if (k < 13) NPS_PREFETCH(T.stage[k + 1]);
+            const StageCarried c = nxt;
+            if (k < 13) nxt = stage_carried(T.stage[k + 1]);
             double ratio = stage_dynamic_pressure_ratio(p, k, 14, cur_p, steam_flow);
             double outp = cur_p * ratio;
             outp = py_max(outp, final_pressure);
@@ -360,7 +396,7 @@ NPS_HD void turbine_update(TurbineState& T, const PlantParams& p, const TurbineI
             if (k == 2) ed = 25.0 * load_demand; else if (k == 3) ed = 30.0 * load_demand;
             else if (k == 4) ed = 20.0 * load_demand; else if (k == 8) ed = 15.0 * load_demand;
             else if (k == 9) ed = 10.0 * load_demand;
-            stage_expand(T.stage[k], p, k, cur_p, cur_t, cur_f, outp, ed, memo, emit_outputs);
+            stage_expand(T.stage[k], c, p, k, cur_p, cur_t, cur_f, outp, ed, memo, emit_outputs);
             total_power += T.stage[k].power_output;
             total_extraction += T.stage[k].extraction_flow;
             if (k < 8) hp_power += T.stage[k].power_output; else lp_power += T.stage[k].power_output;
@@ -370,15 +406,15 @@ NPS_HD void turbine_update(TurbineState& T, const PlantParams& p, const TurbineI
             // factors, which no later stage reads, so doing it here is the same arithmetic on the same values while
             // the stage record is still on chip.
             TurbineStageState& s = T.stage[k];
-            s.efficiency_degradation += p.ts_fouling_rate * dt;
-            s.deposit_thickness += p.ts_deposit_buildup_rate * dt;
+            s.efficiency_degradation = c.efficiency_degradation + p.ts_fouling_rate * dt;
+            s.deposit_thickness = c.deposit_thickness + p.ts_deposit_buildup_rate * dt;
             s.fouling_factor = 1.0 / (1.0 + s.deposit_thickness / 0.5);
             double wear_inc = p.ts_erosion_rate * dt;
             double blade_wear = wear_inc * py_pow(s.loading_factor, 2.0);
-            s.blade_wear_factor = py_max(0.7, s.blade_wear_factor - blade_wear);
+            s.blade_wear_factor = py_max(0.7, c.blade_wear_factor - blade_wear);
             s.blade_condition_factor = py_min(s.fouling_factor, s.blade_wear_factor);
             s.actual_efficiency = py_max(0.7, p.ts_design_efficiency[k] - s.efficiency_degradation);
-            s.operating_hours += dt;
+            s.operating_hours = c.operating_hours + dt;
         }
         if (prefetch_next) {
             NPS_PREFETCH_FAR(*prefetch_next);
@@ -427,9 +463,11 @@ NPS_HD void turbine_update(TurbineState& T, const PlantParams& p, const TurbineI
         }
         const double weight_per_bearing = p.rd_rotor_mass * 9.81 / 1000.0 / 4;
         const double steam_thrust = (100.0 * load_demand) / 4;
+        TurbineBearingState nxtB = bearing_fetch(T.bearing[0]);
         NPS_UNIT_LOOP
         for (int b = 0; b < 4; ++b) {
-            TurbineBearingState B = T.bearing[b];   // 11 fields: one group of loads, written back after the block
+            TurbineBearingState B = nxtB;           // 11 fields, fetched while the previous bearing was processed; written back after the block
+            if (b < 3) nxtB = bearing_fetch(T.bearing[b + 1]);
             // calculate_bearing_loads: rotor_dynamics.py:83-130 (TB-003 is the thrust bearing)
             double thrust_load = (b == 2) ? steam_thrust : 0.0;
             double thermal_load = fabs(T.thermal_expansion) * p.rd_bearing_stiffness / 1000.0;
