@@ -128,6 +128,10 @@ NPS_HD void fwp_performance_factors(FWPumpState& u, double cavitation_damage) {
 // Lubrication part of update_with_lubrication: pump_lubrication.py:1659-1830 (uses the pump state
 // left by the previous step), followed by update_pump_lubrication_effects (:570-623).
 NPS_HD void fwp_update_lubrication(FWPumpState& u, const PlantParams& p, const PumpSysCond& sc, double dt) {
+    NPS_TOUCH(u.flow_rate); NPS_TOUCH(u.speed_percent); NPS_TOUCH(u.power_consumption); NPS_TOUCH(u.cavitation_intensity);
+    NPS_TOUCH(u.differential_pressure); NPS_TOUCH(u.lub.lubrication_effectiveness); NPS_TOUCH(u.lub.oil_level);
+    for (int c = 0; c < FWL_NCOMP; ++c) NPS_TOUCH(u.lub.component_wear[c]);
+    NPS_TOUCH(u.cavitation_damage); NPS_TOUCH(u.lub.oil_contamination_level); NPS_TOUCH(u.lub.oil_temperature);
     double load_factor = (p.fwp_rated_flow > 0) ? u.flow_rate / p.fwp_rated_flow : 0.0;
     double speed_factor = u.speed_percent / 100.0;
     double elf = (p.fwp_rated_power > 0) ? u.power_consumption / p.fwp_rated_power : 0.0;
