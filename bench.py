@@ -20,6 +20,9 @@ Keys of the JSON line (all plant-steps/s unless noted):
   value_at_power   control: BASELINE config #2 plants (constant heat source, steady 100 %, NO_ACTION), same plant count
   strong_65536     N > 1: the 65,536-plant batch split over the N GPUs (strong scaling point of the north star)
   small_batch      N = 1: 4,096 (config #2 size) and 16,384 (config #4 size) plants on one GPU
+  cfg5_maintenance_loop   BASELINE config #5 end to end: 131,072 plants per GPU, 24 h at dt = 5 min, thresholds inside the
+                   launches, work orders through the native work-order table and the maintenance kernel; each GPU's plants
+                   as two independent batches whose host work and launches overlap (wall clock, max over ranks)
   roofline         SURVEY.md 8(d): frac = max(rate x 2e4 flop / measured FP64 peak, rate x (26,240 / K + 6,312 x logged
                    fraction) B / measured HBM peak), per GPU; the implementation's own traffic figures are named extras
   cpu_baseline     the host C restatement of the reference step on ALL host cores (count stated), bounded sample
