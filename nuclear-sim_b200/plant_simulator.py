@@ -342,10 +342,13 @@ class NuclearPlantSimulator:
                          "steam_flow": g("sec.total_steam_flow", 1665.0), "steam_pressure": g("sec.sg_avg_pressure", 6.895),
                          "condenser_pressure": g("sec.condenser_pressure", 0.007),
                          "condenser_heat_rejection": g("sec.total_system_heat_rejection", 0.0)})
+        if not self.enable_secondary:
+            obs = obs[:12]          # the reference's observation has the 12 primary entries only (sim.py:292-333)
         return {"observation": obs, "reward": float(reward), "done": bool(done), "info": info}
 
     def get_observation(self) -> np.ndarray:
-        return self._engine.observe_plant(self._p)
+        obs = self._engine.observe_plant(self._p)
+        return obs if self.enable_secondary else obs[:12]
 
     def calculate_reward(self, secondary_result: dict = None) -> float:
         """sim.py:500-544 on the current state.  Called by hand it is the primary-side reward unless the caller passes a

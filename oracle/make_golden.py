@@ -41,15 +41,15 @@ def save_snapshot(name, sim):
                         state_names=sn, param_names=pn)
 
 
-def run_scenario(name, plants, T, checkpoints, policy, *, inject=None, seed_base=1000):
+def run_scenario(name, plants, T, checkpoints, policy, *, inject=None, seed_base=1000, strict=True):
     """plants: list of ReferencePlant; policy(p, t, sim) -> (action, magnitude, setpoint_or_nan)."""
     P = len(plants)
     L = R._layout()
     NS = L.N_STATE
-    params = [R.extract_params(rp.sim) for rp in plants]
+    params = [R.extract_params(rp.sim, strict) for rp in plants]
     for q in params[1:]:
         assert np.array_equal(q, params[0]), "plants of one golden must share PlantParams"
-    state0 = np.stack([R.extract_state(rp.sim) for rp in plants])
+    state0 = np.stack([R.extract_state(rp.sim, strict) for rp in plants])
     actions = np.full((T, P), 8, dtype=np.int8)
     mags = np.ones((T, P))
     noise = np.zeros((T, P, 5))
@@ -88,8 +88,9 @@ def run_scenario(name, plants, T, checkpoints, policy, *, inject=None, seed_base
                 done_step[p] = t
             if (t + 1) in cps:
                 c = cps.index(t + 1)
-                states[c, p] = R.extract_state(sim)
-                obs[c, p] = out["observation"]
+                states[c, p] = R.extract_state(sim, strict)
+                o = np.asarray(out["observation"], dtype=np.float64)      # 12 entries without a secondary side: stored with a zero tail
+                obs[c, p, :len(o)] = o
                 rew[c, p] = out["reward"]
     os.makedirs(GOLDEN, exist_ok=True)
     sn, pn = _names()
@@ -342,7 +343,27 @@ def cfg9():
                  inject=inject)
 
 
-ALL = {"cfg9": cfg9, "cfg8": cfg8, "cfg1": cfg1, "cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5, "cfg6": cfg6, "cfg7": cfg7}
+def cfg10():
+    """Primary side alone (NuclearPlantSimulator(enable_secondary=False)): reactor heat source under load-following rods and a
+    mixed action sequence, constant heat source with setpoint steps; the secondary half of the observation is zero."""
+    plants = [R.make_reference_plant(None, dt=1.0, heat_source="reactor", enable_secondary=False),
+              R.make_reference_plant(None, dt=1.0, heat_source="reactor", enable_secondary=False)]
+
+    def policy(p, t, sim):
+        if p == 0:
+            s = np.sin(t / 60.0)
+            return (1 if s > 0.5 else (0 if s < -0.5 else 8)), 0.7, np.nan
+        seq = [10, 8, 9, 8, 2, 3, 4, 5, 6, 7, 0, 1]
+        return seq[(t // 20) % len(seq)], 0.5, np.nan
+    # strict=False: a plant without secondary side has no secondary members; those state fields and parameters are stored as 0
+    run_scenario("cfg10_primary_only", plants, 600, [1, 2, 10, 100, 300, 600], policy, strict=False)
+    plants = [R.make_reference_plant(None, dt=1.0, heat_source="constant", noise_enabled=True, noise_std_percent=0.5,
+                                     enable_secondary=False)]
+    run_scenario("cfg10_primary_only_constant", plants, 600, [1, 2, 10, 100, 300, 600],
+                 lambda p, t, sim: (8, 1.0, (80.0 if t == 100 else (95.0 if t == 300 else np.nan))), strict=False)
+
+
+ALL = {"cfg10": cfg10, "cfg9": cfg9, "cfg8": cfg8, "cfg1": cfg1, "cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5, "cfg6": cfg6, "cfg7": cfg7}
 
 if __name__ == "__main__":
     if not R.reference_available():

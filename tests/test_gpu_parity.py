@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 from tests.test_oracle_vs_reference_golden import TRIP_SCENARIOS  # noqa: E402  (one plant per protection path)
 
 SCENARIOS = ["cfg1_oil_top_off", "cfg2_steady", "cfg3_loadfollow", "cfg4_scram", "cfg5_degradation", "cfg6_secondary_trips",
-             "cfg7_turbine_trips_fouling", "cfg9_pump_trips_modes"] + TRIP_SCENARIOS
+             "cfg7_turbine_trips_fouling", "cfg9_pump_trips_modes", "cfg10_primary_only", "cfg10_primary_only_constant"] + TRIP_SCENARIOS
 
 
 def _sim(state0, params):

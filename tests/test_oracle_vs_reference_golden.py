@@ -14,7 +14,7 @@ TRIP_SCENARIOS = ["trip_overspeed", "trip_vibration", "trip_bearing_temp", "trip
                   "trip_fw_high_discharge", "trip_fw_low_flow", "trip_fw_npsh_alarm", "trip_fw_npsh_trip",
                   "trip_vacuum_lag_rotation", "trip_cond_tube_vibration", "trip_sg_no_load_balancing"]
 SCENARIOS = ["cfg1_oil_top_off", "cfg2_steady", "cfg3_loadfollow", "cfg4_scram", "cfg5_degradation", "cfg6_secondary_trips",
-             "cfg7_turbine_trips_fouling", "cfg9_pump_trips_modes"] + TRIP_SCENARIOS
+             "cfg7_turbine_trips_fouling", "cfg9_pump_trips_modes", "cfg10_primary_only", "cfg10_primary_only_constant"] + TRIP_SCENARIOS
 
 
 @pytest.mark.parametrize("name", SCENARIOS)

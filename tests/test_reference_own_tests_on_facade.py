@@ -16,6 +16,7 @@ import re
 import sys
 import warnings
 
+import numpy as np
 import pytest
 
 from tests import _util as U
@@ -125,3 +126,32 @@ def test_the_comparison_is_not_vacuous():
     assert out["Emergency Shutdown"][0] == "pass"          # Tf := 1600 => scram, rods at 0 (tests/test_scenarios.py:98-110)
     assert out["Load Following"][0] == "pass"
     assert "99.82029897" in out["Steady State Operation"][1]   # the drift the reference itself reports at HEAD
+
+
+def test_primary_only_facade_equals_reference_step_by_step():
+    """NuclearPlantSimulator(enable_secondary=False): the 12-entry observation, reward, done and the primary state of the
+    drop-in class equal the reference's after every step of a rod / boron / flow action sequence."""
+    R.setup_paths()
+    import simulator.core.sim as refsim
+    from systems.primary import ControlAction
+    from nuclear_sim_b200.plant_simulator import NuclearPlantSimulator as Ours
+    R._clear_registries()
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref = refsim.NuclearPlantSimulator(dt=1.0, enable_secondary=False, enable_state_management=False)
+        built = refsim.NuclearPlantSimulator(dt=1.0, enable_secondary=False, enable_state_management=False)
+    s0, p0 = R.extract_state(built, strict=False), R.extract_params(built, strict=False)
+    ours = Ours(dt=1.0, heat_source=built.primary_physics.heat_source, enable_secondary=False, enable_state_management=False,
+                initial_state=s0, params=p0, engine=U.OracleSim(s0, p0))
+    acts = [ControlAction.CONTROL_ROD_WITHDRAW, ControlAction.NO_ACTION, ControlAction.CONTROL_ROD_INSERT, ControlAction.DILUTE_BORON,
+            ControlAction.BORATE_COOLANT, ControlAction.INCREASE_COOLANT_FLOW, ControlAction.DECREASE_COOLANT_FLOW]
+    assert len(ours.get_observation()) == 12 == len(ref.get_observation())
+    for t in range(60):
+        a = acts[(t // 5) % len(acts)]
+        with contextlib.redirect_stdout(io.StringIO()):
+            r = ref.step(a, 0.6)
+        o = ours.step(a, 0.6)
+        assert len(o["observation"]) == 12 == len(r["observation"])
+        np.testing.assert_allclose(o["observation"], r["observation"], rtol=1e-12, atol=1e-14)
+        assert abs(o["reward"] - r["reward"]) <= 1e-12 * max(1.0, abs(r["reward"])) and o["done"] == r["done"]
+        assert abs(ours.state.power_level - ref.state.power_level) <= 1e-10 * max(1.0, abs(ref.state.power_level))
+    R._clear_registries()
