@@ -419,10 +419,10 @@ NPS_HD void feedwater_update(FeedwaterState& fw, WaterChemState& wc, const Plant
         total_demand = 0.0 + individual[0]; total_demand += individual[1]; total_demand += individual[2];
         double avg_err = abs_err_sum / 3.0;
         fw.lc_control_performance = py_max(0.0, 1.0 - avg_err / 2.0);
+        fw.total_flow_demand = total_demand;   // ThreeElementControl.flow_demand_history[-1]: appended by the controller only
     } else {
-        total_demand = manual_total_flow;
+        total_demand = manual_total_flow;      // manual mode (feedwater/physics.py:735-741): the level controller is not called
     }
-    fw.total_flow_demand = total_demand;
 
     PumpSysCond sc;
     sc.feedwater_temperature = fw_temperature;

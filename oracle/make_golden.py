@@ -276,6 +276,10 @@ TRIP_CASES = {
     # cooling-water velocity above the tube vibration-damage threshold; steam demand split evenly instead of by primary flow
     "cond_tube_vibration": lambda sp: _set(sp.condenser.tube_degradation.config, vibration_damage_threshold=0.5),
     "sg_no_load_balancing": lambda sp: _set(sp.steam_generator_system.config, auto_load_balancing=False),
+    # feedwater level control in manual mode (total flow demand taken as given); rotor held below 100 rpm by its speed limit
+    # (thermal-bow accumulation of a rotor at rest)
+    "fw_manual_flow": lambda sp: _set(sp.feedwater_system.config, auto_level_control=False),
+    "rotor_slow": lambda sp: _set(sp.turbine.rotor_dynamics.config, max_speed=90.0),
     # lag ejector started by the pressure rule, then lead / lag rotation after 20 s
     "vacuum_lag_rotation": lambda sp: _set(sp.condenser.vacuum_system.config, auto_start_pressure=0.003, auto_stop_pressure=0.002,
                                            rotation_interval=20.0 / 3600.0),
