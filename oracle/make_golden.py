@@ -280,6 +280,10 @@ TRIP_CASES = {
     # (thermal-bow accumulation of a rotor at rest)
     "fw_manual_flow": lambda sp: _set(sp.feedwater_system.config, auto_level_control=False),
     "rotor_slow": lambda sp: _set(sp.turbine.rotor_dynamics.config, max_speed=90.0),
+    # condenser pressure outside the lead ejector's working range: no capacity, vacuum decays
+    "ejector_out_of_range": lambda sp: [_set(e.config, min_suction_pressure=0.05) for e in
+                                        (sp.condenser.vacuum_system.ejectors.values() if isinstance(sp.condenser.vacuum_system.ejectors, dict)
+                                         else sp.condenser.vacuum_system.ejectors)],
     # lag ejector started by the pressure rule, then lead / lag rotation after 20 s
     "vacuum_lag_rotation": lambda sp: _set(sp.condenser.vacuum_system.config, auto_start_pressure=0.003, auto_stop_pressure=0.002,
                                            rotation_interval=20.0 / 3600.0),
@@ -300,7 +304,7 @@ def cfg9():
     """Pump-level trips, pump start / stop dynamics, the un-frozen sensor path and pH-controller modes that no other
     fixture reaches (found with gcov on the host build of the restatement): one forced condition per plant, written into
     the reference's own objects before the first step."""
-    plants = _plants(["oil_top_off"] * 17, dt=1.0, heat_source="constant", noise_enabled=False)
+    plants = _plants(["oil_top_off"] * 19, dt=1.0, heat_source="constant", noise_enabled=False)
 
     def pumps(i):
         return list(plants[i].sim.secondary_physics.feedwater_system.pump_system.pumps.values())
@@ -343,6 +347,12 @@ def cfg9():
     # 16: a NaN written into the fuel temperature before step 3: the silent reset of thermal_hydraulics.py:257-269
     def inject(p, t):
         return ("pri.fuel_temperature", float("nan")) if (p == 16 and t == 3) else None
+    # 17: every pump out of oil: all four trip, total loss of feedwater (no pump power, steam generators boiling down,
+    # electrical output gated to zero)
+    for q in pumps(17):
+        q.lubrication_system.oil_level = 3.0
+    # 18: NPSH just above the required value on a running pump: cavitation strong enough to accumulate damage, no trip
+    pumps(18)[1].state.npsh_available = 12.05
     run_scenario("cfg9_pump_trips_modes", plants, 90, [1, 2, 3, 4, 5, 6, 8, 12, 20, 30, 45, 60, 90], lambda p, t, sim: NO,
                  inject=inject)
 

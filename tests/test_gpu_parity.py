@@ -738,7 +738,7 @@ def test_fused_launches_report_the_same_event_steps_as_single_steps(name):
 
 @pytest.mark.parametrize("name", [t for t in TRIP_SCENARIOS if t not in ("trip_vacuum_lag_rotation", "trip_cond_tube_vibration",
                                                                        "trip_sg_no_load_balancing", "trip_fw_manual_flow",
-                                                                       "trip_rotor_slow")])
+                                                                       "trip_rotor_slow", "trip_ejector_out_of_range")])
 def test_trip_latch_steps_equal_the_reference_inside_one_fused_launch(name):
     """Each trip_* fixture latches one protection path of the live reference.  All 60 steps run as ONE monitored launch;
     the step the monitor stamps for every watched latch must be the step at which the reference's flag first reads 1

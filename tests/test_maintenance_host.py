@@ -49,6 +49,27 @@ def test_effects_match_reference(oracle_lib):
         U.assert_states_close(st[None, :], z["after"][i][None, :], 1e-13, f"{cid} {action} {sub}")
 
 
+def test_apply_maintenance_error_conventions(oracle_lib):
+    """A bearing selector outside 0..3 makes bearing_replacement fail without touching the state (the reference's
+    'Unknown bearing component' branch, pump_lubrication.py:756-805); a target id without a restated perform_maintenance
+    reports status 2 and changes nothing."""
+    M = _maint()
+    z = _load_effects()
+    params = np.ascontiguousarray(z["params"])
+    oracle_lib.nps_oracle_apply_maintenance.restype = ctypes.c_int
+    st0 = np.ascontiguousarray(z["before"][0])
+    st = st0.copy()
+    assert oracle_lib.nps_oracle_apply_maintenance(U.ptr(st), U.ptr(params), M.target_code("FWP-1"), M.action_code("bearing_replacement"), 7) == 0
+    rep = [i for i, n in enumerate(z["state_names"]) if str(n).startswith("rep.")]
+    keep = np.setdiff1d(np.arange(len(st)), rep)          # the report columns are refreshed after every request
+    assert np.array_equal(st[keep], st0[keep], equal_nan=True)
+    st = st0.copy()
+    assert oracle_lib.nps_oracle_apply_maintenance(U.ptr(st), U.ptr(params), 99, M.action_code("oil_change"), 0) == 2
+    assert np.array_equal(st[keep], st0[keep], equal_nan=True)
+    with pytest.raises(KeyError):
+        M.target_code("SECONDARY-COMP-001-FW")
+
+
 def _load_sweep():
     z = np.load(os.path.join(U.GOLDEN, "maint_effects_sweep.npz"), allow_pickle=False)
     from nuclear_sim_b200 import field_names

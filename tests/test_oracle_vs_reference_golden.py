@@ -13,7 +13,7 @@ TRIP_SCENARIOS = ["trip_overspeed", "trip_vibration", "trip_bearing_temp", "trip
                   "trip_thermal_stress", "trip_rotor_vibration_alarms", "trip_vacuum_alarms", "trip_fw_low_suction",
                   "trip_fw_high_discharge", "trip_fw_low_flow", "trip_fw_npsh_alarm", "trip_fw_npsh_trip",
                   "trip_vacuum_lag_rotation", "trip_cond_tube_vibration", "trip_sg_no_load_balancing",
-                  "trip_fw_manual_flow", "trip_rotor_slow"]
+                  "trip_fw_manual_flow", "trip_rotor_slow", "trip_ejector_out_of_range"]
 SCENARIOS = ["cfg1_oil_top_off", "cfg2_steady", "cfg3_loadfollow", "cfg4_scram", "cfg5_degradation", "cfg6_secondary_trips",
              "cfg7_turbine_trips_fouling", "cfg9_pump_trips_modes", "cfg10_primary_only", "cfg10_primary_only_constant"] + TRIP_SCENARIOS
 
